@@ -1,0 +1,238 @@
+"""
+Reader / flattener for the `.glb` annotation index that te_genome builds.
+
+The index is a pickle of a `te_count.miniglbase.genelist.genelist` whose rows hold a
+`te_count.miniglbase.location.location` (reference: miniglbase/base_genelist.py:302-306 `save`,
+miniglbase/utils.py:21-59 `glload`, te_count.py:31-35 `load_genome`).  This module reads that
+format WITHOUT importing the reference package: a restricted unpickler maps the two class paths
+onto attribute bags, then the rows are flattened to the arrays the CUDA library consumes:
+
+    per feature, in linearData order : chrom_id, L, R, ensg_id, type_code, strand_code
+    per chromosome, sorted by (L, R) : the same columns + offsets          (device layout)
+    names                            : sorted(set(ensg))  == TSV row / column order (te_count.py:35)
+
+The reference's candidate set is the 10 kb bucket hash stored in the pickle
+(`genelist.buckets`, miniglbase/genelist.py:367-380).  The kernels use its closed form
+(L//bs <= b <= R//bs), so `verify_buckets` checks the stored hash against that closed form and the
+load fails loudly if they differ (e.g. an index written with another bucket_size).
+"""
+import io
+import os
+import pickle
+
+import numpy as np
+
+BUCKET_SIZE = 10000                      # miniglbase/config.py:36
+
+T_OTHER, T_GENE, T_TE, T_SNRNA, T_ENH = 0, 1, 2, 3, 4
+_TYPE_CODES = {"protein_coding": T_GENE, "lincRNA": T_GENE, "lncRNA": T_GENE,   # te_count.py:134
+               "TE": T_TE,                                                         # :139
+               "snRNA": T_SNRNA,                                                   # :142
+               "enhancer": T_ENH}                                                  # :145
+STRAND_MISSING = 255
+MAX_ENSG = 1 << 24                       # ensg id field width in the packed device word
+
+
+class _Bag:
+    """Attribute bag standing in for genelist / location instances while unpickling."""
+
+    def __setstate__(self, state):
+        if isinstance(state, dict):
+            self.__dict__.update(state)
+        elif isinstance(state, tuple) and len(state) == 2:       # (dict, slots)
+            for part in state:
+                if part:
+                    self.__dict__.update(part)
+
+
+class _Genelist(_Bag):
+    pass
+
+
+class _Location(_Bag):
+    pass
+
+
+_CLASS_MAP = {
+    ("te_count.miniglbase.genelist", "genelist"): _Genelist,
+    ("te_count.miniglbase.location", "location"): _Location,
+    # the same classes when the index was written by a stand-alone glbase3 / miniglbase
+    ("miniglbase.genelist", "genelist"): _Genelist,
+    ("miniglbase.location", "location"): _Location,
+    ("glbase3.genelist", "genelist"): _Genelist,
+    ("glbase3.location", "location"): _Location,
+}
+_SAFE_BUILTINS = {"set", "frozenset", "list", "dict", "tuple", "int", "float", "str", "bool",
+                  "bytes", "complex", "slice", "range"}
+
+
+class _GlbUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if (module, name) in _CLASS_MAP:
+            return _CLASS_MAP[(module, name)]
+        if module == "builtins" and name in _SAFE_BUILTINS:
+            return getattr(__import__("builtins"), name)
+        if module == "collections" and name in ("OrderedDict", "defaultdict"):
+            import collections
+            return getattr(collections, name)
+        raise pickle.UnpicklingError("refusing to unpickle %s.%s from a .glb index" % (module, name))
+
+
+class GlbIndex:
+    """Flattened index.  Attributes (numpy, linearData order):
+    chrom_id i32, L i32, R i32, ensg_id i32, type_code u8, strand_code u8;
+    names (sorted unique ensg), chrom_keys (normalised chromosome strings, id order),
+    strand_strings (code -> string)."""
+
+    def __init__(self, chrom_keys, chrom_id, L, R, ensg_id, type_code, strand_code, names,
+                 strand_strings=("+", "-"), bucket_size=BUCKET_SIZE, type_strings=None):
+        self.chrom_keys = list(chrom_keys)
+        self.chrom_lookup = {k: i for i, k in enumerate(self.chrom_keys)}
+        self.chrom_id = np.ascontiguousarray(chrom_id, dtype=np.int32)
+        self.L = np.ascontiguousarray(L, dtype=np.int32)
+        self.R = np.ascontiguousarray(R, dtype=np.int32)
+        self.ensg_id = np.ascontiguousarray(ensg_id, dtype=np.int32)
+        self.type_code = np.ascontiguousarray(type_code, dtype=np.uint8)
+        self.strand_code = np.ascontiguousarray(strand_code, dtype=np.uint8)
+        self.names = list(names)
+        self.strand_strings = list(strand_strings)
+        self.bucket_size = int(bucket_size)
+        self.type_strings = type_strings
+        n = len(self.L)
+        assert all(len(a) == n for a in (self.chrom_id, self.R, self.ensg_id, self.type_code,
+                                         self.strand_code))
+        if len(self.names) > MAX_ENSG:
+            raise ValueError("index has %d distinct ensg names; the device word holds %d"
+                             % (len(self.names), MAX_ENSG))
+        self._sorted = None
+
+    @property
+    def n_features(self):
+        return len(self.L)
+
+    @property
+    def n_ensg(self):
+        return len(self.names)
+
+    @property
+    def n_chrom(self):
+        return len(self.chrom_keys)
+
+    def sorted_layout(self):
+        """Device layout: features grouped by chromosome id and sorted by (L, R, original index).
+        Returns dict(chrom_off i64[n_chrom+1], L, R, ensg_id, type_code, strand_code, order)."""
+        if self._sorted is None:
+            n = self.n_features
+            order = np.lexsort((np.arange(n), self.R, self.L, self.chrom_id))
+            cid = self.chrom_id[order]
+            off = np.zeros(self.n_chrom + 1, dtype=np.int64)
+            if n:
+                off[1:] = np.cumsum(np.bincount(cid, minlength=self.n_chrom))
+            self._sorted = {
+                "chrom_off": off,
+                "L": np.ascontiguousarray(self.L[order]),
+                "R": np.ascontiguousarray(self.R[order]),
+                "ensg_id": np.ascontiguousarray(self.ensg_id[order]),
+                "type_code": np.ascontiguousarray(self.type_code[order]),
+                "strand_code": np.ascontiguousarray(self.strand_code[order]),
+                "order": order,
+            }
+        return self._sorted
+
+
+def _read_pickle(path):
+    with open(os.path.realpath(path), "rb") as fh:
+        return _GlbUnpickler(io.BufferedReader(fh)).load()
+
+
+def verify_buckets(gl_buckets, chrom_str, L, R, bs=BUCKET_SIZE):
+    """Check the pickled bucket hash == {b*bs: [n : L[n]//bs <= b <= R[n]//bs]} per chromosome
+    (miniglbase/genelist.py:367-380).  Raises ValueError when it is anything else."""
+    n = len(L)
+    L = np.asarray(L, dtype=np.int64)
+    R = np.asarray(R, dtype=np.int64)
+    expected_total = int(np.sum(R // bs - L // bs + 1)) if n else 0
+    total = 0
+    for chrom, bdict in gl_buckets.items():
+        for b, ids in bdict.items():
+            ids = np.asarray(ids, dtype=np.int64)
+            total += len(ids)
+            if len(ids) == 0:
+                continue
+            if len(np.unique(ids)) != len(ids) or ids.min() < 0 or ids.max() >= n:
+                raise ValueError("bucket %s:%s holds duplicate or out-of-range feature ids" % (chrom, b))
+            ok = ((L[ids] // bs) * bs <= b) & (b <= (R[ids] // bs) * bs)
+            if not ok.all() or (b % bs) != 0:
+                raise ValueError("bucket %s:%s is not the 10 kb bucket hash of its features" % (chrom, b))
+            for i in ids[:1]:
+                if chrom_str[int(i)] != chrom:
+                    raise ValueError("bucket chromosome key %r does not match its features" % (chrom,))
+    if total != expected_total:
+        raise ValueError("bucket hash has %d entries, closed form expects %d (bucket_size mismatch?)"
+                         % (total, expected_total))
+
+
+def from_rows(rows, buckets=None, verify=True):
+    """rows: iterable of dicts with keys loc (chr/left/right mapping), type, ensg [, strand].
+    Mirrors what load_genome() exposes: all_feature_names = sorted(set(ensg)) (te_count.py:35) and
+    chromosome keys = the keys of genelist.buckets (first-appearance order of loc['chr'])."""
+    chrom_keys, chrom_lookup = [], {}
+    strand_strings, strand_lookup = ["+", "-"], {"+": 0, "-": 1}
+    n = len(rows)
+    chrom_id = np.empty(n, np.int32)
+    L = np.empty(n, np.int32)
+    R = np.empty(n, np.int32)
+    type_code = np.empty(n, np.uint8)
+    strand_code = np.empty(n, np.uint8)
+    ensg = [None] * n
+    chrom_str = [None] * n
+    for i, row in enumerate(rows):
+        if "tss_loc" in row:
+            raise ValueError("index rows carry 'tss_loc'; the reference would bucket on it "
+                             "(miniglbase/genelist.py:345) -- unsupported")
+        loc = row["loc"]
+        loc = loc.loc if hasattr(loc, "loc") else loc
+        c = loc["chr"]
+        cid = chrom_lookup.get(c)
+        if cid is None:
+            cid = chrom_lookup[c] = len(chrom_keys)
+            chrom_keys.append(c)
+        chrom_id[i] = cid
+        chrom_str[i] = c
+        L[i] = loc["left"]
+        R[i] = loc["right"]
+        type_code[i] = _TYPE_CODES.get(row["type"], T_OTHER)
+        if "strand" in row:
+            s = row["strand"]
+            sc = strand_lookup.get(s)
+            if sc is None:
+                if len(strand_strings) >= 4:
+                    raise ValueError("more than 4 distinct strand strings in the index")
+                sc = strand_lookup[s] = len(strand_strings)
+                strand_strings.append(s)
+            strand_code[i] = sc
+        else:
+            strand_code[i] = STRAND_MISSING
+        ensg[i] = row["ensg"]
+    names = sorted(set(ensg))
+    name_id = {k: i for i, k in enumerate(names)}
+    ensg_id = np.fromiter((name_id[e] for e in ensg), dtype=np.int32, count=n)
+    if buckets is not None and verify:
+        verify_buckets(buckets, chrom_str, L, R)
+        if list(buckets.keys()) != chrom_keys:
+            raise ValueError("bucket chromosome keys differ from the feature rows")
+    return GlbIndex(chrom_keys, chrom_id, L, R, ensg_id, type_code, strand_code, names, strand_strings)
+
+
+def load_glb(path, verify=True):
+    """Equivalent of miniglbase.glload (utils.py:21-59) + the flattening above."""
+    assert os.path.exists(os.path.realpath(path)), "File '%s' not found" % path
+    gl = _read_pickle(path)
+    rows = getattr(gl, "linearData", None)
+    if rows is None:
+        raise ValueError("%s is not a glbase genelist pickle (no linearData)" % path)
+    buckets = getattr(gl, "buckets", None)
+    if buckets is None:
+        # utils.py:52-54: old lists are re-bucketed at load with the same closed form
+        verify = False
+    return from_rows(rows, buckets=buckets, verify=verify)
