@@ -1,0 +1,173 @@
+/*
+ * tecount.h -- C ABI of libtecount.so, the B200 (sm_100a) counting engine behind te_count.
+ *
+ * The reference (oaxiom/te_counter) is pure Python and has no FFI; the seam this library sits
+ * behind is the `measureTE` method set (reference te_count/te_count.py:14-754) called from
+ * bin/te_count:77-120.  Each entry point below names the reference lines whose work it takes
+ * over.  Python binds it with ctypes (te_counter_b200/_lib.py); INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every call returns 0 (TEC_OK) or a negative tec_status; nothing throws across the ABI;
+ *     tec_last_error(ctx) gives the text of the last failure on that context.
+ *   - plain pointers and sizes only.  The caller owns every host buffer.  The library owns all
+ *     device memory inside the context, except where a parameter is documented as a device
+ *     pointer (`*_dev` entry points), which the caller (e.g. a torch tensor) owns.
+ *   - one context per GPU; a context is not thread-safe.  Work is enqueued on the context's
+ *     stream; calls that return results to host memory synchronise before returning.
+ *   - there is no CPU fallback: tec_create fails when no CUDA device is usable.
+ *
+ * Record layout (structure of arrays, one element per alignment record):
+ *   int32  start   pysam reference_start (0-based)
+ *   int32  end     pysam reference_end   (exclusive)
+ *   uint16 chrom   index chromosome id (< n_chrom of tec_index_upload); any other value means
+ *                  "not in the index"; 0xFFFE = name contains '_' or 'alt' (single-cell skip)
+ *   uint8  mapq
+ *   uint8  flag    bit0 unmapped(0x4) bit1 duplicate(0x400) bit2 qcfail(0x200) bit3 reverse(0x10)
+ *                  bit4 paired-end query-name mismatch (te_count.py:92)
+ *   uint32 cell    [single cell] id of the barcode in the sorted whitelist, 0xFFFFFFFF = not in it
+ *   uint64 umi     [single cell] order-preserving code of the UMI string
+ */
+#ifndef TECOUNT_H
+#define TECOUNT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEC_ABI_VERSION 1
+
+typedef struct tec_ctx tec_ctx;
+
+typedef enum tec_status {
+    TEC_OK = 0,
+    TEC_ERR_CUDA = -1,          /* a CUDA runtime call failed (text in tec_last_error) */
+    TEC_ERR_ARG = -2,           /* bad argument */
+    TEC_ERR_STATE = -3,         /* call out of order (no index, no begin, ...) */
+    TEC_ERR_NOMEM = -4,         /* device or host allocation failed */
+    TEC_ERR_LIMIT = -5,         /* input exceeds a documented limit (key width, record count) */
+    TEC_ERR_UNIMPLEMENTED = -6
+} tec_status;
+
+/* feature type codes: which branch of te_count.py:134-146 / :662-682 a feature can trigger */
+#define TEC_T_OTHER 0
+#define TEC_T_GENE 1            /* protein_coding, lincRNA, lncRNA */
+#define TEC_T_TE 2
+#define TEC_T_SNRNA 3
+#define TEC_T_ENHANCER 4
+#define TEC_STRAND_MISSING 255  /* feature row has no 'strand' key */
+
+#define TEC_F_UNMAPPED 1
+#define TEC_F_DUP 2
+#define TEC_F_QCFAIL 4
+#define TEC_F_REVERSE 8
+#define TEC_F_NAME_MISMATCH 16
+#define TEC_CHROM_SC_SKIP 0xFFFE
+#define TEC_CELL_INVALID 0xFFFFFFFFu
+
+/* bulk statistics block, int64[TEC_BULK_NSTATS]  (te_count.py:158-163, :269-275) */
+#define TEC_BULK_NSTATS 8
+#define TEC_BS_UNITS 0          /* records (SE) or pairs (PE) consumed; total_reads = this + 1 */
+#define TEC_BS_ASSIGNED 1       /* "Reads were assigned to a gene" */
+#define TEC_BS_LOWQ 2           /* "Read quality is too low" */
+#define TEC_BS_BADCHROM 3       /* "Reads mapped to an invalid chromosome" */
+#define TEC_BS_QCFAIL 4         /* "Reads are QC fails" */
+#define TEC_BS_CRASH_ENHANCER 5 /* units at which the reference raises NameError (te_count.py:147) */
+#define TEC_BS_CRASH_NAME 6     /* units at which the reference dies in sys.quit (te_count.py:94) */
+
+/* single-cell statistics block, int64[TEC_SC_NSTATS]  (te_count.py:696-705) */
+#define TEC_SC_NSTATS 16
+#define TEC_SS_UNITS 0          /* records consumed; total_reads = this + 1 */
+#define TEC_SS_INVALID_BARCODE 1
+#define TEC_SS_ALREADY_SEEN 2
+#define TEC_SS_LOWQ 3
+#define TEC_SS_QCFAIL 4
+#define TEC_SS_VALID 5          /* lines kept by Part 2 ("total valid reads") */
+#define TEC_SS_ASSIGNED 6       /* "Assigned N of total valid reads to features" */
+#define TEC_SS_RAW_BARCODES 7   /* "Observed N raw barcodes" */
+#define TEC_SS_BUNDLES 8        /* spill bundles the reference would have written */
+#define TEC_SS_CRASH_STRAND 9   /* fragments at which the reference raises KeyError 'strand' (:661) */
+#define TEC_SS_SURVIVORS 10     /* records that reached the UMI table */
+#define TEC_SS_SEGMENTS 11      /* (cell, UMI, bundle) lines over all bundles */
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int tec_abi_version(void);
+const char* tec_strerror(int status);
+/* device: CUDA ordinal.  Replaces measureTE.__init__ state (te_count.py:15-29). */
+int tec_create(int device, tec_ctx** out);
+void tec_destroy(tec_ctx* ctx);
+const char* tec_last_error(const tec_ctx* ctx);
+int tec_sync(tec_ctx* ctx);
+/* pinned host memory for the SoA batches (optional; any host memory is accepted) */
+int tec_host_alloc(tec_ctx* ctx, uint64_t bytes, void** out);
+int tec_host_free(tec_ctx* ctx, void* p);
+/* the CUDA stream of the context as a cudaStream_t value (for event timing by the caller) */
+void* tec_stream(tec_ctx* ctx);
+/* elapsed GPU milliseconds of the kernels of the last bulk push / sc finalize on this context */
+float tec_last_kernel_ms(tec_ctx* ctx);
+/* number of kernel launches issued by this context since creation */
+int64_t tec_launch_count(const tec_ctx* ctx);
+
+/* ---- index ------------------------------------------------------------------------------
+ * Replaces load_genome() + the structures of genelist._optimiseData that the read loops reach
+ * into (te_count.py:31-35, :68-73, :586-590; miniglbase/genelist.py:332-396).
+ * Features are grouped by chromosome id and sorted by (L, R) inside each chromosome:
+ *   chrom_off[n_chrom + 1]  offsets into the feature arrays
+ *   L, R                    loc['left'], loc['right']
+ *   ensg_id                 index into sorted(set(ensg))  (== output row / column order)
+ *   type_code               TEC_T_*;  strand_code 0 '+', 1 '-', 2..3 other strings, 255 missing
+ *   bucket_size             miniglbase/config.py:36 (10000)
+ */
+int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* chrom_off,
+                     const int32_t* L, const int32_t* R, const int32_t* ensg_id,
+                     const uint8_t* type_code, const uint8_t* strand_code,
+                     int32_t n_ensg, int32_t bucket_size);
+
+/* ---- bulk (parse_bamse te_count.py:167-277, parse_bampe te_count.py:42-165) ---------------
+ * begin: zero the per-feature counters and statistics.  paired != 0 consumes records two at a
+ * time (record 2i = read1, 2i+1 = read2); every push must then hold an even number of records.
+ * push: filter + mate merge + point overlap + type rule + tally for one batch, host buffers.
+ * push_dev: the same with DEVICE pointers, asynchronous on the context stream.
+ * finish: counts[n_ensg] and stats[TEC_BULK_NSTATS] to host (either may be NULL).
+ */
+int tec_bulk_begin(tec_ctx* ctx, int paired, int qual);
+int tec_bulk_push(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
+                  const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag);
+int tec_bulk_push_dev(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
+                      const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag);
+int tec_bulk_finish(tec_ctx* ctx, int64_t* counts, int64_t* stats);
+/* device address of the int64 counters [n_ensg] followed by stats [TEC_BULK_NSTATS]; lets the
+ * caller run the cross-GPU reduction (NCCL) on the library's buffer without a host round trip */
+void* tec_bulk_counts_dev(tec_ctx* ctx);
+/* multi-GPU: peer-mapped addresses of every rank's counter block (this rank's own included).
+ * When set, the tally kernel's flush adds its per-CTA partial counts directly into ALL ranks'
+ * blocks over NVLink, so the merge is part of the kernel and no collective follows. */
+int tec_bulk_set_peers(tec_ctx* ctx, int n_peers, void* const* peer_counts);
+
+/* ---- single cell (sc_parse_bamse te_count.py:298-707, sc_save_result :709-754) ------------ */
+int tec_sc_begin(tec_ctx* ctx, int qual, int strand, int64_t n_whitelist);
+int tec_sc_push(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
+                const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag,
+                const uint32_t* cell, const uint64_t* umi);
+int tec_sc_push_dev(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
+                    const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag,
+                    const uint32_t* cell, const uint64_t* umi);
+/* Parts 1-3: bundle_keys is the 1e7 of te_count.py:377, pad the +1000 of :502.
+ * Returns the sizes of the two result lists. */
+int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcells, int64_t pad,
+                    int64_t* n_triples, int64_t* n_hit_cells);
+/* triples sorted by (ensg, cell): final_results[ensg][barcode] = count (te_count.py:668-682);
+ * hit cells ascending by cell id: self.barcodes after Part 3 (te_count.py:653-655);
+ * stats[TEC_SC_NSTATS].  Any pointer may be NULL. */
+int tec_sc_fetch(tec_ctx* ctx, int32_t* ensg, uint32_t* cell, int64_t* count,
+                 uint32_t* hit_cell, int64_t* hit_count, int64_t* stats);
+/* sc_save_result's choice of rows (te_count.py:724-733): hit cells by count descending, ties by
+ * ascending id, at most maxcells.  cells_out must hold min(maxcells, n_hit_cells) entries. */
+int tec_sc_select(tec_ctx* ctx, int64_t maxcells, uint32_t* cells_out, int64_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TECOUNT_H */

@@ -1,0 +1,226 @@
+"""
+ctypes binding of libtecount.so (include/tecount.h).  There is no CPU fallback: importing the
+engine without the built CUDA library, or creating it without a usable GPU, raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtecount.so")
+
+BULK_NSTATS = 8
+BS_UNITS, BS_ASSIGNED, BS_LOWQ, BS_BADCHROM, BS_QCFAIL, BS_CRASH_ENHANCER, BS_CRASH_NAME = range(7)
+SC_NSTATS = 16
+(SS_UNITS, SS_INVALID_BARCODE, SS_ALREADY_SEEN, SS_LOWQ, SS_QCFAIL, SS_VALID, SS_ASSIGNED,
+ SS_RAW_BARCODES, SS_BUNDLES, SS_CRASH_STRAND, SS_SURVIVORS, SS_SEGMENTS) = range(12)
+
+_c_i32p = ctypes.POINTER(ctypes.c_int32)
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+_c_u8p = ctypes.POINTER(ctypes.c_uint8)
+_c_u16p = ctypes.POINTER(ctypes.c_uint16)
+_c_u32p = ctypes.POINTER(ctypes.c_uint32)
+_c_u64p = ctypes.POINTER(ctypes.c_uint64)
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); tests check that every symbol of include/tecount.h is listed and exported
+SIGNATURES = {
+    "tec_abi_version": (ctypes.c_int, []),
+    "tec_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "tec_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "tec_destroy": (None, [_vp]),
+    "tec_last_error": (ctypes.c_char_p, [_vp]),
+    "tec_sync": (ctypes.c_int, [_vp]),
+    "tec_host_alloc": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.POINTER(_vp)]),
+    "tec_host_free": (ctypes.c_int, [_vp, _vp]),
+    "tec_stream": (_vp, [_vp]),
+    "tec_last_kernel_ms": (ctypes.c_float, [_vp]),
+    "tec_launch_count": (ctypes.c_int64, [_vp]),
+    "tec_index_upload": (ctypes.c_int, [_vp, ctypes.c_int32, _c_i64p, _c_i32p, _c_i32p, _c_i32p, _c_u8p,
+                                        _c_u8p, ctypes.c_int32, ctypes.c_int32]),
+    "tec_bulk_begin": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    "tec_bulk_push": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "tec_bulk_push_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "tec_bulk_finish": (ctypes.c_int, [_vp, _c_i64p, _c_i64p]),
+    "tec_bulk_counts_dev": (_vp, [_vp]),
+    "tec_bulk_set_peers": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "tec_sc_begin": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64]),
+    "tec_sc_push": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tec_sc_push_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tec_sc_finalize": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_i64p, _c_i64p]),
+    "tec_sc_fetch": (ctypes.c_int, [_vp, _c_i32p, _c_u32p, _c_i64p, _c_u32p, _c_i64p, _c_i64p]),
+    "tec_sc_select": (ctypes.c_int, [_vp, ctypes.c_int64, _c_u32p, _c_i64p]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libtecount.so and attach the prototypes.  Raises ImportError when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libtecount.so is not built (%s); run `python -m te_counter_b200.build` "
+                              "-- there is no CPU fallback" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class TecError(RuntimeError):
+    def __init__(self, status, text):
+        RuntimeError.__init__(self, "libtecount: %s (status %d)" % (text, status))
+        self.status = status
+
+
+def _ptr(a, dtype):
+    if a is None:
+        return None
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags.c_contiguous:
+        raise TypeError("expected a C-contiguous numpy array of %s" % np.dtype(dtype).name)
+    return a.ctypes.data
+
+
+class Engine:
+    """One CUDA context of libtecount on one GPU."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = _vp()
+        rc = self._lib.tec_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise TecError(rc, "tec_create(device=%d) failed: %s -- a CUDA GPU is required, there is no "
+                               "CPU fallback" % (device, self._lib.tec_strerror(rc).decode()))
+        self._h = h
+        self.device = device
+        self.n_ensg = 0
+        self._pinned = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for p in self._pinned:
+                self._lib.tec_host_free(self._h, p)
+            self._pinned = []
+            self._lib.tec_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise TecError(rc, (self._lib.tec_last_error(self._h) or b"").decode() or
+                           self._lib.tec_strerror(rc).decode())
+
+    # -- memory / timing
+    def pinned(self, n, dtype):
+        """numpy array of n elements backed by cudaHostAlloc memory (lives as long as the engine)."""
+        dt = np.dtype(dtype)
+        p = _vp()
+        self._check(self._lib.tec_host_alloc(self._h, max(1, n) * dt.itemsize, ctypes.byref(p)))
+        self._pinned.append(p)
+        buf = (ctypes.c_char * (max(1, n) * dt.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=n)
+
+    def sync(self):
+        self._check(self._lib.tec_sync(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.tec_stream(self._h)
+
+    def last_kernel_ms(self):
+        return float(self._lib.tec_last_kernel_ms(self._h))
+
+    def launch_count(self):
+        return int(self._lib.tec_launch_count(self._h))
+
+    # -- index
+    def upload_index(self, idx):
+        """idx: te_counter_b200.index.GlbIndex"""
+        s = idx.sorted_layout()
+        self.upload_index_arrays(idx.n_chrom, s["chrom_off"], s["L"], s["R"], s["ensg_id"], s["type_code"],
+                                 s["strand_code"], idx.n_ensg, idx.bucket_size)
+
+    def upload_index_arrays(self, n_chrom, chrom_off, L, R, ensg_id, type_code, strand_code, n_ensg, bucket_size):
+        f = self._lib.tec_index_upload
+        self._check(f(self._h, int(n_chrom),
+                      ctypes.cast(_ptr(chrom_off, np.int64), _c_i64p), ctypes.cast(_ptr(L, np.int32), _c_i32p),
+                      ctypes.cast(_ptr(R, np.int32), _c_i32p), ctypes.cast(_ptr(ensg_id, np.int32), _c_i32p),
+                      ctypes.cast(_ptr(type_code, np.uint8), _c_u8p), ctypes.cast(_ptr(strand_code, np.uint8), _c_u8p),
+                      int(n_ensg), int(bucket_size)))
+        self.n_ensg = int(n_ensg)
+
+    # -- bulk
+    def bulk_begin(self, paired, qual):
+        self._check(self._lib.tec_bulk_begin(self._h, 1 if paired else 0, int(qual)))
+
+    def bulk_push(self, n, start, end, chrom, mapq, flag):
+        self._check(self._lib.tec_bulk_push(self._h, int(n), _ptr(start, np.int32), _ptr(end, np.int32),
+                                            _ptr(chrom, np.uint16), _ptr(mapq, np.uint8), _ptr(flag, np.uint8)))
+
+    def bulk_push_dev(self, n, start, end, chrom, mapq, flag):
+        """device pointers (ints), asynchronous"""
+        self._check(self._lib.tec_bulk_push_dev(self._h, int(n), start, end, chrom, mapq, flag))
+
+    def bulk_finish(self):
+        counts = np.zeros(self.n_ensg, dtype=np.int64)
+        stats = np.zeros(BULK_NSTATS, dtype=np.int64)
+        self._check(self._lib.tec_bulk_finish(self._h, ctypes.cast(counts.ctypes.data, _c_i64p),
+                                              ctypes.cast(stats.ctypes.data, _c_i64p)))
+        return counts, stats
+
+    def bulk_counts_dev(self):
+        return self._lib.tec_bulk_counts_dev(self._h)
+
+    def bulk_set_peers(self, ptrs):
+        arr = (_vp * len(ptrs))(*ptrs)
+        self._check(self._lib.tec_bulk_set_peers(self._h, len(ptrs), arr))
+
+    # -- single cell
+    def sc_begin(self, qual, strand, n_whitelist):
+        self._check(self._lib.tec_sc_begin(self._h, int(qual), 1 if strand else 0, int(n_whitelist)))
+
+    def sc_push(self, n, start, end, chrom, mapq, flag, cell, umi):
+        self._check(self._lib.tec_sc_push(self._h, int(n), _ptr(start, np.int32), _ptr(end, np.int32),
+                                          _ptr(chrom, np.uint16), _ptr(mapq, np.uint8), _ptr(flag, np.uint8),
+                                          _ptr(cell, np.uint32), _ptr(umi, np.uint64)))
+
+    def sc_push_dev(self, n, start, end, chrom, mapq, flag, cell, umi):
+        self._check(self._lib.tec_sc_push_dev(self._h, int(n), start, end, chrom, mapq, flag, cell, umi))
+
+    def sc_finalize(self, bundle_keys, maxcells, pad):
+        nt, nh = ctypes.c_int64(0), ctypes.c_int64(0)
+        self._check(self._lib.tec_sc_finalize(self._h, int(bundle_keys), int(maxcells), int(pad),
+                                              ctypes.byref(nt), ctypes.byref(nh)))
+        return nt.value, nh.value
+
+    def sc_fetch(self, n_triples, n_hit_cells):
+        ensg = np.zeros(n_triples, dtype=np.int32)
+        cell = np.zeros(n_triples, dtype=np.uint32)
+        count = np.zeros(n_triples, dtype=np.int64)
+        hcell = np.zeros(n_hit_cells, dtype=np.uint32)
+        hcount = np.zeros(n_hit_cells, dtype=np.int64)
+        stats = np.zeros(SC_NSTATS, dtype=np.int64)
+        self._check(self._lib.tec_sc_fetch(self._h, ctypes.cast(ensg.ctypes.data, _c_i32p),
+                                           ctypes.cast(cell.ctypes.data, _c_u32p),
+                                           ctypes.cast(count.ctypes.data, _c_i64p),
+                                           ctypes.cast(hcell.ctypes.data, _c_u32p),
+                                           ctypes.cast(hcount.ctypes.data, _c_i64p),
+                                           ctypes.cast(stats.ctypes.data, _c_i64p)))
+        return ensg, cell, count, hcell, hcount, stats
+
+    def sc_select(self, maxcells, n_hit_cells):
+        out = np.zeros(max(1, min(int(maxcells), int(n_hit_cells))), dtype=np.uint32)
+        n = ctypes.c_int64(0)
+        self._check(self._lib.tec_sc_select(self._h, int(maxcells), ctypes.cast(out.ctypes.data, _c_u32p),
+                                            ctypes.byref(n)))
+        return out[:n.value]

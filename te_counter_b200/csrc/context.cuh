@@ -1,0 +1,119 @@
+// Context object behind the opaque tec_ctx handle.
+#pragma once
+#include "common.cuh"
+
+#define TEC_STAGE_RECORDS (int64_t(16) << 20)     // records per host->device staging chunk
+
+struct DevIndex {
+    int32_t* L = nullptr;
+    int32_t* R = nullptr;
+    int32_t* pmaxR = nullptr;
+    u32* info = nullptr;
+    int64_t* chrom_off = nullptr;
+    u32* dir = nullptr;
+    int64_t* dir_off = nullptr;
+    int n_chrom = 0, n_ensg = 0, bs = 10000, shift = 9;
+    int64_t n_feat = 0, n_dir = 0;
+    IndexView view() const {
+        IndexView v;
+        v.L = L; v.R = R; v.pmaxR = pmaxR; v.info = info; v.chrom_off = chrom_off;
+        v.dir = dir; v.dir_off = dir_off; v.n_chrom = n_chrom; v.shift = shift; v.bs = bs; v.n_ensg = n_ensg;
+        return v;
+    }
+};
+
+struct StageSlot {
+    void* base = nullptr;
+    int32_t* start = nullptr;
+    int32_t* end = nullptr;
+    uint16_t* chrom = nullptr;
+    uint8_t* mapq = nullptr;
+    uint8_t* flag = nullptr;
+    u32* cell = nullptr;
+    u64* umi = nullptr;
+};
+
+struct ScState;      // sc.cuh
+
+struct tec_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int64_t launches = 0;
+    std::string err;
+
+    DevIndex idx;
+    bool has_index = false;
+
+    // bulk
+    bool bulk_active = false;
+    int paired = 0, qual = 20;
+    u64* d_counts = nullptr;              // n_ensg counters + TEC_BULK_NSTATS statistics
+
+    // host staging
+    StageSlot stage[2];
+    int64_t stage_cap = 0;
+    bool stage_sc = false;
+    int stage_next = 0;
+
+    ScState* sc = nullptr;
+
+    int ensure_stage(int64_t n, bool sc_layout);
+    void free_stage();
+    void free_index();
+    void free_sc();
+    void free_all() { free_stage(); free_index(); free_sc(); }
+};
+
+inline void tec_ctx::free_stage() {
+    for (int i = 0; i < 2; ++i) {
+        if (stage[i].base) cudaFree(stage[i].base);
+        stage[i] = StageSlot();
+    }
+    stage_cap = 0;
+}
+
+inline void tec_ctx::free_index() {
+    DevIndex& ix = idx;
+    cudaFree(ix.L); cudaFree(ix.R); cudaFree(ix.pmaxR); cudaFree(ix.info);
+    cudaFree(ix.chrom_off); cudaFree(ix.dir); cudaFree(ix.dir_off);
+    ix = DevIndex();
+    cudaFree(d_counts);
+    d_counts = nullptr;
+    has_index = false;
+    bulk_active = false;
+}
+
+// two staging slots, each one allocation carved into the SoA columns (256-byte aligned)
+inline int tec_ctx::ensure_stage(int64_t n, bool sc_layout) {
+    tec_ctx* ctx = this;
+    if (n <= stage_cap && (stage_sc || !sc_layout)) return TEC_OK;
+    TEC_CUDA(cudaStreamSynchronize(stream));
+    TEC_CUDA(cudaStreamSynchronize(copy_stream));
+    free_stage();
+    const int64_t cap = std::max<int64_t>(n, 1 << 16);
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t o_start = 0, o_end = o_start + al((size_t)cap * 4), o_chrom = o_end + al((size_t)cap * 4),
+                 o_mapq = o_chrom + al((size_t)cap * 2), o_flag = o_mapq + al((size_t)cap),
+                 o_cell = o_flag + al((size_t)cap), o_umi = o_cell + (sc_layout ? al((size_t)cap * 4) : 0),
+                 total = o_umi + (sc_layout ? al((size_t)cap * 8) : 0);
+    for (int i = 0; i < 2; ++i) {
+        TEC_CUDA(cudaMalloc(&stage[i].base, total));
+        char* b = (char*)stage[i].base;
+        stage[i].start = (int32_t*)(b + o_start);
+        stage[i].end = (int32_t*)(b + o_end);
+        stage[i].chrom = (uint16_t*)(b + o_chrom);
+        stage[i].mapq = (uint8_t*)(b + o_mapq);
+        stage[i].flag = (uint8_t*)(b + o_flag);
+        stage[i].cell = sc_layout ? (u32*)(b + o_cell) : nullptr;
+        stage[i].umi = sc_layout ? (u64*)(b + o_umi) : nullptr;
+    }
+    stage_cap = cap;
+    stage_sc = sc_layout;
+    // mark both slots free
+    for (int i = 0; i < 2; ++i) TEC_CUDA(cudaEventRecord(stage_free[i], stream));
+    return TEC_OK;
+}

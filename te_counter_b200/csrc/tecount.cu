@@ -1,0 +1,295 @@
+// libtecount.so -- C ABI implementation (see include/tecount.h).  sm_100a only, no CPU fallback.
+#include "common.cuh"
+#include "bulk.cuh"
+#include "context.cuh"
+#include "sc.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+// ------------------------------------------------------------------------------------ misc
+extern "C" int tec_abi_version(void) { return TEC_ABI_VERSION; }
+
+extern "C" const char* tec_strerror(int s) {
+    switch (s) {
+        case TEC_OK: return "ok";
+        case TEC_ERR_CUDA: return "CUDA runtime error";
+        case TEC_ERR_ARG: return "bad argument";
+        case TEC_ERR_STATE: return "call out of order";
+        case TEC_ERR_NOMEM: return "out of memory";
+        case TEC_ERR_LIMIT: return "input exceeds a documented limit";
+        case TEC_ERR_UNIMPLEMENTED: return "not implemented";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int tec_create(int device, tec_ctx** out) {
+    if (!out) return TEC_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return TEC_ERR_CUDA;   // no CPU fallback
+    if (device < 0 || device >= n) return TEC_ERR_ARG;
+    tec_ctx* ctx = new tec_ctx();
+    ctx->device = device;
+    auto fail = [&](int code) { tec_destroy(ctx); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(TEC_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(TEC_ERR_CUDA);
+    ctx->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TEC_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TEC_ERR_CUDA);
+    for (int i = 0; i < 2; ++i) {
+        if (cudaEventCreateWithFlags(&ctx->stage_ready[i], cudaEventDisableTiming) != cudaSuccess) return fail(TEC_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming) != cudaSuccess) return fail(TEC_ERR_CUDA);
+    }
+    if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return fail(TEC_ERR_CUDA);
+    *out = ctx;
+    return TEC_OK;
+}
+
+extern "C" void tec_destroy(tec_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    ctx->free_all();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage_ready[i]) cudaEventDestroy(ctx->stage_ready[i]);
+        if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]);
+    }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+extern "C" const char* tec_last_error(const tec_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int tec_sync(tec_ctx* ctx) {
+    if (!ctx) return TEC_ERR_ARG;
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    TEC_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TEC_OK;
+}
+
+extern "C" int tec_host_alloc(tec_ctx* ctx, uint64_t bytes, void** out) {
+    if (!ctx || !out) return TEC_ERR_ARG;
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    TEC_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return TEC_OK;
+}
+
+extern "C" int tec_host_free(tec_ctx* ctx, void* p) {
+    if (!ctx) return TEC_ERR_ARG;
+    TEC_CUDA(cudaFreeHost(p));
+    return TEC_OK;
+}
+
+extern "C" void* tec_stream(tec_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" float tec_last_kernel_ms(tec_ctx* ctx) {
+    if (!ctx || !ctx->timed) return -1.f;
+    float ms = -1.f;
+    cudaSetDevice(ctx->device);
+    if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+extern "C" int64_t tec_launch_count(const tec_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------ index
+__global__ void build_dir_kernel(const int32_t* __restrict__ L, const int64_t* __restrict__ chrom_off,
+                                 const int64_t* __restrict__ dir_off, int n_chrom, int shift,
+                                 u32* __restrict__ dir, int64_t n_dir) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dir;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int c = 0;                                   // few chromosomes: linear scan of offsets
+        while (c + 1 < n_chrom && dir_off[c + 1] <= i) ++c;
+        const int64_t lo = chrom_off[c];
+        const int64_t n = chrom_off[c + 1] - lo;
+        const int64_t key = (i - dir_off[c]) << shift;           // first coordinate of the cell
+        int64_t a = 0, b = n;                                    // #features with L < key
+        while (a < b) {
+            int64_t m = (a + b) >> 1;
+            if ((int64_t)L[lo + m] < key) a = m + 1; else b = m;
+        }
+        dir[i] = (u32)a;
+    }
+}
+
+extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* chrom_off,
+                                const int32_t* L, const int32_t* R, const int32_t* ensg_id,
+                                const uint8_t* type_code, const uint8_t* strand_code,
+                                int32_t n_ensg, int32_t bucket_size) {
+    if (!ctx) return TEC_ERR_ARG;
+    if (n_chrom < 0 || n_chrom >= 0xFFF0 || !chrom_off || n_ensg < 0 || n_ensg > (1 << TEC_ENSG_BITS) || bucket_size <= 0)
+        TEC_FAIL(TEC_ERR_ARG, "tec_index_upload: bad sizes");
+    const int64_t nf = chrom_off[n_chrom];
+    if (chrom_off[0] != 0 || nf < 0 || (nf > 0 && (!L || !R || !ensg_id || !type_code || !strand_code)))
+        TEC_FAIL(TEC_ERR_ARG, "tec_index_upload: bad arrays");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->free_index();
+    DevIndex& ix = ctx->idx;
+    const int shift = 9;                            // 512 bp directory cells
+    std::vector<int32_t> pmax((size_t)nf);
+    std::vector<u32> info((size_t)nf);
+    std::vector<int64_t> dir_off((size_t)n_chrom + 1, 0);
+    for (int c = 0; c < n_chrom; ++c) {
+        const int64_t lo = chrom_off[c], hi = chrom_off[c + 1];
+        if (hi < lo) TEC_FAIL(TEC_ERR_ARG, "tec_index_upload: chrom_off not monotone");
+        if (hi - lo >= (int64_t)0x7FFFFFFF) TEC_FAIL(TEC_ERR_LIMIT, "tec_index_upload: chromosome with >= 2^31 features");
+        int32_t run = INT32_MIN, maxL = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            if (L[i] < 0) TEC_FAIL(TEC_ERR_ARG, "tec_index_upload: negative feature start");
+            if (R[i] > 0x7FFFFFF0) TEC_FAIL(TEC_ERR_ARG, "tec_index_upload: feature end too large");
+            if (i > lo && L[i] < L[i - 1]) TEC_FAIL(TEC_ERR_ARG, "tec_index_upload: features not sorted by start within a chromosome");
+            if (ensg_id[i] < 0 || ensg_id[i] >= n_ensg) TEC_FAIL(TEC_ERR_ARG, "tec_index_upload: ensg id out of range");
+            if (type_code[i] > 7) TEC_FAIL(TEC_ERR_ARG, "tec_index_upload: type code out of range");
+            run = std::max(run, R[i]);
+            pmax[(size_t)i] = run;
+            maxL = std::max(maxL, L[i]);
+            info[(size_t)i] = info_pack((u32)ensg_id[i], type_code[i], strand_code[i]);
+        }
+        dir_off[(size_t)c + 1] = dir_off[(size_t)c] + ((int64_t)(maxL >> shift) + 2);
+    }
+    const int64_t n_dir = dir_off[(size_t)n_chrom];
+    ix.n_chrom = n_chrom; ix.n_feat = nf; ix.n_ensg = n_ensg; ix.bs = bucket_size; ix.shift = shift; ix.n_dir = n_dir;
+    const size_t nfa = (size_t)std::max<int64_t>(nf, 1);
+    TEC_CUDA(cudaMalloc(&ix.L, nfa * 4));
+    TEC_CUDA(cudaMalloc(&ix.R, nfa * 4));
+    TEC_CUDA(cudaMalloc(&ix.pmaxR, nfa * 4));
+    TEC_CUDA(cudaMalloc(&ix.info, nfa * 4));
+    TEC_CUDA(cudaMalloc(&ix.chrom_off, ((size_t)n_chrom + 1) * 8));
+    TEC_CUDA(cudaMalloc(&ix.dir_off, ((size_t)n_chrom + 1) * 8));
+    TEC_CUDA(cudaMalloc(&ix.dir, (size_t)std::max<int64_t>(n_dir, 1) * 4));
+    if (nf) {
+        TEC_CUDA(cudaMemcpyAsync(ix.L, L, nfa * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TEC_CUDA(cudaMemcpyAsync(ix.R, R, nfa * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TEC_CUDA(cudaMemcpyAsync(ix.pmaxR, pmax.data(), nfa * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TEC_CUDA(cudaMemcpyAsync(ix.info, info.data(), nfa * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TEC_CUDA(cudaMemcpyAsync(ix.chrom_off, chrom_off, ((size_t)n_chrom + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TEC_CUDA(cudaMemcpyAsync(ix.dir_off, dir_off.data(), ((size_t)n_chrom + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_dir) {
+        const int blocks = (int)std::min<int64_t>((n_dir + 255) / 256, (int64_t)ctx->n_sm * 16);
+        build_dir_kernel<<<blocks, 256, 0, ctx->stream>>>(ix.L, ix.chrom_off, ix.dir_off, n_chrom, shift, ix.dir, n_dir);
+        ctx->launches++;
+        TEC_CUDA(cudaGetLastError());
+    }
+    // per-feature counters + statistics block
+    TEC_CUDA(cudaMalloc(&ctx->d_counts, ((size_t)n_ensg + TEC_BULK_NSTATS) * 8));
+    TEC_CUDA(cudaMemsetAsync(ctx->d_counts, 0, ((size_t)n_ensg + TEC_BULK_NSTATS) * 8, ctx->stream));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));     // host staging vectors go out of scope
+    ctx->has_index = true;
+    return TEC_OK;
+}
+
+// ------------------------------------------------------------------------------------ bulk
+extern "C" int tec_bulk_begin(tec_ctx* ctx, int paired, int qual) {
+    if (!ctx) return TEC_ERR_ARG;
+    if (!ctx->has_index) TEC_FAIL(TEC_ERR_STATE, "tec_bulk_begin: no index uploaded");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    ctx->paired = paired ? 1 : 0;
+    ctx->qual = qual;
+    TEC_CUDA(cudaMemsetAsync(ctx->d_counts, 0, ((size_t)ctx->idx.n_ensg + TEC_BULK_NSTATS) * 8, ctx->stream));
+    ctx->bulk_active = true;
+    return TEC_OK;
+}
+
+static int bulk_launch(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
+                       const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
+    const int64_t n_units = ctx->paired ? n_rec / 2 : n_rec;
+    if (n_units <= 0) return TEC_OK;
+    IndexView iv = ctx->idx.view();
+    u64* counts = ctx->d_counts;
+    u64* stats = ctx->d_counts + ctx->idx.n_ensg;
+    const int threads = 256;
+    const int64_t want = (n_units + threads - 1) / threads;
+    const int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->n_sm * 8);     // 8 CTAs of 256 = 2048 threads / SM
+    if (ctx->paired)
+        bulk_count_kernel<true><<<blocks, threads, 0, ctx->stream>>>(iv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats);
+    else
+        bulk_count_kernel<false><<<blocks, threads, 0, ctx->stream>>>(iv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats);
+    ctx->launches++;
+    TEC_CUDA(cudaGetLastError());
+    return TEC_OK;
+}
+
+extern "C" int tec_bulk_push_dev(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
+                                 const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
+    if (!ctx) return TEC_ERR_ARG;
+    if (!ctx->bulk_active) TEC_FAIL(TEC_ERR_STATE, "tec_bulk_push_dev: tec_bulk_begin not called");
+    if (n_rec < 0 || (ctx->paired && (n_rec & 1))) TEC_FAIL(TEC_ERR_ARG, "tec_bulk_push_dev: record count must be even in paired mode");
+    if (n_rec == 0) return TEC_OK;
+    if (!start || !end || !chrom || !mapq || !flag) TEC_FAIL(TEC_ERR_ARG, "tec_bulk_push_dev: null array");
+    if (((uintptr_t)start & 7) || ((uintptr_t)end & 3) || ((uintptr_t)chrom & 1) || ((uintptr_t)flag & 1))
+        TEC_FAIL(TEC_ERR_ARG, "tec_bulk_push_dev: misaligned array");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    TEC_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = bulk_launch(ctx, n_rec, start, end, chrom, mapq, flag);
+    if (rc) return rc;
+    TEC_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->timed = true;
+    return TEC_OK;
+}
+
+// Host buffers: chunks are copied on the copy stream into one of two staging slots while the
+// previous chunk is counted on the compute stream.
+extern "C" int tec_bulk_push(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
+                             const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
+    if (!ctx) return TEC_ERR_ARG;
+    if (!ctx->bulk_active) TEC_FAIL(TEC_ERR_STATE, "tec_bulk_push: tec_bulk_begin not called");
+    if (n_rec < 0 || (ctx->paired && (n_rec & 1))) TEC_FAIL(TEC_ERR_ARG, "tec_bulk_push: record count must be even in paired mode");
+    if (n_rec == 0) return TEC_OK;
+    if (!start || !end || !chrom || !mapq || !flag) TEC_FAIL(TEC_ERR_ARG, "tec_bulk_push: null array");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    const int64_t chunk = TEC_STAGE_RECORDS;
+    int rc = ctx->ensure_stage(std::min<int64_t>(n_rec, chunk), /*sc=*/false);
+    if (rc) return rc;
+    TEC_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int64_t off = 0; off < n_rec; off += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, n_rec - off);
+        const int s = ctx->stage_next;
+        ctx->stage_next ^= 1;
+        StageSlot& sl = ctx->stage[s];
+        TEC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[s], 0));
+        TEC_CUDA(cudaMemcpyAsync(sl.start, start + off, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        TEC_CUDA(cudaMemcpyAsync(sl.end, end + off, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        TEC_CUDA(cudaMemcpyAsync(sl.chrom, chrom + off, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->copy_stream));
+        TEC_CUDA(cudaMemcpyAsync(sl.mapq, mapq + off, (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        TEC_CUDA(cudaMemcpyAsync(sl.flag, flag + off, (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        TEC_CUDA(cudaEventRecord(ctx->stage_ready[s], ctx->copy_stream));
+        TEC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->stage_ready[s], 0));
+        rc = bulk_launch(ctx, n, sl.start, sl.end, sl.chrom, sl.mapq, sl.flag);
+        if (rc) return rc;
+        TEC_CUDA(cudaEventRecord(ctx->stage_free[s], ctx->stream));
+    }
+    TEC_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->timed = true;
+    // the caller may reuse its host buffers as soon as we return
+    TEC_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return TEC_OK;
+}
+
+extern "C" int tec_bulk_finish(tec_ctx* ctx, int64_t* counts, int64_t* stats) {
+    if (!ctx) return TEC_ERR_ARG;
+    if (!ctx->bulk_active) TEC_FAIL(TEC_ERR_STATE, "tec_bulk_finish: tec_bulk_begin not called");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    if (counts && ctx->idx.n_ensg)
+        TEC_CUDA(cudaMemcpyAsync(counts, ctx->d_counts, (size_t)ctx->idx.n_ensg * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats)
+        TEC_CUDA(cudaMemcpyAsync(stats, ctx->d_counts + ctx->idx.n_ensg, TEC_BULK_NSTATS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TEC_OK;
+}
+
+extern "C" void* tec_bulk_counts_dev(tec_ctx* ctx) { return ctx ? (void*)ctx->d_counts : nullptr; }
+
+extern "C" int tec_bulk_set_peers(tec_ctx* ctx, int n_peers, void* const* peer_counts) {
+    if (!ctx) return TEC_ERR_ARG;
+    (void)n_peers; (void)peer_counts;
+    TEC_FAIL(TEC_ERR_UNIMPLEMENTED, "tec_bulk_set_peers: not implemented yet");
+}

@@ -1,0 +1,93 @@
+"""Parity of the CUDA bulk path (through the C ABI) with the reference's outputs (golden cases)
+and with the CPU oracle on larger seeded inputs."""
+import numpy as np
+import pytest
+
+import helpers as H
+from te_counter_b200 import synth
+from oracle import te_oracle
+from te_counter_b200 import _lib
+from test_host_mirror import run_bulk_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    eng = _lib.Engine(0)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("name", H.case_names("bulk"))
+def test_bulk_golden_through_mirror(monkeypatch, tmp_path, name):
+    run_bulk_case(monkeypatch, tmp_path, name, _lib.Engine, batch=1024)
+
+
+@pytest.mark.parametrize("paired", [False, True])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_bulk_matches_oracle_seeded(engine, paired, seed):
+    idx = synth.synth_index(seed, n_te=30000, n_exon=9000, n_gene=600, chrom_len=3_000_000, n_chrom=3)
+    r = synth.synth_bulk_reads(seed + 10, idx, 60000, paired=paired, edge_frac=0.1)
+    engine.upload_index(idx)
+    engine.bulk_begin(paired, 20)
+    engine.bulk_push(len(r["start"]), r["start"], r["end"], r["chrom"], r["mapq"], r["flag"])
+    counts, st = engine.bulk_finish()
+    oc, os_ = te_oracle.bulk_count(H.oracle_index(idx), paired, 20, r["start"].tolist(), r["end"].tolist(),
+                                   r["chrom"].tolist(), r["mapq"].tolist(), r["flag"].tolist())
+    assert counts.tolist() == oc
+    assert st[_lib.BS_UNITS] + 1 == os_["total_reads"]
+    assert (st[_lib.BS_ASSIGNED], st[_lib.BS_LOWQ], st[_lib.BS_BADCHROM], st[_lib.BS_QCFAIL]) == \
+        (os_["assigned"], os_["lowq"], os_["badchrom"], os_["qcfail"])
+    assert counts.sum() > 1000
+
+
+def test_bulk_deep_pileup_overflow_path(engine):
+    """> BULK_MAX_DISTINCT distinct ensg under one read: the O(h^2) re-walk path."""
+    n = 40
+    L = np.full(n, 1000, np.int32) + np.arange(n, dtype=np.int32)
+    R = np.full(n, 5000, np.int32)
+    from te_counter_b200.index import GlbIndex
+    idx = GlbIndex(["1"], np.zeros(n, np.int32), L, R, np.arange(n, dtype=np.int32) % 30,
+                   np.full(n, 2, np.uint8), np.zeros(n, np.uint8), ["e%02d" % i for i in range(30)])
+    engine.upload_index(idx)
+    engine.bulk_begin(False, 0)
+    start = np.array([2000, 1010, 900], np.int32)
+    end = np.array([2100, 1011, 1001], np.int32)
+    z8 = np.zeros(3, np.uint8)
+    engine.bulk_push(3, start, end, np.zeros(3, np.uint16), z8 + 60, z8)
+    counts, st = engine.bulk_finish()
+    oc, _ = te_oracle.bulk_count(H.oracle_index(idx), False, 0, start.tolist(), end.tolist(), [0, 0, 0], [60] * 3, [0] * 3)
+    assert counts.tolist() == oc
+
+
+def test_bulk_linearity_and_chunking(engine):
+    """counts(A ++ B) == counts(A) + counts(B); pushing in many small batches == one batch."""
+    idx = synth.synth_index(5, n_te=20000, n_exon=5000, n_gene=300, chrom_len=2_000_000, n_chrom=2)
+    r = synth.synth_bulk_reads(6, idx, 200000, paired=True)
+    engine.upload_index(idx)
+    cols = [r[k] for k in ("start", "end", "chrom", "mapq", "flag")]
+
+    def run(slices):
+        engine.bulk_begin(True, 20)
+        for a, b in slices:
+            engine.bulk_push(b - a, *[np.ascontiguousarray(c[a:b]) for c in cols])
+        return engine.bulk_finish()
+
+    n = len(cols[0])
+    whole, st = run([(0, n)])
+    parts, st2 = run([(a, min(n, a + 10000)) for a in range(0, n, 10000)])
+    a_, _ = run([(0, 70000)])
+    b_, _ = run([(70000, n)])
+    assert (whole == parts).all() and (st == st2).all()
+    assert (whole == a_ + b_).all()
+
+
+def test_misuse_errors(engine):
+    with pytest.raises(_lib.TecError):
+        engine.bulk_push(3, *[np.zeros(4, d) for d in (np.int32, np.int32, np.uint16, np.uint8, np.uint8)]) \
+            if engine.bulk_begin(True, 20) is None else None
+    e2 = _lib.Engine(0)
+    with pytest.raises(_lib.TecError):
+        e2.bulk_begin(False, 20)          # no index
+    e2.close()
