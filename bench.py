@@ -1,0 +1,386 @@
+#!/usr/bin/env python3
+"""
+bench.py -- reads/sec of the counting hot path on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload bulk_pe|bulk_se|sc]
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port), host cores
+
+A "step" is one pass of filter -> overlap -> tally (+ cross-GPU merge) over the whole workload
+(default: BASELINE.json configs[3], synthetic 500 M-record paired-end bulk on an hg38-like
+genes_tes index).  Inputs are resident in HBM for `value`; `e2e` goes through the
+host-buffer C ABI call (tec_bulk_push + tec_bulk_finish) with pinned host arrays, H2D/D2H inside
+the timed region.  Inputs (>= 6 GB per step) are far larger than the 126 MB L2, so no explicit
+flush is needed between timed iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_RECORD = {"bulk_pe": 12, "bulk_se": 12, "sc": 24}
+INDEX_BYTES_PER_FEATURE = 16
+CONFIG_RECORDS = {"bulk_pe": 500_000_000, "bulk_se": 500_000_000, "sc": 1_000_000_000}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bulk_pe", choices=["bulk_pe", "bulk_se", "sc"])
+    ap.add_argument("--records", type=int, default=0, help="records per GPU (default: the config's size)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--index-scale", type=float, default=1.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="records of the CPU-baseline sample")
+    ap.add_argument("--cpu-cores", type=int, default=0, help="reference arm: worker processes (0 = all)")
+    ap.add_argument("--sorted", action="store_true", help="coordinate-sorted arrival order (bulk_se)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_index(scale):
+    from te_counter_b200 import synth
+    if scale == 1.0:
+        return synth.synth_index()
+    return synth.synth_index(n_te=int(4_600_000 * scale), n_exon=int(1_300_000 * scale),
+                             n_gene=max(10, int(38_000 * scale)), n_te_names=max(10, int(1200 * min(1.0, scale * 4))))
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines[-3:]]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax = max(smax, float(f[1]))
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+_W = {}
+
+
+def _ref_worker(args):
+    a, b = args
+    from oracle import te_oracle
+    cols = _W["cols"]
+    t = time.perf_counter()
+    if _W["workload"] == "sc":
+        raise RuntimeError("sc reference arm runs single process")
+    c, st = te_oracle.bulk_count(_W["oidx"], _W["paired"], 20, *[x[a:b] for x in cols])
+    return st["assigned"], time.perf_counter() - t
+
+
+def run_reference(args):
+    """The reference's pure-Python algorithm (oracle/te_oracle.py, a line-by-line restatement pinned
+    to the unmodified reference by tests/golden) on the host cores.  Bulk units are independent, so
+    the sample is split over worker processes (fork; the index is shared copy-on-write)."""
+    import multiprocessing as mp
+    from te_counter_b200 import synth
+    from oracle import te_oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    paired = wl == "bulk_pe"
+    cores = args.cpu_cores or (os.cpu_count() or 1)
+    idx = make_index(args.index_scale)
+    oidx = te_oracle.Index(idx.chrom_id, idx.L, idx.R, idx.ensg_id, idx.type_code, idx.strand_code,
+                           idx.n_ensg, idx.bucket_size)
+    per_core = max(2, args.cpu_sample // 8)
+    n = per_core * cores if wl != "sc" else args.cpu_sample
+    n -= n & 1
+    if wl == "sc":
+        r = synth.synth_sc_reads(synth.SEED, idx, n)
+        cols = [r[k].tolist() for k in ("start", "end", "chrom", "mapq", "flag", "cell", "umi")]
+        cores = 1
+    else:
+        r = synth.synth_bulk_reads(synth.SEED, idx, n, paired=paired, sort=args.sorted)
+        cols = [r[k].tolist() for k in ("start", "end", "chrom", "mapq", "flag")]
+    _W.update(cols=cols, oidx=oidx, paired=paired, workload=wl)
+    chunk = (n // cores) & ~1
+    tasks = [(i * chunk, (i + 1) * chunk if i < cores - 1 else n) for i in range(cores)]
+    times = []
+
+    def one_step(pool):
+        t = time.perf_counter()
+        if wl == "sc":
+            te_oracle.sc_count(oidx, 20, True, 10_000_000, 10_000, 1000, *cols)
+        elif pool is None:
+            _ref_worker(tasks[0])
+        else:
+            pool.map(_ref_worker, tasks)
+        return time.perf_counter() - t
+
+    pool = mp.get_context("fork").Pool(cores) if (cores > 1 and wl != "sc") else None
+    for _ in range(args.warmup):
+        one_step(pool)
+    for _ in range(args.steps):
+        times.append(one_step(pool))
+    if pool:
+        pool.close()
+    ms = 1e3 * float(np.mean(times))
+    value = n / (ms / 1e3)
+    line = {"impl": "reference", "metric": "reads_per_sec", "value": value, "unit": "records/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "gpu_launches": 0,
+            "config": workload_config(args, n, 1),
+            "cpu_baseline": {"value": value, "unit": "records/s", "cores": cores, "kind": "port",
+                             "sample": "%d-record sample of the same synthetic workload per step, split over %d "
+                                       "worker process(es); pure-Python restatement of te_count.py's loop, BAM decode "
+                                       "excluded" % (n, cores)},
+            "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_rec_per_gpu, world):
+    wl = args.workload
+    names = {"bulk_pe": "BASELINE.json configs[3]: synthetic paired-end bulk RNA-seq, hg38-like genes_tes index "
+                        "(5.9 M features, 39.2 k ensg), name-collated random arrival order",
+             "bulk_se": "synthetic single-end bulk RNA-seq (configs[3] reads taken as SE), hg38-like genes_tes index",
+             "sc": "BASELINE.json configs[4]: synthetic 10x-style single cell, 100 k barcodes, --maxcells 10000"}
+    return {"workload": names[wl], "records_per_gpu": int(n_rec_per_gpu), "records_total": int(n_rec_per_gpu * world),
+            "sharding": "genomic coordinate range per GPU, index replicated" if world > 1 else "single GPU",
+            "index_scale": args.index_scale, "l2_policy": "inputs >> L2 (no flush needed)",
+            "bytes_per_record": BYTES_PER_RECORD[wl]}
+
+
+# ------------------------------------------------------------------------------ our arm
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from te_counter_b200 import _lib, synth
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload
+    if wl == "sc":
+        return run_ours_sc(args, rank, world, local, dev)
+    paired = wl == "bulk_pe"
+    n_cfg = args.records or CONFIG_RECORDS[wl]
+    n_rec = n_cfg if args.scaling == "weak" else n_cfg // world
+    n_rec -= n_rec & 1
+    idx = make_index(args.index_scale)
+    eng = _lib.Engine(local)
+    eng.upload_index(idx)
+    reads = synth.synth_bulk_reads(synth.SEED + rank, idx, n_rec, paired=paired, device=dev, as_numpy=False,
+                                   shard=(rank, world), sort=args.sorted)
+    cols = [reads[k] for k in ("start", "end", "chrom", "mapq", "flag")]
+    ptrs = [t.data_ptr() for t in cols]
+    torch.cuda.synchronize()
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+    counts_t = torch.as_tensor(_DevArray(eng.bulk_counts_dev(), idx.n_ensg + _lib.BULK_NSTATS, "<i8"), device=dev)
+
+    def step():
+        eng.bulk_begin(paired, 20)
+        eng.bulk_push_dev(n_rec, *ptrs)
+        if world > 1:
+            with torch.cuda.stream(ext):
+                dist.all_reduce(counts_t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        eng.sync()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    K = args.steps
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = eng.launch_count()
+    barrier()
+    t0 = time.time()
+    e0.record(ext)
+    for k in range(K):
+        eng.bulk_begin(paired, 20)
+        k0[k].record(ext)
+        eng.bulk_push_dev(n_rec, *ptrs)
+        k1[k].record(ext)
+        if world > 1:
+            with torch.cuda.stream(ext):
+                dist.all_reduce(counts_t)
+    e1.record(ext)
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    launches = eng.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = n_rec * world / (ms_step / 1e3)
+    counts, st = eng.bulk_finish()
+
+    # ---- end to end through the host-buffer ABI (pinned host arrays, H2D + D2H in the timed region)
+    e2e = None
+    if not args.no_e2e:
+        host = [eng.pinned(n_rec, dt) for dt in (np.int32, np.int32, np.uint16, np.uint8, np.uint8)]
+        for h, t in zip(host, cols):
+            torch.from_numpy(h.view(np.int16) if h.dtype == np.uint16 else h).copy_(
+                t.view(torch.int16) if t.dtype == torch.uint16 else t)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            eng.bulk_begin(paired, 20)
+            eng.bulk_push(n_rec, *host)
+            return eng.bulk_finish()
+
+        for _ in range(2):
+            c2, s2 = e2e_step()
+        barrier()
+        ta = time.perf_counter()
+        for _ in range(K):
+            c2, s2 = e2e_step()
+        tb = time.perf_counter()
+        dt = (tb - ta) / K
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n_rec * world / dt, "unit": "records/s", "h2d_bytes_per_step": int(n_rec) * 12,
+               "d2h_bytes_per_step": (idx.n_ensg + _lib.BULK_NSTATS) * 8, "ms_per_step": dt * 1e3,
+               "api": "tec_bulk_begin + tec_bulk_push(host SoA, pinned) + tec_bulk_finish"}
+        if world == 1:
+            assert (c2 == counts).all(), "e2e counts differ from the device-resident run"
+        del host
+
+    # ---- CPU baseline + parity on a bounded prefix (rank 0, N = 1)
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import te_oracle
+        ns = min(n_rec, args.cpu_sample) & ~1
+        sample = [t[:ns].cpu().numpy() for t in cols]
+        sample[2] = sample[2].view(np.uint16)
+        eng.bulk_begin(paired, 20)
+        eng.bulk_push(ns, *[np.ascontiguousarray(a) for a in sample])
+        gc, gs = eng.bulk_finish()
+        oidx = te_oracle.Index(idx.chrom_id, idx.L, idx.R, idx.ensg_id, idx.type_code, idx.strand_code,
+                               idx.n_ensg, idx.bucket_size)
+        lists = [a.tolist() for a in sample]
+        ta = time.perf_counter()
+        oc, os_ = te_oracle.bulk_count(oidx, paired, 20, *lists)
+        tb = time.perf_counter()
+        ok = (gc.tolist() == oc and int(gs[_lib.BS_UNITS]) + 1 == os_["total_reads"]
+              and int(gs[_lib.BS_ASSIGNED]) == os_["assigned"] and int(gs[_lib.BS_LOWQ]) == os_["lowq"]
+              and int(gs[_lib.BS_BADCHROM]) == os_["badchrom"] and int(gs[_lib.BS_QCFAIL]) == os_["qcfail"])
+        parity = {"sample_records": ns, "bit_exact": bool(ok)}
+        cpu = {"value": ns / (tb - ta), "unit": "records/s", "cores": 1, "kind": "port",
+               "host_cores_available": os.cpu_count(),
+               "sample": "first %d records of this workload; pure-Python restatement of te_count.py's loop "
+                         "(oracle/te_oracle.py, pinned to the unmodified reference by tests/golden), single thread "
+                         "as the reference; BAM decode excluded" % ns}
+
+    peak, peak_src = load_peaks()
+    bpr = BYTES_PER_RECORD[wl] + INDEX_BYTES_PER_FEATURE * idx.n_features / float(n_rec)
+    achieved = n_rec * bpr / (kern_ms / 1e3) / 1e9
+    line = {"metric": "reads_per_sec", "value": value, "unit": "records/s", "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args, n_rec, world), "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "bulk_count_kernel<%s>" % ("paired" if paired else "single"),
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_record": bpr},
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
+            "stats": {"units": int(st[0]), "assigned": int(st[1]), "lowq": int(st[2]), "badchrom": int(st[3]),
+                      "qcfail": int(st[4]), "counts_sum": int(counts.sum())}}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_ours_sc(args, rank, world, local, dev):
+    raise SystemExit("sc workload bench: not wired yet")
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

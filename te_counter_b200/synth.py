@@ -71,9 +71,12 @@ def _torch():
     return torch
 
 
-def synth_bulk_reads(seed, idx, n_records, paired, device="cpu", edge_frac=0.001, sort=False, as_numpy=None):
+def synth_bulk_reads(seed, idx, n_records, paired, device="cpu", edge_frac=0.001, sort=False, as_numpy=None,
+                     shard=(0, 1)):
     """SURVEY.md 8(d) bulk reads.  paired: records come as adjacent mate pairs (name-collated),
-    arrival order random.  Returns dict of arrays (numpy on cpu unless as_numpy=False)."""
+    arrival order random.  shard=(rank, world): this rank's reads fall in its slice of the
+    genome-linear coordinate axis (reads shard by genomic range across GPUs, BASELINE.json).
+    Returns dict of arrays (numpy on cpu unless as_numpy=False)."""
     torch = _torch()
     dev = torch.device(device)
     g = torch.Generator(device=dev)
@@ -84,12 +87,25 @@ def synth_bulk_reads(seed, idx, n_records, paired, device="cpu", edge_frac=0.001
     fC = torch.from_numpy(idx.chrom_id).to(dev)
     lens = torch.from_numpy(np.asarray(idx.chrom_lengths, dtype=np.int64)).to(dev)
     rnd = lambda n: torch.rand(n, generator=g, device=dev)
-    pick = torch.randint(0, idx.n_features, (n_units,), generator=g, device=dev)
+    rank, world = shard
+    cum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens, 0)])
+    G = int(cum[-1].item())
+    lin_lo, lin_hi = G * rank // world, G * (rank + 1) // world
+    # features of this shard: contiguous in (chrom, L) order
+    order = torch.from_numpy(s["order"]).to(dev)
+    lin_sorted = cum[torch.from_numpy(idx.chrom_id[s["order"]]).to(dev).to(torch.int64)] + \
+        torch.from_numpy(s["L"]).to(dev).to(torch.int64)
+    f_lo = int(torch.searchsorted(lin_sorted, torch.tensor([lin_lo], device=dev)).item())
+    f_hi = max(f_lo + 1, int(torch.searchsorted(lin_sorted, torch.tensor([lin_hi], device=dev)).item()))
+    del lin_sorted
+    pick = order[torch.randint(f_lo, min(f_hi, idx.n_features), (n_units,), generator=g, device=dev)]
     near = rnd(n_units) < 0.85
     c_near = fC[pick].to(torch.int64)
     s_near = fL[pick].to(torch.int64) + torch.randint(-100, 101, (n_units,), generator=g, device=dev)
-    c_uni = torch.multinomial(lens.double() / lens.sum().double(), n_units, replacement=True, generator=g)
-    s_uni = (rnd(n_units).double() * (lens[c_uni] - 200).clamp(min=1).double()).to(torch.int64)
+    lin = lin_lo + (rnd(n_units).double() * float(lin_hi - lin_lo)).to(torch.int64)
+    c_uni = (torch.searchsorted(cum, lin, right=True) - 1).clamp(0, idx.n_chrom - 1)
+    s_uni = torch.minimum(lin - cum[c_uni], (lens[c_uni] - 200).clamp(min=0))
+    del lin, order
     chrom = torch.where(near, c_near, c_uni)
     start = torch.where(near, s_near, s_uni).clamp(min=0)
     edge = rnd(n_units) < edge_frac
