@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="records of the CPU-baseline sample")
     ap.add_argument("--cpu-cores", type=int, default=0, help="reference arm: worker processes (0 = all)")
     ap.add_argument("--sorted", action="store_true", help="coordinate-sorted arrival order (bulk_se)")
+    ap.add_argument("--opt", action="append", default=[], help="engine tuning knob key=value (tec_set_option)")
     return ap.parse_args()
 
 
@@ -230,6 +231,9 @@ def run_ours(args):
     n_rec -= n_rec & 1
     idx = make_index(args.index_scale)
     eng = _lib.Engine(local)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     eng.upload_index(idx)
     reads = synth.synth_bulk_reads(synth.SEED + rank, idx, n_rec, paired=paired, device=dev, as_numpy=False,
                                    shard=(rank, world), sort=args.sorted)
@@ -358,7 +362,8 @@ def run_ours(args):
             "config": workload_config(args, n_rec, world), "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "bulk_count_kernel<%s>" % ("paired" if paired else "single"),
+                         "kernel": "bulk_count_cell_kernel<%s> (+ bulk_slow_kernel on flagged units)" % ("paired" if paired else "single"),
+                         "cell_table_bytes": eng.get_info("stab_bytes"),
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_record": bpr},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
             "stats": {"units": int(st[0]), "assigned": int(st[1]), "lowq": int(st[2]), "badchrom": int(st[3]),

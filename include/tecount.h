@@ -110,6 +110,12 @@ float tec_last_kernel_ms(tec_ctx* ctx);
 /* number of kernel launches issued by this context since creation */
 int64_t tec_launch_count(const tec_ctx* ctx);
 
+/* tuning knobs: "bulk_algo" (-1 auto, 0 exact search kernel, 1 stab-table kernel), "stab_shift"
+ * (log2 of the stab-table cell size, used by the next tec_index_upload), "ctas_per_sm".
+ * tec_get_info: "has_stab", "stab_bytes", "n_sm", "n_features"; -1 for unknown keys. */
+int tec_set_option(tec_ctx* ctx, const char* key, int64_t value);
+int64_t tec_get_info(tec_ctx* ctx, const char* key);
+
 /* ---- index ------------------------------------------------------------------------------
  * Replaces load_genome() + the structures of genelist._optimiseData that the read loops reach
  * into (te_count.py:31-35, :68-73, :586-590; miniglbase/genelist.py:332-396).
@@ -139,7 +145,9 @@ int tec_bulk_push_dev(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const i
                       const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag);
 int tec_bulk_finish(tec_ctx* ctx, int64_t* counts, int64_t* stats);
 /* device address of the int64 counters [n_ensg] followed by stats [TEC_BULK_NSTATS]; lets the
- * caller run the cross-GPU reduction (NCCL) on the library's buffer without a host round trip */
+ * caller run the cross-GPU reduction (NCCL) on the library's buffer without a host round trip.
+ * The counters are in the library's internal order (the same on every rank for the same index);
+ * tec_bulk_finish returns them in ensg-id order. */
 void* tec_bulk_counts_dev(tec_ctx* ctx);
 /* multi-GPU: peer-mapped addresses of every rank's counter block (this rank's own included).
  * When set, the tally kernel's flush adds its per-CTA partial counts directly into ALL ranks'

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtecount.so")
+LIB_PATH = os.environ.get("TEC_LIB") or os.path.join(_HERE, "libtecount.so")
 
 BULK_NSTATS = 8
 BS_UNITS, BS_ASSIGNED, BS_LOWQ, BS_BADCHROM, BS_QCFAIL, BS_CRASH_ENHANCER, BS_CRASH_NAME = range(7)
@@ -37,6 +37,8 @@ SIGNATURES = {
     "tec_stream": (_vp, [_vp]),
     "tec_last_kernel_ms": (ctypes.c_float, [_vp]),
     "tec_launch_count": (ctypes.c_int64, [_vp]),
+    "tec_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
+    "tec_get_info": (ctypes.c_int64, [_vp, ctypes.c_char_p]),
     "tec_index_upload": (ctypes.c_int, [_vp, ctypes.c_int32, _c_i64p, _c_i32p, _c_i32p, _c_i32p, _c_u8p,
                                         _c_u8p, ctypes.c_int32, ctypes.c_int32]),
     "tec_bulk_begin": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
@@ -142,6 +144,12 @@ class Engine:
 
     def launch_count(self):
         return int(self._lib.tec_launch_count(self._h))
+
+    def set_option(self, key, value):
+        self._check(self._lib.tec_set_option(self._h, key.encode(), int(value)))
+
+    def get_info(self, key):
+        return int(self._lib.tec_get_info(self._h, key.encode()))
 
     # -- index
     def upload_index(self, idx):

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libtecount.so")
+LIB = os.environ.get("TEC_LIB") or os.path.join(HERE, "libtecount.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
@@ -26,6 +26,7 @@ def build(force=False, verbose=False):
         return LIB
     cmd = [NVCC, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-o", LIB, os.path.join(CSRC, "tecount.cu")]
+    cmd[1:1] = os.environ.get("TEC_NVCC_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -1,6 +1,7 @@
 // Context object behind the opaque tec_ctx handle.
 #pragma once
 #include "common.cuh"
+#include "bulk.cuh"
 
 #define TEC_STAGE_RECORDS (int64_t(16) << 20)     // records per host->device staging chunk
 
@@ -14,6 +15,20 @@ struct DevIndex {
     int64_t* dir_off = nullptr;
     int n_chrom = 0, n_ensg = 0, bs = 10000, shift = 9;
     int64_t n_feat = 0, n_dir = 0;
+    // cell table (stab_build.h); absent when the index exceeds its limits
+    u32* st_sectors = nullptr;
+    int64_t* st_cell_base = nullptr;
+    uint8_t* st_slot_type = nullptr;
+    int st_shift = 11, st_all_counted = 1;
+    bool has_stab = false;
+    size_t stab_bytes = 0;
+    int64_t st_primary = 0, st_overflow = 0, st_entries = 0;
+    StabView stab_view() const {
+        StabView v;
+        v.sectors = st_sectors; v.cell_base = st_cell_base; v.slot_type = st_slot_type;
+        v.shift = st_shift; v.all_counted = st_all_counted;
+        return v;
+    }
     IndexView view() const {
         IndexView v;
         v.L = L; v.R = R; v.pmaxR = pmaxR; v.info = info; v.chrom_off = chrom_off;
@@ -51,7 +66,14 @@ struct tec_ctx {
     // bulk
     bool bulk_active = false;
     int paired = 0, qual = 20;
-    u64* d_counts = nullptr;              // n_ensg counters + TEC_BULK_NSTATS statistics
+    u64* d_counts = nullptr;              // n_ensg counters (slot order) + TEC_BULK_NSTATS statistics
+    u32* d_slow_bits = nullptr;           // one ballot word per 32 units of a launch (bulk_slow_kernel)
+    int64_t slow_cap = 0;                 // words
+    std::vector<int32_t> ensg_of_slot;    // slot = rank of an ensg by number of feature rows
+    // options (tec_set_option)
+    int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 stab-table kernel
+    int opt_stab_shift = 11;
+    int opt_ctas_per_sm = 2;              // resident CTAs per SM of the fast bulk kernel (512 threads each)
 
     // host staging
     StageSlot stage[2];
@@ -80,9 +102,13 @@ inline void tec_ctx::free_index() {
     DevIndex& ix = idx;
     cudaFree(ix.L); cudaFree(ix.R); cudaFree(ix.pmaxR); cudaFree(ix.info);
     cudaFree(ix.chrom_off); cudaFree(ix.dir); cudaFree(ix.dir_off);
+    cudaFree(ix.st_sectors); cudaFree(ix.st_cell_base); cudaFree(ix.st_slot_type);
     ix = DevIndex();
     cudaFree(d_counts);
     d_counts = nullptr;
+    cudaFree(d_slow_bits);
+    d_slow_bits = nullptr;
+    slow_cap = 0;
     has_index = false;
     bulk_active = false;
 }

@@ -1,6 +1,7 @@
 // libtecount.so -- C ABI implementation (see include/tecount.h).  sm_100a only, no CPU fallback.
 #include "common.cuh"
 #include "bulk.cuh"
+#include "stab_build.h"
 #include "context.cuh"
 #include "sc.cuh"
 
@@ -134,6 +135,19 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
     ctx->free_index();
     DevIndex& ix = ctx->idx;
     const int shift = 9;                            // 512 bp directory cells
+    // slot = rank of the ensg by number of feature rows (most first): hot counters -> shared memory
+    std::vector<int64_t> rows((size_t)std::max(n_ensg, 1), 0);
+    for (int64_t i = 0; i < nf; ++i) {
+        if (ensg_id[i] < 0 || ensg_id[i] >= n_ensg) TEC_FAIL(TEC_ERR_ARG, "tec_index_upload: ensg id out of range");
+        rows[(size_t)ensg_id[i]]++;
+    }
+    ctx->ensg_of_slot.resize((size_t)n_ensg);
+    for (int i = 0; i < n_ensg; ++i) ctx->ensg_of_slot[(size_t)i] = i;
+    std::stable_sort(ctx->ensg_of_slot.begin(), ctx->ensg_of_slot.end(),
+                     [&](int32_t a, int32_t b) { return rows[(size_t)a] > rows[(size_t)b]; });
+    std::vector<uint32_t> slot_of((size_t)std::max(n_ensg, 1), 0);
+    for (int s = 0; s < n_ensg; ++s) slot_of[(size_t)ctx->ensg_of_slot[(size_t)s]] = (uint32_t)s;
+    std::vector<uint32_t> fslot((size_t)nf);
     std::vector<int32_t> pmax((size_t)nf);
     std::vector<u32> info((size_t)nf);
     std::vector<int64_t> dir_off((size_t)n_chrom + 1, 0);
@@ -151,7 +165,8 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
             run = std::max(run, R[i]);
             pmax[(size_t)i] = run;
             maxL = std::max(maxL, L[i]);
-            info[(size_t)i] = info_pack((u32)ensg_id[i], type_code[i], strand_code[i]);
+            fslot[(size_t)i] = slot_of[(size_t)ensg_id[i]];
+            info[(size_t)i] = info_pack(fslot[(size_t)i], type_code[i], strand_code[i]);
         }
         dir_off[(size_t)c + 1] = dir_off[(size_t)c] + ((int64_t)(maxL >> shift) + 2);
     }
@@ -178,6 +193,25 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
         build_dir_kernel<<<blocks, 256, 0, ctx->stream>>>(ix.L, ix.chrom_off, ix.dir_off, n_chrom, shift, ix.dir, n_dir);
         ctx->launches++;
         TEC_CUDA(cudaGetLastError());
+    }
+    // cell table for the bulk fast path
+    {
+        StabTable st;
+        stab_build(st, n_chrom, chrom_off, L, R, fslot.data(), type_code, n_ensg, ctx->opt_stab_shift);
+        if (st.why_not.empty()) {
+            TEC_CUDA(cudaMalloc(&ix.st_sectors, std::max<size_t>(st.sectors.size(), 8) * 4));
+            TEC_CUDA(cudaMalloc(&ix.st_cell_base, st.cell_base.size() * 8));
+            TEC_CUDA(cudaMalloc(&ix.st_slot_type, st.slot_type.size()));
+            if (!st.sectors.empty())
+                TEC_CUDA(cudaMemcpyAsync(ix.st_sectors, st.sectors.data(), st.sectors.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            TEC_CUDA(cudaMemcpyAsync(ix.st_cell_base, st.cell_base.data(), st.cell_base.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            TEC_CUDA(cudaMemcpyAsync(ix.st_slot_type, st.slot_type.data(), st.slot_type.size(), cudaMemcpyHostToDevice, ctx->stream));
+            TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+            ix.st_shift = st.shift; ix.st_all_counted = st.all_counted; ix.has_stab = true; ix.stab_bytes = st.bytes();
+            ix.st_primary = st.n_primary; ix.st_overflow = st.n_overflow; ix.st_entries = st.n_entries;
+        } else {
+            ctx->err = "cell table not built: " + st.why_not;      // informational; exact kernel is used
+        }
     }
     // per-feature counters + statistics block
     TEC_CUDA(cudaMalloc(&ctx->d_counts, ((size_t)n_ensg + TEC_BULK_NSTATS) * 8));
@@ -206,9 +240,40 @@ static int bulk_launch(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const 
     IndexView iv = ctx->idx.view();
     u64* counts = ctx->d_counts;
     u64* stats = ctx->d_counts + ctx->idx.n_ensg;
+    const bool use_stab = ctx->idx.has_stab && ctx->opt_bulk_algo != 0;
+    if (ctx->opt_bulk_algo == 1 && !ctx->idx.has_stab) TEC_FAIL(TEC_ERR_STATE, "bulk_algo=1 but the index has no cell table");
+    if (use_stab) {
+        // fast kernel: one warp per 32 units, persistent grid; then the exact kernel on flagged units
+        const int64_t n_tiles = (n_units + 31) / 32;
+        if (n_tiles > ctx->slow_cap) {
+            TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_slow_bits);
+            ctx->d_slow_bits = nullptr;
+            ctx->slow_cap = 0;
+            TEC_CUDA(cudaMalloc(&ctx->d_slow_bits, (size_t)n_tiles * 4));
+            ctx->slow_cap = n_tiles;
+        }
+        StabView sv = ctx->idx.stab_view();
+        const int wpb = BULK_THREADS / 32;
+        const int blocks = (int)std::min<int64_t>((n_tiles + wpb - 1) / wpb, (int64_t)ctx->n_sm * ctx->opt_ctas_per_sm);
+        if (ctx->paired)
+            bulk_count_cell_kernel<true><<<blocks, BULK_THREADS, 0, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, ctx->d_slow_bits);
+        else
+            bulk_count_cell_kernel<false><<<blocks, BULK_THREADS, 0, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, ctx->d_slow_bits);
+        ctx->launches++;
+        TEC_CUDA(cudaGetLastError());
+        const int sblocks = (int)std::min<int64_t>((n_tiles + 255) / 256, (int64_t)ctx->n_sm * 8);
+        if (ctx->paired)
+            bulk_slow_kernel<true><<<sblocks, 256, 0, ctx->stream>>>(iv, n_units, start, end, chrom, counts, stats, ctx->d_slow_bits);
+        else
+            bulk_slow_kernel<false><<<sblocks, 256, 0, ctx->stream>>>(iv, n_units, start, end, chrom, counts, stats, ctx->d_slow_bits);
+        ctx->launches++;
+        TEC_CUDA(cudaGetLastError());
+        return TEC_OK;
+    }
     const int threads = 256;
     const int64_t want = (n_units + threads - 1) / threads;
-    const int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->n_sm * 8);     // 8 CTAs of 256 = 2048 threads / SM
+    const int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->n_sm * 8);
     if (ctx->paired)
         bulk_count_kernel<true><<<blocks, threads, 0, ctx->stream>>>(iv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats);
     else
@@ -225,7 +290,7 @@ extern "C" int tec_bulk_push_dev(tec_ctx* ctx, int64_t n_rec, const int32_t* sta
     if (n_rec < 0 || (ctx->paired && (n_rec & 1))) TEC_FAIL(TEC_ERR_ARG, "tec_bulk_push_dev: record count must be even in paired mode");
     if (n_rec == 0) return TEC_OK;
     if (!start || !end || !chrom || !mapq || !flag) TEC_FAIL(TEC_ERR_ARG, "tec_bulk_push_dev: null array");
-    if (((uintptr_t)start & 7) || ((uintptr_t)end & 3) || ((uintptr_t)chrom & 1) || ((uintptr_t)flag & 1))
+    if (((uintptr_t)start & 7) || ((uintptr_t)end & 3) || ((uintptr_t)chrom & 3) || ((uintptr_t)mapq & 1) || ((uintptr_t)flag & 1))
         TEC_FAIL(TEC_ERR_ARG, "tec_bulk_push_dev: misaligned array");
     TEC_CUDA(cudaSetDevice(ctx->device));
     TEC_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -278,15 +343,40 @@ extern "C" int tec_bulk_finish(tec_ctx* ctx, int64_t* counts, int64_t* stats) {
     if (!ctx) return TEC_ERR_ARG;
     if (!ctx->bulk_active) TEC_FAIL(TEC_ERR_STATE, "tec_bulk_finish: tec_bulk_begin not called");
     TEC_CUDA(cudaSetDevice(ctx->device));
-    if (counts && ctx->idx.n_ensg)
-        TEC_CUDA(cudaMemcpyAsync(counts, ctx->d_counts, (size_t)ctx->idx.n_ensg * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (stats)
-        TEC_CUDA(cudaMemcpyAsync(stats, ctx->d_counts + ctx->idx.n_ensg, TEC_BULK_NSTATS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t ne = (size_t)ctx->idx.n_ensg;
+    std::vector<int64_t> tmp(ne + TEC_BULK_NSTATS);
+    TEC_CUDA(cudaMemcpyAsync(tmp.data(), ctx->d_counts, (ne + TEC_BULK_NSTATS) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (counts)
+        for (size_t s = 0; s < ne; ++s) counts[(size_t)ctx->ensg_of_slot[s]] = tmp[s];     // slot order -> ensg order
+    if (stats) memcpy(stats, tmp.data() + ne, TEC_BULK_NSTATS * 8);
     return TEC_OK;
 }
 
 extern "C" void* tec_bulk_counts_dev(tec_ctx* ctx) { return ctx ? (void*)ctx->d_counts : nullptr; }
+
+extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return TEC_ERR_ARG;
+    const std::string k(key);
+    if (k == "bulk_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "bulk_algo: -1, 0 or 1"); ctx->opt_bulk_algo = (int)value; }
+    else if (k == "stab_shift") { if (value < 8 || value > STAB_MAX_SHIFT) TEC_FAIL(TEC_ERR_ARG, "stab_shift: 8..11"); ctx->opt_stab_shift = (int)value; }
+    else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
+    else TEC_FAIL(TEC_ERR_ARG, "tec_set_option: unknown key " + k);
+    return TEC_OK;
+}
+
+extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
+    if (!ctx || !key) return -1;
+    const std::string k(key);
+    if (k == "has_stab") return ctx->idx.has_stab ? 1 : 0;
+    if (k == "stab_bytes") return (int64_t)ctx->idx.stab_bytes;
+    if (k == "n_sm") return ctx->n_sm;
+    if (k == "n_features") return ctx->idx.n_feat;
+    if (k == "stab_primary") return ctx->idx.st_primary;
+    if (k == "stab_overflow") return ctx->idx.st_overflow;
+    if (k == "stab_entries") return ctx->idx.st_entries;
+    return -1;
+}
 
 extern "C" int tec_bulk_set_peers(tec_ctx* ctx, int n_peers, void* const* peer_counts) {
     if (!ctx) return TEC_ERR_ARG;

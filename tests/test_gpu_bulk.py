@@ -24,12 +24,17 @@ def test_bulk_golden_through_mirror(monkeypatch, tmp_path, name):
     run_bulk_case(monkeypatch, tmp_path, name, _lib.Engine, batch=1024)
 
 
+@pytest.mark.parametrize("algo,shift", [(0, 11), (1, 11), (1, 9), (1, 8)])
 @pytest.mark.parametrize("paired", [False, True])
 @pytest.mark.parametrize("seed", [1, 2])
-def test_bulk_matches_oracle_seeded(engine, paired, seed):
+def test_bulk_matches_oracle_seeded(engine, paired, seed, algo, shift):
+    """algo 0 = exact search kernel, 1 = stab-table kernel (several cell sizes)."""
     idx = synth.synth_index(seed, n_te=30000, n_exon=9000, n_gene=600, chrom_len=3_000_000, n_chrom=3)
     r = synth.synth_bulk_reads(seed + 10, idx, 60000, paired=paired, edge_frac=0.1)
+    engine.set_option("bulk_algo", algo)
+    engine.set_option("stab_shift", shift)
     engine.upload_index(idx)
+    assert engine.get_info("has_stab") == 1
     engine.bulk_begin(paired, 20)
     engine.bulk_push(len(r["start"]), r["start"], r["end"], r["chrom"], r["mapq"], r["flag"])
     counts, st = engine.bulk_finish()
@@ -40,6 +45,25 @@ def test_bulk_matches_oracle_seeded(engine, paired, seed):
     assert (st[_lib.BS_ASSIGNED], st[_lib.BS_LOWQ], st[_lib.BS_BADCHROM], st[_lib.BS_QCFAIL]) == \
         (os_["assigned"], os_["lowq"], os_["badchrom"], os_["qcfail"])
     assert counts.sum() > 1000
+    engine.set_option("bulk_algo", -1)
+    engine.set_option("stab_shift", 11)
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_bulk_dense_overlaps_and_gapped_reads(engine, algo):
+    """Dense TE pile-ups on a tiny chromosome (sets larger than the register set -> exact path),
+    long N-gapped SE reads whose two points fall in different cells."""
+    idx = synth.synth_index(3, n_te=6000, n_exon=3000, n_gene=40, n_te_names=300, chrom_len=200_000, n_chrom=2)
+    r = synth.synth_bulk_reads(4, idx, 50000, paired=False, edge_frac=0.2)
+    engine.set_option("bulk_algo", algo)
+    engine.upload_index(idx)
+    engine.bulk_begin(False, 20)
+    engine.bulk_push(len(r["start"]), r["start"], r["end"], r["chrom"], r["mapq"], r["flag"])
+    counts, st = engine.bulk_finish()
+    oc, os_ = te_oracle.bulk_count(H.oracle_index(idx), False, 20, r["start"].tolist(), r["end"].tolist(),
+                                   r["chrom"].tolist(), r["mapq"].tolist(), r["flag"].tolist())
+    assert counts.tolist() == oc and st[_lib.BS_ASSIGNED] == os_["assigned"]
+    engine.set_option("bulk_algo", -1)
 
 
 def test_bulk_deep_pileup_overflow_path(engine):
