@@ -363,7 +363,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "bulk_count_cell_kernel<%s> (+ bulk_slow_kernel on flagged units)" % ("paired" if paired else "single"),
-                         "cell_table_bytes": eng.get_info("stab_bytes"),
+                         "cell_table_bytes": eng.get_info("stab_bytes"), "slow_units_per_launch": eng.get_info("last_slow_units"),
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_record": bpr},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
             "stats": {"units": int(st[0]), "assigned": int(st[1]), "lowq": int(st[2]), "badchrom": int(st[3]),

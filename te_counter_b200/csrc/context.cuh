@@ -17,7 +17,7 @@ struct DevIndex {
     int64_t n_feat = 0, n_dir = 0;
     // cell table (stab_build.h); absent when the index exceeds its limits
     u32* st_sectors = nullptr;
-    int64_t* st_cell_base = nullptr;
+    uint2* st_cells = nullptr;            // per chromosome {first sector, number of cells}
     uint8_t* st_slot_type = nullptr;
     int st_shift = 11, st_all_counted = 1;
     bool has_stab = false;
@@ -25,7 +25,7 @@ struct DevIndex {
     int64_t st_primary = 0, st_overflow = 0, st_entries = 0;
     StabView stab_view() const {
         StabView v;
-        v.sectors = st_sectors; v.cell_base = st_cell_base; v.slot_type = st_slot_type;
+        v.sectors = st_sectors; v.cells = st_cells; v.slot_type = st_slot_type;
         v.shift = st_shift; v.all_counted = st_all_counted;
         return v;
     }
@@ -67,7 +67,7 @@ struct tec_ctx {
     bool bulk_active = false;
     int paired = 0, qual = 20;
     u64* d_counts = nullptr;              // n_ensg counters (slot order) + TEC_BULK_NSTATS statistics
-    u32* d_slow_bits = nullptr;           // one ballot word per 32 units of a launch (bulk_slow_kernel)
+    u32* d_slow_list = nullptr;           // [0] = count, then unit indices flagged for bulk_slow_kernel
     int64_t slow_cap = 0;                 // words
     std::vector<int32_t> ensg_of_slot;    // slot = rank of an ensg by number of feature rows
     // options (tec_set_option)
@@ -102,12 +102,12 @@ inline void tec_ctx::free_index() {
     DevIndex& ix = idx;
     cudaFree(ix.L); cudaFree(ix.R); cudaFree(ix.pmaxR); cudaFree(ix.info);
     cudaFree(ix.chrom_off); cudaFree(ix.dir); cudaFree(ix.dir_off);
-    cudaFree(ix.st_sectors); cudaFree(ix.st_cell_base); cudaFree(ix.st_slot_type);
+    cudaFree(ix.st_sectors); cudaFree(ix.st_cells); cudaFree(ix.st_slot_type);
     ix = DevIndex();
     cudaFree(d_counts);
     d_counts = nullptr;
-    cudaFree(d_slow_bits);
-    d_slow_bits = nullptr;
+    cudaFree(d_slow_list);
+    d_slow_list = nullptr;
     slow_cap = 0;
     has_index = false;
     bulk_active = false;

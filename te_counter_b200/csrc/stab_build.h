@@ -10,7 +10,9 @@
 //        slot_i   16 bits   w[i/2] >> 16*(i&1)                              (w0..w2)
 //        pos_i    22 bits   bit string w3..w7 at bit offset 22*i:  s | (len-1) << 11
 //                           s = interval start - cell start, len = clipped length
-//   header   28 bits   w7 >> 4:   n (3 bits) | has_link (1 bit) | link (24 bits)
+//   header   28 bits   w7 >> 4:   code (3 bits: 0..6 = number of entries, 7 = 6 entries + link)
+//                                 | dup (1 bit: two entries of this sector carry the same ensg)
+//                                 | link (24 bits: sector index of the overflow sector)
 //
 // Intervals of the same ensg are merged per chromosome first (union of [L, R)), so one ensg never
 // has two overlapping or touching entries; entries are sorted by start.  A cell with more than 6
@@ -43,7 +45,7 @@ struct StabTable {
     std::vector<int64_t> cell_base;      // n_chrom + 1
     std::vector<uint32_t> sectors;       // 8 words per sector: primary cells, then overflow sectors
     std::vector<uint8_t> slot_type;      // n_slots
-    int64_t n_primary = 0, n_overflow = 0, n_entries = 0, n_merged = 0, max_chain = 0;
+    int64_t n_primary = 0, n_overflow = 0, n_entries = 0, n_merged = 0, max_chain = 0, n_dup = 0;
     std::string why_not;                 // non-empty: no table (limits) -> the exact kernel is used
     size_t bytes() const { return sectors.size() * 4 + cell_base.size() * 8 + slot_type.size(); }
 };
@@ -64,7 +66,10 @@ inline void stab_pack_sector(uint32_t* w, const StabEntry* e, int n, bool has_li
         else if (off < 128) { hi |= pos << (off - 64); if (off + STAB_POS_BITS > 128) top |= pos >> (128 - off); }
         else top |= pos << (off - 128);
     }
-    const uint32_t header = (uint32_t)n | (has_link ? 8u : 0u) | (link << 4);
+    bool dup = false;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) dup |= e[i].slot == e[j].slot;
+    const uint32_t header = (has_link ? 7u : (uint32_t)n) | (dup ? 8u : 0u) | (link << 4);
     top |= (uint64_t)header << 4;                // bit 132 of the string = bit 4 of w7
     w[3] = (uint32_t)lo; w[4] = (uint32_t)(lo >> 32); w[5] = (uint32_t)hi; w[6] = (uint32_t)(hi >> 32);
     w[7] = (uint32_t)top;
@@ -152,6 +157,7 @@ inline void stab_build(StabTable& t, int n_chrom, const int64_t* chrom_off, cons
             const bool more = k + STAB_ENTRIES < j;
             const int64_t link = more ? next_over++ : 0;
             stab_pack_sector(&t.sectors[(size_t)sec * 8], &ent[k], n, more, (uint32_t)link);
+            if (t.sectors[(size_t)sec * 8 + 7] & 0x80u) t.n_dup++;
             sec = link;
         }
         i = j;
@@ -169,7 +175,8 @@ inline std::vector<uint32_t> stab_lookup(const StabTable& t, int c, int64_t x) {
     for (;;) {
         const uint32_t* w = &t.sectors[(size_t)sec * 8];
         const uint32_t header = w[7] >> 4;
-        const int n = (int)(header & 7u);
+        const bool has_link = (header & 7u) == 7u;
+        const int n = has_link ? STAB_ENTRIES : (int)(header & 7u);
         uint32_t last_s = 0;
         for (int i = 0; i < n; ++i) {
             const int off = STAB_POS_BITS * i;
@@ -181,7 +188,7 @@ inline std::vector<uint32_t> stab_lookup(const StabTable& t, int c, int64_t x) {
             last_s = st;
             if (r - st <= lm1) s.push_back((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
         }
-        if (!(header & 8u) || r < last_s) break;
+        if (!has_link || r < last_s) break;
         sec = header >> 4;
     }
     std::sort(s.begin(), s.end());

@@ -200,11 +200,14 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
         stab_build(st, n_chrom, chrom_off, L, R, fslot.data(), type_code, n_ensg, ctx->opt_stab_shift);
         if (st.why_not.empty()) {
             TEC_CUDA(cudaMalloc(&ix.st_sectors, std::max<size_t>(st.sectors.size(), 8) * 4));
-            TEC_CUDA(cudaMalloc(&ix.st_cell_base, st.cell_base.size() * 8));
+            std::vector<uint2> cells((size_t)std::max(n_chrom, 1));
+            for (int c = 0; c < n_chrom; ++c)
+                cells[(size_t)c] = make_uint2((unsigned)st.cell_base[(size_t)c], (unsigned)(st.cell_base[(size_t)c + 1] - st.cell_base[(size_t)c]));
+            TEC_CUDA(cudaMalloc(&ix.st_cells, cells.size() * sizeof(uint2)));
             TEC_CUDA(cudaMalloc(&ix.st_slot_type, st.slot_type.size()));
             if (!st.sectors.empty())
                 TEC_CUDA(cudaMemcpyAsync(ix.st_sectors, st.sectors.data(), st.sectors.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-            TEC_CUDA(cudaMemcpyAsync(ix.st_cell_base, st.cell_base.data(), st.cell_base.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            TEC_CUDA(cudaMemcpyAsync(ix.st_cells, cells.data(), cells.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
             TEC_CUDA(cudaMemcpyAsync(ix.st_slot_type, st.slot_type.data(), st.slot_type.size(), cudaMemcpyHostToDevice, ctx->stream));
             TEC_CUDA(cudaStreamSynchronize(ctx->stream));
             ix.st_shift = st.shift; ix.st_all_counted = st.all_counted; ix.has_stab = true; ix.stab_bytes = st.bytes();
@@ -233,40 +236,39 @@ extern "C" int tec_bulk_begin(tec_ctx* ctx, int paired, int qual) {
     return TEC_OK;
 }
 
-static int bulk_launch(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
-                       const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
-    const int64_t n_units = ctx->paired ? n_rec / 2 : n_rec;
-    if (n_units <= 0) return TEC_OK;
+#define TEC_LAUNCH_UNITS (int64_t(1) << 28)      // units per kernel launch (32-bit unit indices; slow list = 4 B per unit)
+
+static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, const int32_t* end,
+                           const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
     IndexView iv = ctx->idx.view();
     u64* counts = ctx->d_counts;
     u64* stats = ctx->d_counts + ctx->idx.n_ensg;
     const bool use_stab = ctx->idx.has_stab && ctx->opt_bulk_algo != 0;
-    if (ctx->opt_bulk_algo == 1 && !ctx->idx.has_stab) TEC_FAIL(TEC_ERR_STATE, "bulk_algo=1 but the index has no cell table");
     if (use_stab) {
         // fast kernel: one warp per 32 units, persistent grid; then the exact kernel on flagged units
         const int64_t n_tiles = (n_units + 31) / 32;
-        if (n_tiles > ctx->slow_cap) {
+        if (n_units + 1 > ctx->slow_cap) {
             TEC_CUDA(cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->d_slow_bits);
-            ctx->d_slow_bits = nullptr;
+            cudaFree(ctx->d_slow_list);
+            ctx->d_slow_list = nullptr;
             ctx->slow_cap = 0;
-            TEC_CUDA(cudaMalloc(&ctx->d_slow_bits, (size_t)n_tiles * 4));
-            ctx->slow_cap = n_tiles;
+            TEC_CUDA(cudaMalloc(&ctx->d_slow_list, (size_t)(n_units + 1) * 4));
+            ctx->slow_cap = n_units + 1;
         }
+        TEC_CUDA(cudaMemsetAsync(ctx->d_slow_list, 0, 4, ctx->stream));
         StabView sv = ctx->idx.stab_view();
-        const int wpb = BULK_THREADS / 32;
-        const int blocks = (int)std::min<int64_t>((n_tiles + wpb - 1) / wpb, (int64_t)ctx->n_sm * ctx->opt_ctas_per_sm);
+        const int blocks = (int)std::min<int64_t>((n_tiles + BULK_WARPS - 1) / BULK_WARPS, (int64_t)ctx->n_sm * ctx->opt_ctas_per_sm);
         if (ctx->paired)
-            bulk_count_cell_kernel<true><<<blocks, BULK_THREADS, 0, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, ctx->d_slow_bits);
+            bulk_count_cell_kernel<true><<<blocks, BULK_THREADS, 0, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, ctx->d_slow_list);
         else
-            bulk_count_cell_kernel<false><<<blocks, BULK_THREADS, 0, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, ctx->d_slow_bits);
+            bulk_count_cell_kernel<false><<<blocks, BULK_THREADS, 0, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, ctx->d_slow_list);
         ctx->launches++;
         TEC_CUDA(cudaGetLastError());
-        const int sblocks = (int)std::min<int64_t>((n_tiles + 255) / 256, (int64_t)ctx->n_sm * 8);
+        const int sblocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)ctx->n_sm * 8);
         if (ctx->paired)
-            bulk_slow_kernel<true><<<sblocks, 256, 0, ctx->stream>>>(iv, n_units, start, end, chrom, counts, stats, ctx->d_slow_bits);
+            bulk_slow_kernel<true><<<sblocks, 256, 0, ctx->stream>>>(iv, sv, 1, start, end, chrom, counts, stats, ctx->d_slow_list);
         else
-            bulk_slow_kernel<false><<<sblocks, 256, 0, ctx->stream>>>(iv, n_units, start, end, chrom, counts, stats, ctx->d_slow_bits);
+            bulk_slow_kernel<false><<<sblocks, 256, 0, ctx->stream>>>(iv, sv, 1, start, end, chrom, counts, stats, ctx->d_slow_list);
         ctx->launches++;
         TEC_CUDA(cudaGetLastError());
         return TEC_OK;
@@ -280,6 +282,20 @@ static int bulk_launch(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const 
         bulk_count_kernel<false><<<blocks, threads, 0, ctx->stream>>>(iv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats);
     ctx->launches++;
     TEC_CUDA(cudaGetLastError());
+    return TEC_OK;
+}
+
+static int bulk_launch(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
+                       const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
+    const int64_t n_units = ctx->paired ? n_rec / 2 : n_rec;
+    if (ctx->opt_bulk_algo == 1 && !ctx->idx.has_stab) TEC_FAIL(TEC_ERR_STATE, "bulk_algo=1 but the index has no cell table");
+    const int64_t rpu = ctx->paired ? 2 : 1;
+    for (int64_t off = 0; off < n_units; off += TEC_LAUNCH_UNITS) {
+        const int64_t n = std::min<int64_t>(TEC_LAUNCH_UNITS, n_units - off);
+        const int64_t r = off * rpu;
+        int rc = bulk_launch_one(ctx, n, start + r, end + r, chrom + r, mapq + r, flag + r);
+        if (rc) return rc;
+    }
     return TEC_OK;
 }
 
@@ -372,6 +388,13 @@ extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
     if (k == "stab_bytes") return (int64_t)ctx->idx.stab_bytes;
     if (k == "n_sm") return ctx->n_sm;
     if (k == "n_features") return ctx->idx.n_feat;
+    if (k == "last_slow_units") {          // units the last fast-kernel launch handed to the exact kernel
+        u32 n = 0;
+        if (!ctx->d_slow_list) return 0;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+        if (cudaMemcpy(&n, ctx->d_slow_list, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return (int64_t)n;
+    }
     if (k == "stab_primary") return ctx->idx.st_primary;
     if (k == "stab_overflow") return ctx->idx.st_overflow;
     if (k == "stab_entries") return ctx->idx.st_entries;

@@ -15,8 +15,8 @@ int main(int argc, char** argv) {
     int n_chrom = (int)off.size() - 1; uint32_t ns = 0; for (auto s : slot) ns = std::max(ns, s + 1);
     StabTable t; stab_build(t, n_chrom, off.data(), L.data(), R.data(), slot.data(), type.data(), (int)ns, shift);
     if (!t.why_not.empty()) { printf("not built: %s\n", t.why_not.c_str()); return 0; }
-    printf("shift %d: features %ld merged %ld entries %ld primary %ld overflow %ld max_chain %ld total %.1f MB\n", shift, (long)off[n_chrom],
-           (long)t.n_merged, (long)t.n_entries, (long)t.n_primary, (long)t.n_overflow, (long)t.max_chain, t.bytes() * 1e-6);
+    printf("shift %d: features %ld merged %ld entries %ld primary %ld overflow %ld max_chain %ld dup-sectors %ld total %.1f MB\n", shift, (long)off[n_chrom],
+           (long)t.n_merged, (long)t.n_entries, (long)t.n_primary, (long)t.n_overflow, (long)t.max_chain, (long)t.n_dup, t.bytes() * 1e-6);
     std::mt19937_64 rng(1); int bad = 0; long follow = 0, total = 0;
     for (int it = 0; it < 200000; ++it) {
         int c = rng() % n_chrom; int64_t lo = off[c], hi = off[c + 1]; if (hi == lo) continue;
@@ -25,7 +25,7 @@ int main(int argc, char** argv) {
             if (x < 0 || (x >> shift) >= t.cell_base[c + 1] - t.cell_base[c]) continue;
             const uint32_t* w = &t.sectors[(size_t)(t.cell_base[c] + (x >> shift)) * 8];
             uint32_t h = w[7] >> 4; total++;
-            if (h & 8u) { int n = h & 7; int o = 22 * (n - 1); int wi = 3 + o / 32; uint64_t b = (uint64_t)w[wi] | (wi + 1 < 8 ? (uint64_t)w[wi + 1] << 32 : 0); uint32_t ls = (uint32_t)(b >> (o % 32)) & 2047u; if ((uint32_t)(x & ((1 << shift) - 1)) >= ls) follow++; }
+            if ((h & 7u) == 7u) { int n = 6; int o = 22 * (n - 1); int wi = 3 + o / 32; uint64_t b = (uint64_t)w[wi] | (wi + 1 < 8 ? (uint64_t)w[wi + 1] << 32 : 0); uint32_t ls = (uint32_t)(b >> (o % 32)) & 2047u; if ((uint32_t)(x & ((1 << shift) - 1)) >= ls) follow++; }
             continue;
         }
         std::set<uint32_t> want;
