@@ -1,0 +1,114 @@
+"""Parity of the CUDA single-cell path (through the C ABI) with the reference's outputs (golden
+cases, incl. multi-bundle and hash-order-ambiguous inputs under the canonical rule) and with the
+CPU oracle on larger seeded inputs."""
+import numpy as np
+import pytest
+
+import helpers as H
+from te_counter_b200 import synth
+from oracle import te_oracle
+from te_counter_b200 import _lib
+from test_host_mirror import run_sc_case
+
+pytestmark = pytest.mark.gpu
+
+COLS = ("start", "end", "chrom", "mapq", "flag", "cell", "umi")
+
+
+@pytest.fixture(scope="module")
+def engine():
+    eng = _lib.Engine(0)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("name", H.case_names("sc"))
+def test_sc_golden_through_mirror(monkeypatch, tmp_path, name):
+    run_sc_case(monkeypatch, tmp_path, name, _lib.Engine, batch=1000)
+
+
+def run_engine(engine, r, qual, strand, n_wl, bundle_keys, maxcells, pad, chunks=1):
+    engine.sc_begin(qual, strand, n_wl)
+    n = len(r["start"])
+    step = (n + chunks - 1) // chunks if n else 1
+    for a in range(0, max(n, 1), step):
+        b = min(n, a + step)
+        engine.sc_push(b - a, *[np.ascontiguousarray(r[k][a:b]) for k in COLS])
+    nt, nh = engine.sc_finalize(bundle_keys, maxcells, pad)
+    ensg, cell, count, hcell, hcount, st = engine.sc_fetch(nt, nh)
+    sel = engine.sc_select(maxcells, nh)
+    return ensg, cell, count, hcell, hcount, st, sel
+
+
+def check_against_oracle(engine, idx, r, qual, strand, n_wl, bundle_keys, maxcells, pad, chunks=1):
+    ensg, cell, count, hcell, hcount, st, sel = run_engine(engine, r, qual, strand, n_wl, bundle_keys, maxcells, pad, chunks)
+    out = te_oracle.sc_count(H.oracle_index(idx), qual, strand, bundle_keys, maxcells, pad, *[r[k].tolist() for k in COLS])
+    got = {(int(e), int(c)): int(v) for e, c, v in zip(ensg, cell, count)}
+    assert got == out["triples"]
+    assert list(zip(ensg.tolist(), cell.tolist())) == sorted(got)                 # sorted by (ensg, cell)
+    assert list(zip(hcell.tolist(), hcount.tolist())) == sorted(out["cell_hits"])
+    s = out["stats"]
+    assert int(st[_lib.SS_UNITS]) + 1 == s["total_reads"]
+    for k, f in ((_lib.SS_INVALID_BARCODE, "invalid_barcode"), (_lib.SS_ALREADY_SEEN, "already_seen"),
+                 (_lib.SS_LOWQ, "lowq"), (_lib.SS_QCFAIL, "qcfail"), (_lib.SS_VALID, "valid"),
+                 (_lib.SS_ASSIGNED, "assigned"), (_lib.SS_RAW_BARCODES, "raw_barcodes"), (_lib.SS_BUNDLES, "n_bundles")):
+        assert int(st[k]) == s[f], f
+    want_sel = sorted(out["cell_hits"], key=lambda t: (-t[1], t[0]))[:maxcells]
+    assert sel.tolist() == [c for c, _ in want_sel]
+    return out
+
+
+@pytest.mark.parametrize("strand", [False, True])
+@pytest.mark.parametrize("bundle_keys,maxcells,pad", [(10_000_000, 50, 20), (700, 50, 20), (64, 20, 5), (5, 200, 1000)])
+def test_sc_matches_oracle_seeded(engine, strand, bundle_keys, maxcells, pad):
+    idx = synth.synth_index(11, n_te=30000, n_exon=9000, n_gene=600, chrom_len=3_000_000, n_chrom=3)
+    r = synth.synth_sc_reads(12, idx, 30000, n_whitelist=300, n_cells=60, umis_per_cell=40)
+    engine.upload_index(idx)
+    out = check_against_oracle(engine, idx, r, 20, strand, 300, bundle_keys, maxcells, pad, chunks=3)
+    assert out["stats"]["assigned"] > 20
+
+
+def test_sc_many_places_per_key(engine):
+    """Keys seen on several chromosome:strand combinations with repeated and re-ordered fragments:
+    exercises the first-inserted rule, the set semantics and 'later fragment wins' of Part 3."""
+    rng = np.random.default_rng(5)
+    idx = synth.synth_index(13, n_te=20000, n_exon=5000, n_gene=300, chrom_len=1_000_000, n_chrom=4)
+    n = 20000
+    feat = rng.integers(0, idx.n_features, size=n)
+    place = rng.integers(0, 40, size=n)                     # few places -> many repeats
+    pf = rng.integers(0, idx.n_features, size=40)
+    start = (idx.L[pf[place]] + rng.integers(-3, 4, size=n)).clip(0).astype(np.int32)
+    r = {"start": start, "end": (start + 90).astype(np.int32), "chrom": idx.chrom_id[pf[place]].astype(np.uint16),
+         "mapq": np.full(n, 60, np.uint8), "flag": (rng.integers(0, 2, size=n) * 8).astype(np.uint8),
+         "cell": rng.integers(0, 12, size=n).astype(np.uint32),
+         "umi": (rng.integers(1, 30, size=n).astype(np.uint64) << np.uint64(40))}
+    del feat
+    engine.upload_index(idx)
+    for strand in (False, True):
+        for bk in (10_000_000, 50):
+            check_against_oracle(engine, idx, r, 20, strand, 12, bk, 8, 2)
+
+
+def test_sc_empty_and_all_filtered(engine):
+    idx = synth.synth_index(11, n_te=3000, n_exon=900, n_gene=60, chrom_len=300_000, n_chrom=2)
+    engine.upload_index(idx)
+    engine.sc_begin(20, False, 10)
+    nt, nh = engine.sc_finalize(100, 5, 5)
+    assert (nt, nh) == (0, 0)
+    _, _, _, _, _, st = engine.sc_fetch(nt, nh)
+    assert st[_lib.SS_UNITS] == 0 and st[_lib.SS_VALID] == 0
+    r = synth.synth_sc_reads(3, idx, 500, n_whitelist=10, n_cells=5, umis_per_cell=10)
+    r["mapq"][:] = 0
+    ensg, cell, count, hcell, hcount, st, sel = run_engine(engine, r, 20, False, 10, 100, 5, 5)
+    assert len(ensg) == 0 and len(hcell) == 0 and st[_lib.SS_UNITS] == 500 and st[_lib.SS_VALID] == 0
+    assert st[_lib.SS_LOWQ] + st[_lib.SS_QCFAIL] == 500
+
+
+def test_sc_push_chunking_invariance(engine):
+    idx = synth.synth_index(11, n_te=30000, n_exon=9000, n_gene=600, chrom_len=3_000_000, n_chrom=3)
+    r = synth.synth_sc_reads(14, idx, 50000, n_whitelist=500, n_cells=80, umis_per_cell=60)
+    engine.upload_index(idx)
+    a = run_engine(engine, r, 20, True, 500, 3000, 40, 10, chunks=1)
+    b = run_engine(engine, r, 20, True, 500, 3000, 40, 10, chunks=7)
+    for x, y in zip(a, b):
+        assert (x == y).all()
