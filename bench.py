@@ -376,7 +376,146 @@ def run_ours(args):
 
 
 def run_ours_sc(args, rank, world, local, dev):
-    raise SystemExit("sc workload bench: not wired yet")
+    """BASELINE.json configs[4]: one step = tec_sc_begin + tec_sc_push_dev (filter, whitelist,
+    compaction) + tec_sc_finalize (UMI collapse, Part-2 rule, overlap, tally) + tec_sc_select."""
+    import torch
+    import torch.distributed as dist
+    from te_counter_b200 import _lib, synth
+    if world > 1:
+        raise SystemExit("sc workload: multi-GPU sharding by cell is not wired yet (DESIGN.md, next)")
+    n_rec = args.records or CONFIG_RECORDS["sc"]
+    n_wl, maxcells, pad, bundle_keys = 100_000, 10_000, 1000, 10_000_000
+    idx = make_index(args.index_scale)
+    eng = _lib.Engine(local)
+    eng.upload_index(idx)
+    parts = max(1, (n_rec + 124_999_999) // 125_000_000)
+    names = ("start", "end", "chrom", "mapq", "flag", "cell", "umi")
+    chunks = {k: [] for k in names}
+    for p in range(parts):
+        n_p = n_rec // parts + (1 if p < n_rec % parts else 0)
+        r = synth.synth_sc_reads(synth.SEED, idx, n_p, n_whitelist=n_wl, device=dev, as_numpy=False, part=(p, parts))
+        for k in names:
+            chunks[k].append(r[k])
+        del r
+    cols = [torch.cat(chunks[k]) if parts > 1 else chunks[k][0] for k in names]
+    del chunks
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    ptrs = [t.data_ptr() for t in cols]
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+    strand = True
+
+    def step():
+        eng.sc_begin(20, strand, n_wl)
+        eng.sc_push_dev(n_rec, *ptrs)
+        nt, nh = eng.sc_finalize(bundle_keys, maxcells, pad)
+        sel = eng.sc_select(maxcells, nh)
+        return nt, nh, sel
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    eng.sync()
+    K = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = eng.launch_count()
+    eng.sync()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    e0.record(ext)
+    for _ in range(K):
+        nt, nh, sel = step()
+    e1.record(ext)
+    eng.sync()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    launches = eng.launch_count() - l0
+    ms_step = e0.elapsed_time(e1) / K
+    value = n_rec / (ms_step / 1e3)
+    ensg, cell, count, hcell, hcount, st = eng.sc_fetch(nt, nh)
+
+    e2e = None
+    if not args.no_e2e:
+        dts = (np.int32, np.int32, np.uint16, np.uint8, np.uint8, np.uint32, np.uint64)
+        host = [eng.pinned(n_rec, dt) for dt in dts]
+        for h, t in zip(host, cols):
+            hv = h.view(np.int16) if h.dtype == np.uint16 else h.view(np.int32) if h.dtype == np.uint32 else \
+                h.view(np.int64) if h.dtype == np.uint64 else h
+            tv = t.view(torch.int16) if t.dtype == torch.uint16 else t.view(torch.int32) if t.dtype == torch.uint32 else \
+                t.view(torch.int64) if t.dtype == torch.uint64 else t
+            torch.from_numpy(hv).copy_(tv)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            eng.sc_begin(20, strand, n_wl)
+            eng.sc_push(n_rec, *host)
+            a, b = eng.sc_finalize(bundle_keys, maxcells, pad)
+            out = eng.sc_fetch(a, b)
+            return out, eng.sc_select(maxcells, b)
+
+        e2e_step()
+        ta = time.perf_counter()
+        for _ in range(K):
+            out2, sel2 = e2e_step()
+        dt = (time.perf_counter() - ta) / K
+        e2e = {"value": n_rec / dt, "unit": "records/s", "h2d_bytes_per_step": int(n_rec) * 24,
+               "d2h_bytes_per_step": int(len(out2[0]) * 16 + len(out2[3]) * 12 + _lib.SC_NSTATS * 8 + len(sel2) * 4),
+               "ms_per_step": dt * 1e3,
+               "api": "tec_sc_begin + tec_sc_push(host SoA, pinned) + tec_sc_finalize + tec_sc_fetch + tec_sc_select"}
+        assert (out2[0] == ensg).all() and (out2[2] == count).all(), "e2e triples differ from the device-resident run"
+        del host
+
+    cpu = None
+    parity = None
+    if not args.no_cpu:
+        from oracle import te_oracle
+        ns = min(n_rec, args.cpu_sample)
+        sample = [t[:ns].cpu().numpy() for t in cols]
+        sample[2] = sample[2].view(np.uint16)
+        sample[5] = sample[5].view(np.uint32)
+        sample[6] = sample[6].view(np.uint64)
+        eng.sc_begin(20, strand, n_wl)
+        eng.sc_push(ns, *[np.ascontiguousarray(a) for a in sample])
+        a, b = eng.sc_finalize(bundle_keys, maxcells, pad)
+        g_ensg, g_cell, g_count, g_hc, g_hn, g_st = eng.sc_fetch(a, b)
+        oidx = te_oracle.Index(idx.chrom_id, idx.L, idx.R, idx.ensg_id, idx.type_code, idx.strand_code,
+                               idx.n_ensg, idx.bucket_size)
+        lists = [x.tolist() for x in sample]
+        ta = time.perf_counter()
+        out = te_oracle.sc_count(oidx, 20, strand, bundle_keys, maxcells, pad, *lists)
+        tb = time.perf_counter()
+        got = {(int(e), int(c)): int(v) for e, c, v in zip(g_ensg, g_cell, g_count)}
+        ok = got == out["triples"] and list(zip(g_hc.tolist(), g_hn.tolist())) == sorted(out["cell_hits"]) and \
+            int(g_st[_lib.SS_VALID]) == out["stats"]["valid"] and int(g_st[_lib.SS_ASSIGNED]) == out["stats"]["assigned"]
+        parity = {"sample_records": ns, "bit_exact": bool(ok)}
+        cpu = {"value": ns / (tb - ta), "unit": "records/s", "cores": 1, "kind": "port",
+               "host_cores_available": os.cpu_count(),
+               "sample": "first %d records of this workload; pure-Python restatement of sc_parse_bamse "
+                         "(oracle/te_oracle.py), single thread as the reference; BAM decode and index load excluded" % ns}
+
+    peak, peak_src = load_peaks()
+    bpr = BYTES_PER_RECORD["sc"] + INDEX_BYTES_PER_FEATURE * idx.n_features / float(n_rec)
+    achieved = n_rec * bpr / (ms_step / 1e3) / 1e9
+    line = {"metric": "reads_per_sec", "value": value, "unit": "records/s", "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": dict(workload_config(args, n_rec, world), n_whitelist=n_wl, maxcells=maxcells, strand=strand,
+                           bundle_keys=bundle_keys),
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "whole sc step (radix sort passes dominate; see profiles/)", "kernel_ms": ms_step,
+                         "algorithmic_bytes_per_record": bpr},
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
+            "stats": {"units": int(st[_lib.SS_UNITS]), "survivors": int(st[_lib.SS_SURVIVORS]),
+                      "segments": int(st[_lib.SS_SEGMENTS]), "bundles": int(st[_lib.SS_BUNDLES]),
+                      "valid": int(st[_lib.SS_VALID]), "assigned": int(st[_lib.SS_ASSIGNED]),
+                      "triples": int(nt), "hit_cells": int(nh), "selected": int(len(sel))}}
+    print(json.dumps(line))
+    eng.close()
 
 
 def main():

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "bulk.cuh"
+#include <map>
 
 #define TEC_STAGE_RECORDS (int64_t(16) << 20)     // records per host->device staging chunk
 
@@ -50,6 +51,47 @@ struct StageSlot {
 
 struct ScState;      // sc.cuh
 
+// Size-keyed cache of device blocks: the single-cell finalize asks for the same sequence of
+// temporaries on every call, and cudaMalloc / cudaFree (a device-wide synchronisation each) would
+// otherwise sit inside the timed path.
+struct DevCache {
+    std::multimap<size_t, void*> free_blocks;
+    std::map<void*, size_t> live;
+    size_t cached_bytes = 0;
+    cudaError_t get(void** out, size_t bytes) {
+        bytes = (std::max<size_t>(bytes, 1) + 511) & ~size_t(511);
+        auto it = free_blocks.lower_bound(bytes);
+        if (it != free_blocks.end() && it->first <= bytes + (bytes >> 2) + (size_t(1) << 20)) {
+            *out = it->second;
+            live[*out] = it->first;
+            cached_bytes -= it->first;
+            free_blocks.erase(it);
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(out, bytes);
+        }
+        if (e == cudaSuccess) live[*out] = bytes;
+        return e;
+    }
+    void put(void* p) {
+        if (!p) return;
+        auto it = live.find(p);
+        if (it == live.end()) { cudaFree(p); return; }
+        free_blocks.emplace(it->second, p);
+        cached_bytes += it->second;
+        live.erase(it);
+    }
+    void trim() {
+        for (auto& kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+};
+
 struct tec_ctx {
     int device = 0;
     int n_sm = 148;
@@ -82,12 +124,13 @@ struct tec_ctx {
     int stage_next = 0;
 
     ScState* sc = nullptr;
+    DevCache cache;
 
     int ensure_stage(int64_t n, bool sc_layout);
     void free_stage();
     void free_index();
     void free_sc();
-    void free_all() { free_stage(); free_index(); free_sc(); }
+    void free_all() { free_stage(); free_index(); free_sc(); cache.trim(); }
 };
 
 inline void tec_ctx::free_stage() {

@@ -57,8 +57,8 @@ struct ScState {
     int64_t stats[TEC_SC_NSTATS] = {0};
 };
 
-static void sc_free_results(ScState* s) {
-    cudaFree(s->t_ensg); cudaFree(s->t_cell); cudaFree(s->t_count); cudaFree(s->h_cell); cudaFree(s->h_count);
+static void sc_free_results(tec_ctx* ctx, ScState* s) {
+    ctx->cache.put(s->t_ensg); ctx->cache.put(s->t_cell); ctx->cache.put(s->t_count); ctx->cache.put(s->h_cell); ctx->cache.put(s->h_count);
     s->t_ensg = nullptr; s->t_cell = nullptr; s->t_count = nullptr; s->h_cell = nullptr; s->h_count = nullptr;
     s->n_triples = s->n_hit = 0;
 }
@@ -67,24 +67,27 @@ inline void tec_ctx::free_sc() {
     if (!sc) return;
     cudaFree(sc->cell); cudaFree(sc->umi); cudaFree(sc->left); cudaFree(sc->rite); cudaFree(sc->cs);
     cudaFree(sc->d_stats); cudaFree(sc->pos); cudaFree(sc->cub_tmp);
-    sc_free_results(sc);
+    sc_free_results(this, sc);
     delete sc;
     sc = nullptr;
 }
 
-// every temporary of finalize goes through this and is released at the end (also on errors)
+// every temporary of finalize goes through this and goes back to the context's block cache at the
+// end (also on errors)
 struct ScArena {
+    DevCache& cache;
     std::vector<void*> ptrs;
-    ~ScArena() { for (void* p : ptrs) cudaFree(p); }
+    explicit ScArena(DevCache& c) : cache(c) {}
+    ~ScArena() { for (void* p : ptrs) cache.put(p); }
     template <class T> cudaError_t get(T** out, size_t count) {
         void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        cudaError_t e = cache.get(&p, std::max<size_t>(count, 1) * sizeof(T));
         if (e == cudaSuccess) ptrs.push_back(p);
         *out = (T*)p;
         return e;
     }
     void release(void* p) {
-        for (auto& q : ptrs) if (q == p) { cudaFree(p); q = nullptr; }
+        for (auto& q : ptrs) if (q == p && p) { cache.put(p); q = nullptr; }
     }
 };
 
@@ -466,7 +469,7 @@ extern "C" int tec_sc_begin(tec_ctx* ctx, int qual, int strand, int64_t n_whitel
     TEC_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->sc) ctx->sc = new ScState();
     ScState* s = ctx->sc;
-    sc_free_results(s);
+    sc_free_results(ctx, s);
     s->qual = qual; s->strand = strand ? 1 : 0; s->n_wl = n_whitelist;
     s->n = 0; s->units = 0; s->active = true; s->finalized = false;
     if (!s->d_stats) TEC_CUDA(cudaMalloc(&s->d_stats, TEC_SC_NSTATS * 8));
@@ -634,8 +637,8 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
     if (bundle_keys < 1 || maxcells < 0 || pad < 0) TEC_FAIL(TEC_ERR_ARG, "tec_sc_finalize: bad arguments");
     TEC_CUDA(cudaSetDevice(ctx->device));
     TEC_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    sc_free_results(s);
-    ScArena A;
+    sc_free_results(ctx, s);
+    ScArena A(ctx->cache);
     const int64_t N = s->n, W = std::max<int64_t>(s->n_wl, 1);
     if (N >= (int64_t)0x7FFFFFF0) TEC_FAIL(TEC_ERR_LIMIT, "single-cell path: more than 2^31 surviving records on one GPU");
     int64_t n_b = 0;
@@ -834,9 +837,9 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
             TEC_CUDA(cudaMemcpyAsync(&h_runs, d_nruns, 4, cudaMemcpyDeviceToHost, ctx->stream));
             TEC_CUDA(cudaStreamSynchronize(ctx->stream));
             s->n_triples = h_runs;
-            TEC_CUDA(cudaMalloc(&s->t_ensg, std::max<size_t>(h_runs, 1) * 4));
-            TEC_CUDA(cudaMalloc(&s->t_cell, std::max<size_t>(h_runs, 1) * 4));
-            TEC_CUDA(cudaMalloc(&s->t_count, std::max<size_t>(h_runs, 1) * 8));
+            TEC_CUDA(ctx->cache.get((void**)&s->t_ensg, std::max<size_t>(h_runs, 1) * 4));
+            TEC_CUDA(ctx->cache.get((void**)&s->t_cell, std::max<size_t>(h_runs, 1) * 4));
+            TEC_CUDA(ctx->cache.get((void**)&s->t_count, std::max<size_t>(h_runs, 1) * 8));
             if (h_runs) sc_split_kernel<<<SC_GRID(h_runs)>>>(h_runs, ukeys, ucnt, s->t_ensg, s->t_cell, s->t_count);
             ctx->launches += 8;
         }
@@ -853,8 +856,8 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         TEC_CUDA(cudaMemcpyAsync(&h_n, nz + W, 4, cudaMemcpyDeviceToHost, ctx->stream));
         TEC_CUDA(cudaStreamSynchronize(ctx->stream));
         s->n_hit = h_n;
-        TEC_CUDA(cudaMalloc(&s->h_cell, std::max<size_t>(h_n, 1) * 4));
-        TEC_CUDA(cudaMalloc(&s->h_count, std::max<size_t>(h_n, 1) * 8));
+        TEC_CUDA(ctx->cache.get((void**)&s->h_cell, std::max<size_t>(h_n, 1) * 4));
+        TEC_CUDA(ctx->cache.get((void**)&s->h_count, std::max<size_t>(h_n, 1) * 8));
         if (h_n) sc_hitcells_kernel<<<SC_GRID(W)>>>(W, hits, nz, s->h_cell, s->h_count);
         ctx->launches += 2;
     }
@@ -904,7 +907,7 @@ extern "C" int tec_sc_select(tec_ctx* ctx, int64_t maxcells, uint32_t* cells_out
     const int64_t n = s->n_hit, take = std::min(n, maxcells);
     if (n_out) *n_out = take;
     if (!take) return TEC_OK;
-    ScArena A;
+    ScArena A(ctx->cache);
     u64 *key = nullptr, *key_s = nullptr;
     u32* cell_s = nullptr;
     TEC_CUDA(A.get(&key, (size_t)n));

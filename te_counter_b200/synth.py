@@ -151,10 +151,12 @@ def synth_bulk_reads(seed, idx, n_records, paired, device="cpu", edge_frac=0.001
 
 
 def synth_sc_reads(seed, idx, n_records, n_whitelist=100_000, n_cells=10_000, umis_per_cell=10_000,
-                   umi_len=12, device="cpu", as_numpy=None, sort=True):
+                   umi_len=12, device="cpu", as_numpy=None, sort=True, part=(0, 1)):
     """SURVEY.md 8(d) single-cell reads: coordinate-sorted; `n_cells` real cells take 90 % of the
     reads (lognormal sizes), the other whitelist barcodes 8 %, 2 % not whitelisted; ~umis_per_cell
-    distinct UMIs per real cell; 1 % of (cell, UMI) keys get a second chromosome/strand."""
+    distinct UMIs per real cell; 1 % of (cell, UMI) keys get a second chromosome/strand.
+    part=(p, P): the p-th of P consecutive genome slices of one coordinate-sorted file -- every
+    (cell, UMI) key lives in exactly one slice, so concatenating the parts gives the whole file."""
     torch = _torch()
     dev = torch.device(device)
     g = torch.Generator(device=dev)
@@ -173,7 +175,12 @@ def synth_sc_reads(seed, idx, n_records, n_whitelist=100_000, n_cells=10_000, um
     cell = torch.where(r >= 0.98, torch.full_like(cell, 0xFFFFFFFF), cell)
     del cell_real, cell_bg
     # UMI: a per-(cell, k) pseudo-random 12-mer over ACGT; k < umis_per_cell
-    k = torch.randint(0, umis_per_cell, (n,), generator=g, device=dev)
+    p_i, p_n = part
+    if p_n > 1:
+        g.manual_seed(int(seed) * 1009 + p_i)                    # same cells in every part, new reads
+        k = torch.randint(0, max(1, umis_per_cell // p_n), (n,), generator=g, device=dev) * p_n + ((p_i - cell) % p_n)
+    else:
+        k = torch.randint(0, umis_per_cell, (n,), generator=g, device=dev)
     h = (cell * 1000003 + k * 7919 + 12345) & 0x7FFFFFFFFFFF
     h = (h * 6364136223846793005 + 1442695040888963407) & 0x7FFFFFFFFFFFFFFF
     code = torch.zeros(n, dtype=torch.int64, device=dev)
@@ -184,9 +191,18 @@ def synth_sc_reads(seed, idx, n_records, n_whitelist=100_000, n_cells=10_000, um
     code = code << (3 * (21 - umi_len))
     # the read's place is a function of the key (a UMI tags one molecule) + small jitter; 1 % of
     # keys jump to a second place
-    hk = (h >> 3) % idx.n_features
-    second = ((h >> 40) % 100 == 0) & (rnd(n) < 0.5)
-    hk = torch.where(second, (hk * 31 + 17) % idx.n_features, hk)
+    if p_n > 1:
+        order = torch.from_numpy(idx.sorted_layout()["order"]).to(dev)
+        f_lo, f_hi = idx.n_features * p_i // p_n, idx.n_features * (p_i + 1) // p_n
+        span = max(1, f_hi - f_lo)
+        hk = f_lo + (h >> 3) % span
+        second = ((h >> 40) % 100 == 0) & (rnd(n) < 0.5)
+        hk = order[torch.where(second, f_lo + ((hk - f_lo) * 31 + 17) % span, hk)]
+        del order
+    else:
+        hk = (h >> 3) % idx.n_features
+        second = ((h >> 40) % 100 == 0) & (rnd(n) < 0.5)
+        hk = torch.where(second, (hk * 31 + 17) % idx.n_features, hk)
     chrom = fC[hk].to(torch.int64)
     start = (fL[hk].to(torch.int64) + torch.randint(-60, 61, (n,), generator=g, device=dev)).clamp(min=0)
     end = start + 91
