@@ -206,15 +206,11 @@ def workload_config(args, n_rec_per_gpu, world):
 
 
 # ------------------------------------------------------------------------------ our arm
-class _DevArray:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from te_counter_b200 import _lib, synth
+    from te_counter_b200 import dist as tdist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,7 +237,7 @@ def run_ours(args):
     ptrs = [t.data_ptr() for t in cols]
     torch.cuda.synchronize()
     ext = torch.cuda.ExternalStream(eng.stream, device=dev)
-    counts_t = torch.as_tensor(_DevArray(eng.bulk_counts_dev(), idx.n_ensg + _lib.BULK_NSTATS, "<i8"), device=dev)
+    counts_t = tdist.counts_tensor(eng, idx.n_ensg, dev)
 
     def step():
         eng.bulk_begin(paired, 20)
