@@ -504,6 +504,7 @@ def run_ours_sc(args, rank, world, local, dev):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "kernel": "whole sc step (radix sort passes dominate; see profiles/)", "kernel_ms": ms_step,
+                         "sc_cell_table": bool(eng.get_info("has_sc_stab")), "sc_cell_table_bytes": eng.get_info("sc_stab_bytes"),
                          "algorithmic_bytes_per_record": bpr},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
             "stats": {"units": int(st[_lib.SS_UNITS]), "survivors": int(st[_lib.SS_SURVIVORS]),

@@ -180,6 +180,7 @@ bulk_count_kernel(IndexView iv, int64_t n_units, int qual,
 struct StabView {
     const u32* sectors;          // 8 words per sector, 32-byte aligned
     const uint2* cells;          // per chromosome: {first sector, number of cells}
+    const u32* ovf_base;         // per 256 primary sectors: first overflow sector
     const uint8_t* slot_type;    // n_slots
     int shift;
     int all_counted;
@@ -193,7 +194,7 @@ struct StabView {
 #endif
 #define BULK_WARPS (BULK_THREADS / 32)
 #define BULK_QCAP 64             // deferred-unit ring per warp (entries)
-#define R_NONE 0xFFFFu           // "no point in this sector": (R_NONE - start) > any length
+#define R_NONE 0x7FFFu           // "no point in this sector": fails the e >= r test of every entry
 
 struct Sector { u32 w[8]; };
 
@@ -238,60 +239,47 @@ __device__ __forceinline__ u32 ld_stream_u8(const uint8_t* p, u64 pol) {
     return r;
 }
 
-// bit i set <=> entry i of the sector contains point ra or rb (cell-relative, R_NONE = no point).
-// last_s = start of entry 5 (the link test of stab_build.h).
-__device__ __forceinline__ u32 sector_hits(const Sector& s, u32 ra, u32 rb, u32& last_s) {
-    const u32 M = (1u << 22) - 1;
-    u32 pos[6];
-    pos[0] = s.w[3] & M;
-    pos[1] = __funnelshift_r(s.w[3], s.w[4], 22) & M;
-    pos[2] = __funnelshift_r(s.w[4], s.w[5], 12) & M;
-    pos[3] = (s.w[5] >> 2) & M;
-    pos[4] = __funnelshift_r(s.w[5], s.w[6], 24) & M;
-    pos[5] = __funnelshift_r(s.w[6], s.w[7], 14) & M;
-    u32 hit = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const u32 st = pos[i] & 2047u, lm1 = pos[i] >> 11;
-        hit |= (u32)((ra - st <= lm1) | (rb - st <= lm1)) << i;
-    }
-    last_s = pos[5] & 2047u;
-    const u32 code = (s.w[7] >> 4) & 7u;
-    return hit & ((code == 7u) ? 63u : ((1u << code) - 1u));
+// A point r (cell-relative, < 2^11, or R_NONE) prepared for the 16-bit-lane test of stab_build.h:
+// bit 15 of each lane of (xg - w_s) says r >= s, of (w_e + kg) says e >= r.
+struct PointK { u32 xg, kg; };
+__device__ __forceinline__ PointK make_point(u32 r) {
+    const u32 rr = r * 0x10001u;
+    PointK p;
+    p.xg = rr + 0x80008000u;
+    p.kg = 0x80008000u - rr;
+    return p;
 }
-__device__ __forceinline__ u32 sector_slot(const Sector& s, int i) {
-    const u32 pair = (i < 2) ? s.w[0] : ((i < 4) ? s.w[1] : s.w[2]);
-    return (pair >> ((i & 1) << 4)) & 0xFFFFu;
+// hit mask of a sector for points a or b.  Bit positions: entry 0 -> 15, 1 -> 31, 2 -> 14, 3 -> 30, 4 -> 13.
+#define HB0 (1u << 15)
+#define HB1 (1u << 31)
+#define HB2 (1u << 14)
+#define HB3 (1u << 30)
+#define HB4 (1u << 13)
+__device__ __forceinline__ u32 sector_hits(const Sector& s, const PointK a, const PointK b) {
+    const u32 a0 = ((a.xg - s.w[0]) & (s.w[3] + a.kg)) | ((b.xg - s.w[0]) & (s.w[3] + b.kg));
+    const u32 a1 = ((a.xg - s.w[1]) & (s.w[4] + a.kg)) | ((b.xg - s.w[1]) & (s.w[4] + b.kg));
+    const u32 a2 = ((a.xg - s.w[2]) & (s.w[5] + a.kg)) | ((b.xg - s.w[2]) & (s.w[5] + b.kg));
+    return (a0 & 0x80008000u) | ((a1 & 0x80008000u) >> 1) | ((a2 & 0x8000u) >> 2);
 }
 template <int I>
 __device__ __forceinline__ u32 sector_slot_c(const Sector& s) {
-    return (I & 1) ? (s.w[I >> 1] >> 16) : (s.w[I >> 1] & 0xFFFFu);
+    return I == 0 ? (s.w[6] & 0xFFFFu) : I == 1 ? (s.w[6] >> 16) : I == 2 ? (s.w[7] & 0xFFFFu) : I == 3 ? (s.w[7] >> 16) : (s.w[5] >> 16);
 }
-__device__ __forceinline__ bool sector_has_link(const Sector& s) { return ((s.w[7] >> 4) & 7u) == 7u; }
-__device__ __forceinline__ bool sector_has_dup(const Sector& s) { return (s.w[7] >> 7) & 1u; }
-__device__ __forceinline__ u32 sector_link(const Sector& s) { return s.w[7] >> 8; }
+__device__ __forceinline__ bool sector_more(const Sector& s) { return (s.w[2] >> 16) & 1u; }
+// two hit entries that both have a twin (same ensg elsewhere in the sector): the ensg may be hit twice
+__device__ __forceinline__ bool sector_twin_hit(const Sector& s, u32 hit) {
+    const u32 m5 = ((hit >> 13) & 7u) | ((hit >> 27) & 0x18u);          // e4, e2, e0, e3, e1
+    return __popc(m5 & (s.w[2] >> 17)) >= 2;
+}
+__device__ __forceinline__ u32 sector_link(const Sector& s) { return s.w[2] >> 22; }
+__device__ __forceinline__ u32 sector_last_s(const Sector& s) { return s.w[2] & 0xFFFFu; }
 
-// distinct ensg slots of one unit (registers only)
-struct SlotSet {
-    u32 v0, v1, v2, v3;
-    int n;
-    __device__ __forceinline__ void clear() { v0 = v1 = v2 = v3 = 0xFFFFFFFFu; n = 0; }
-    // branch-free: `on` gates the whole insertion
-    __device__ __forceinline__ void add(u32 w, bool on) {
-        const bool fresh = on & !((v0 == w) | (v1 == w) | (v2 == w) | (v3 == w));
-        v0 = (fresh & (n == 0)) ? w : v0;
-        v1 = (fresh & (n == 1)) ? w : v1;
-        v2 = (fresh & (n == 2)) ? w : v2;
-        v3 = (fresh & (n == 3)) ? w : v3;
-        n += fresh;                                      // n > STAB_MAXD: overflow
-    }
-};
-
-// x % 10000 == 0 for x >= 0 (negative x answers true: the exact kernel then decides):
-// 10000 = 16 * 625, and for odd d  n % d == 0  <=>  n * d^-1 (mod 2^32) <= (2^32 - 1) / d
+// x % 10000 == 0 (as unsigned; a negative position never hits anything in either path, so its
+// answer does not matter): 10000 = 2^4 * 625, and n % (2^k * d) == 0  <=>
+// rotr(n * d^-1 mod 2^32, k) <= (2^32 - 1) / (2^k * d)
 __device__ __forceinline__ bool mult_of_10000(int x) {
-    const u32 ux = (u32)x;
-    return (x < 0) | (((ux & 15u) == 0) & ((ux >> 4) * 0x3AFB7E91u <= 0xFFFFFFFFu / 625u));
+    const u32 t = (u32)x * 0x3AFB7E91u;
+    return __funnelshift_r(t, t, 4) <= 0xFFFFFFFFu / 10000u;
 }
 
 struct BulkRec {
@@ -300,15 +288,15 @@ struct BulkRec {
 };
 
 template <bool PAIRED>
-__device__ __forceinline__ BulkRec bulk_load(int64_t u, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+__device__ __forceinline__ BulkRec bulk_load(u32 u, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                                              const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ mapq,
                                              const uint8_t* __restrict__ flag, u64 pol) {
     BulkRec r;
     if (PAIRED) {
-        r.fl = ld_stream_u16(flag + 2 * u, pol);                    // both mates' flag bytes
-        r.q = ld_stream_u16(mapq + 2 * u, pol) & 0xFFu;             // read1 only (:88)
-        r.c = (int)(ld_stream_u32(chrom + 2 * u, pol) & 0xFFFFu);   // read1 only (:96)
-        const int2 s2 = ld_stream_int2(start + 2 * u, pol);
+        r.fl = ld_stream_u16(flag + 2 * (size_t)u, pol);            // both mates' flag bytes
+        r.q = ld_stream_u16(mapq + 2 * (size_t)u, pol) & 0xFFu;     // read1 only (:88)
+        r.c = (int)(ld_stream_u32(chrom + 2 * (size_t)u, pol) & 0xFFFFu);   // read1 only (:96)
+        const int2 s2 = ld_stream_int2(start + 2 * (size_t)u, pol);
         r.loc1 = s2.x;                                              // :97
         r.loc2 = s2.y;                                              // :98 mate START
     } else {
@@ -351,17 +339,20 @@ __device__ __forceinline__ void bump_entry(u32 hit, const Sector& s, u32 hot_add
                  "not.pred q, q;\n\t"
                  "and.pred r, p, q;\n\t"
                  "@r red.global.add.u64 [%5], %7;\n\t}"
-                 :: "r"(hit), "n"(1 << I), "r"(slot), "n"(TEC_HOT_SLOTS), "r"(hot_addr + slot * 4u), "l"(counts + slot),
+                 :: "r"(hit), "n"(I == 0 ? HB0 : I == 1 ? HB1 : I == 2 ? HB2 : I == 3 ? HB3 : HB4), "r"(slot), "n"(TEC_HOT_SLOTS), "r"(hot_addr + slot * 4u), "l"(counts + slot),
                     "r"(one), "l"((u64)one) : "memory");
 }
 
-__device__ __forceinline__ void bulk_bump(BulkShared& sh, u64* __restrict__ counts, u32 slot) {
-    if (slot < TEC_HOT_SLOTS) atomicAdd(&sh.hot[slot], 1u);
-    else atomicAdd(counts + slot, 1ULL);
+// slow list: word 0 = number of flagged units, then their indices (capacity = units of the launch).
+// Called by a converged warp: one atomic per warp.
+__device__ __forceinline__ void flag_slow_warp(u32* __restrict__ slow_list, bool slow, u32 u, u32 lt_mask) {
+    const u32 sm = __ballot_sync(0xFFFFFFFFu, slow);
+    if (!sm) return;
+    u32 base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(slow_list, (u32)__popc(sm));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (slow) slow_list[1 + base + __popc(sm & lt_mask)] = u;
 }
-
-// slow list: word 0 = number of flagged units, then their indices (capacity = units of the launch)
-__device__ __forceinline__ void flag_slow(u32* __restrict__ slow_list, u32 u) { slow_list[1 + atomicAdd(slow_list, 1u)] = u; }
 
 // type rule of te_count.py:134-147 over the distinct slots of a unit; returns "count it"
 __device__ __forceinline__ bool bulk_type_rule(const StabView& sv, u32 typemask, u64* __restrict__ stats) {
@@ -371,49 +362,69 @@ __device__ __forceinline__ bool bulk_type_rule(const StabView& sv, u32 typemask,
     return false;
 }
 
-// all entries of a sector chain that contain point ra or rb go into S
-__device__ __forceinline__ void chain_collect(const StabView& sv, u32 sec, u32 ra, u32 rb, SlotSet& S) {
-    const int rmax = max((int)(short)ra, (int)(short)rb);                              // R_NONE -> -1
-    for (;;) {
-        const Sector s = ld_sector(sv.sectors, sec);
-        u32 last_s;
-        const u32 hit = sector_hits(s, ra, rb, last_s);
-        if (hit) {
-            S.add(sector_slot_c<0>(s), hit & 1u);
-            S.add(sector_slot_c<1>(s), hit & 2u);
-            S.add(sector_slot_c<2>(s), hit & 4u);
-            S.add(sector_slot_c<3>(s), hit & 8u);
-            S.add(sector_slot_c<4>(s), hit & 16u);
-            S.add(sector_slot_c<5>(s), hit & 32u);
-        }
-        if (!sector_has_link(s) || rmax < (int)last_s) break;
-        sec = sector_link(s);
-    }
+// B-entry J is dropped from hitB when a hit entry of A carries the same ensg
+template <int J>
+__device__ __forceinline__ u32 drop_if_in_a(u32 hitA, u32 hitB, const Sector& A, const Sector& B) {
+    const u32 w = sector_slot_c<J>(B);
+    const bool dup = ((hitA & HB0) && sector_slot_c<0>(A) == w) | ((hitA & HB1) && sector_slot_c<1>(A) == w) |
+                     ((hitA & HB2) && sector_slot_c<2>(A) == w) | ((hitA & HB3) && sector_slot_c<3>(A) == w) |
+                     ((hitA & HB4) && sector_slot_c<4>(A) == w);
+    const u32 bit = J == 0 ? HB0 : J == 1 ? HB1 : J == 2 ? HB2 : J == 3 ? HB3 : HB4;
+    return dup ? (hitB & ~bit) : hitB;
 }
 
-__device__ __forceinline__ void bulk_deferred(const StabView& sv, BulkShared& sh, const QEnt e, u32 u, bool live,
-                                              u64* __restrict__ counts, u64* __restrict__ stats,
-                                              u32* __restrict__ slow_list, u32& n_assigned) {
-    if (!live) return;
-    SlotSet S;
-    S.clear();
-    chain_collect(sv, e.secA & 0xFFFFFFu, e.pa & 0xFFFFu, e.pa >> 16, S);
-    if (e.secA >> 24) chain_collect(sv, e.secB, e.pb & 0xFFFFu, e.pb >> 16, S);
-    const bool slow = false;
-    if (slow || S.n > STAB_MAXD) { flag_slow(slow_list, u); return; }
-    if (!S.n) return;                                                                  // :128 no result
+__device__ __forceinline__ u32 sector_typemask(const StabView& sv, const Sector& s, u32 hit) {
+    u32 typemask = 0;
+    if (hit & HB0) typemask |= 1u << __ldg(sv.slot_type + sector_slot_c<0>(s));
+    if (hit & HB1) typemask |= 1u << __ldg(sv.slot_type + sector_slot_c<1>(s));
+    if (hit & HB2) typemask |= 1u << __ldg(sv.slot_type + sector_slot_c<2>(s));
+    if (hit & HB3) typemask |= 1u << __ldg(sv.slot_type + sector_slot_c<3>(s));
+    if (hit & HB4) typemask |= 1u << __ldg(sv.slot_type + sector_slot_c<4>(s));
+    return typemask;
+}
+
+__device__ __forceinline__ int points_rmax(u32 p) {
+    const u32 ra = p & 0xFFFFu, rb = p >> 16;
+    return max(ra == R_NONE ? -1 : (int)ra, rb == R_NONE ? -1 : (int)rb);
+}
+
+// A unit that needs exactly two sectors: two cells (kind 1), or a cell and its first overflow sector
+// (kind 0).  Straight-line code for a full warp of such units; anything longer (a third sector, two
+// hit entries with the same ensg inside one sector) goes to the exact kernel.
+__device__ __forceinline__ bool bulk_deferred(const StabView& sv, const QEnt e, bool live,
+                                              u32 hot_addr, u64* __restrict__ counts, u64* __restrict__ stats,
+                                              u32& n_assigned, u32 one) {
+    if (!live) return false;
+    const u32 kind = e.secA >> 24, prim = e.secA & 0xFFFFFFu;
+    const Sector A = ld_sector(sv.sectors, prim);
+    const u32 hitA = sector_hits(A, make_point(e.pa & 0xFFFFu), make_point(e.pa >> 16));
+    const bool a_over = sector_more(A) && points_rmax(e.pa) >= (int)sector_last_s(A);
+    const u32 secB = kind ? e.secB : (__ldg(sv.ovf_base + (prim >> 7)) + sector_link(A));
+    const u32 pB = kind ? e.pb : e.pa;
+    const Sector B = ld_sector(sv.sectors, (kind || a_over) ? secB : prim);
+    u32 hitB = (kind || a_over) ? sector_hits(B, make_point(pB & 0xFFFFu), make_point(pB >> 16)) : 0u;
+    bool slow = (kind && a_over) || ((kind || a_over) && sector_more(B) && points_rmax(pB) >= (int)sector_last_s(B));
+    slow |= sector_twin_hit(A, hitA) || sector_twin_hit(B, hitB);
+    if (slow) return true;
+    if (!(hitA | hitB)) return false;                                                  // :128 no result
     n_assigned++;                                                                      // :149
-    if (!sv.all_counted) {
-        u32 typemask = 1u << __ldg(sv.slot_type + S.v0);
-        if (S.n > 1) typemask |= 1u << __ldg(sv.slot_type + S.v1);
-        if (S.n > 2) typemask |= 1u << __ldg(sv.slot_type + S.v2);
-        if (S.n > 3) typemask |= 1u << __ldg(sv.slot_type + S.v3);
-        if (!bulk_type_rule(sv, typemask, stats)) return;
-    }
-    bulk_bump(sh, counts, S.v0);
-    if (S.n > 1) bulk_bump(sh, counts, S.v1);
-    if (S.n > 2) bulk_bump(sh, counts, S.v2);
-    if (S.n > 3) bulk_bump(sh, counts, S.v3);
+    if (!sv.all_counted && !bulk_type_rule(sv, sector_typemask(sv, A, hitA) | sector_typemask(sv, B, hitB), stats)) return false;
+    hitB = drop_if_in_a<0>(hitA, hitB, A, B);
+    hitB = drop_if_in_a<1>(hitA, hitB, A, B);
+    hitB = drop_if_in_a<2>(hitA, hitB, A, B);
+    hitB = drop_if_in_a<3>(hitA, hitB, A, B);
+    hitB = drop_if_in_a<4>(hitA, hitB, A, B);
+    bump_entry<0>(hitA, A, hot_addr, counts, one);
+    bump_entry<1>(hitA, A, hot_addr, counts, one);
+    bump_entry<2>(hitA, A, hot_addr, counts, one);
+    bump_entry<3>(hitA, A, hot_addr, counts, one);
+    bump_entry<4>(hitA, A, hot_addr, counts, one);
+    bump_entry<0>(hitB, B, hot_addr, counts, one);
+    bump_entry<1>(hitB, B, hot_addr, counts, one);
+    bump_entry<2>(hitB, B, hot_addr, counts, one);
+    bump_entry<3>(hitB, B, hot_addr, counts, one);
+    bump_entry<4>(hitB, B, hot_addr, counts, one);
+    return false;
 }
 
 // One warp per 32 consecutive units, grid-stride; the next warp-tile's records are requested before
@@ -445,21 +456,22 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
     QEnt* const ring = sh.q[wib];
     u32* const ring_u = sh.qu[wib];
     u32 q_head = 0, q_count = 0;                     // warp-uniform
-    const int64_t n_tiles = (n_units + 31) >> 5;
-    const int64_t tile_stride = (int64_t)gridDim.x * BULK_WARPS;
-    int64_t tile = (int64_t)blockIdx.x * BULK_WARPS + wib;
+    const u32 n_u = (u32)n_units;                     // a launch holds < 2^28 units (TEC_LAUNCH_UNITS)
+    const u32 n_tiles = (n_u + 31) >> 5;
+    const u32 tile_stride = gridDim.x * BULK_WARPS;
+    u32 tile = blockIdx.x * BULK_WARPS + wib;
     BulkRec cur, nxt;
     cur.fl = cur.q = 0; cur.c = cur.loc1 = cur.loc2 = 0;
     nxt = cur;
-    if (tile < n_tiles && tile * 32 + lane < n_units) cur = bulk_load<PAIRED>(tile * 32 + lane, start, end, chrom, mapq, flag, pol);
+    if (tile < n_tiles && tile * 32 + lane < n_u) cur = bulk_load<PAIRED>(tile * 32 + lane, start, end, chrom, mapq, flag, pol);
     for (; tile < n_tiles; tile += tile_stride) {
-        const int64_t u = tile * 32 + lane;
-        const int64_t un = u + tile_stride * 32;
-        if (un < n_units) nxt = bulk_load<PAIRED>(un, start, end, chrom, mapq, flag, pol);
+        const u32 u = tile * 32 + lane;
+        const u32 un = u + tile_stride * 32;
+        if (un < n_u) nxt = bulk_load<PAIRED>(un, start, end, chrom, mapq, flag, pol);
         // ---- filter (te_count.py:78-102 / :203-218)
         const int c = cur.c, loc1 = cur.loc1, loc2 = cur.loc2;
         bool look = false;
-        if (u < n_units) {
+        if (u < n_u) {
             if (cur.fl & reject2) n_qcfail++;                                              // :81-86 / :204
             else if ((int)cur.q < qual) n_lowq++;                                          // :88 / :208
             else if (PAIRED && (cur.fl & TEC_F_NAME_MISMATCH)) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);   // :92-94
@@ -469,11 +481,12 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
         // ---- which sector(s)
         QEnt qe;
         qe.secA = qe.secB = 0; qe.pa = qe.pb = R_NONE | (R_NONE << 16);
-        bool defer = false, single = false;
+        bool defer = false, single = false, slow = false;
+        int rmax = -1;
         if (look) {
             const bool edge = (bs == 10000) ? (mult_of_10000(loc1) | mult_of_10000(loc2 + 1))
                                             : ((loc1 % bs == 0) || ((loc2 + 1) % bs == 0));
-            if (edge) flag_slow(slow_list, (u32)u);
+            if (edge) slow = true;
             else {
                 const uint2 cell = __ldg(sv.cells + c);
                 const int xa = loc1, xb = loc2 - 1;
@@ -489,6 +502,7 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
                 } else if (va || vb) {
                     qe.secA = cell.x + (u32)(va ? ka : kb);
                     qe.pa = (va ? ra : R_NONE) | ((vb ? rb : R_NONE) << 16);
+                    rmax = max(va ? (int)ra : -1, vb ? (int)rb : -1);
                     single = true;
                 }
             }
@@ -496,31 +510,25 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
         // ---- the common case: one sector
         if (single) {
             const Sector s = ld_sector(sv.sectors, qe.secA);
-            u32 last_s;
-            u32 hit = sector_hits(s, qe.pa & 0xFFFFu, qe.pa >> 16, last_s);
-            const int rmax = max((int)(short)(qe.pa & 0xFFFFu), (int)(short)(qe.pa >> 16));
-            if (sector_has_link(s) && rmax >= (int)last_s) {
+            const u32 hit = sector_hits(s, make_point(qe.pa & 0xFFFFu), make_point(qe.pa >> 16));
+            if (sector_more(s) && rmax >= (int)sector_last_s(s)) {
                 defer = true;                                                              // the chain is walked again from A
-            } else if (sector_has_dup(s) && (hit & (hit - 1))) {
-                defer = true;
+            } else if (sector_twin_hit(s, hit)) {
+                slow = true;                                                               // the same ensg may be hit twice
             } else if (hit) {                                                              // :128 result not empty
                 n_assigned++;                                                              // :149
                 bool count_it = true;
-                if (!sv.all_counted) {
-                    u32 typemask = 0, h = hit;
-                    while (h) { const int i = __ffs(h) - 1; h &= h - 1; typemask |= 1u << __ldg(sv.slot_type + sector_slot(s, i)); }
-                    count_it = bulk_type_rule(sv, typemask, stats);
-                }
+                if (!sv.all_counted) count_it = bulk_type_rule(sv, sector_typemask(sv, s, hit), stats);
                 if (count_it) {
                     bump_entry<0>(hit, s, hot_addr, counts, one);
                     bump_entry<1>(hit, s, hot_addr, counts, one);
                     bump_entry<2>(hit, s, hot_addr, counts, one);
                     bump_entry<3>(hit, s, hot_addr, counts, one);
                     bump_entry<4>(hit, s, hot_addr, counts, one);
-                    bump_entry<5>(hit, s, hot_addr, counts, one);
                 }
             }
         }
+        flag_slow_warp(slow_list, slow, (u32)u, lt_mask);
         // ---- park deferred units; look a full warp of them up when there are 32
         const u32 dm = __ballot_sync(0xFFFFFFFFu, defer);
         if (dm) {
@@ -533,7 +541,8 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
             __syncwarp();
             if (q_count >= 32) {
                 const u32 at = (q_head + lane) & (BULK_QCAP - 1);
-                bulk_deferred(sv, sh, ring[at], ring_u[at], true, counts, stats, slow_list, n_assigned);
+                const bool sl = bulk_deferred(sv, ring[at], true, hot_addr, counts, stats, n_assigned, one);
+                flag_slow_warp(slow_list, sl, ring_u[at], lt_mask);
                 q_head = (q_head + 32) & (BULK_QCAP - 1);
                 q_count -= 32;
                 __syncwarp();
@@ -543,7 +552,8 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
     }
     if (q_count) {
         const u32 at = (q_head + lane) & (BULK_QCAP - 1);
-        bulk_deferred(sv, sh, ring[at], ring_u[at], (u32)lane < q_count, counts, stats, slow_list, n_assigned);
+        const bool sl = bulk_deferred(sv, ring[at], (u32)lane < q_count, hot_addr, counts, stats, n_assigned, one);
+        flag_slow_warp(slow_list, sl, ring_u[at], lt_mask);
     }
     u64 v[4] = {n_assigned, n_lowq, n_badchrom, n_qcfail};
 #pragma unroll
@@ -571,8 +581,17 @@ __global__ void __launch_bounds__(256)
 bulk_slow_kernel(IndexView iv, StabView sv, int has_stab, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                  const uint16_t* __restrict__ chrom, u64* __restrict__ counts, u64* __restrict__ stats,
                  const u32* __restrict__ slow_list) {
+    // hot ensg counters privatised per CTA (a Zipf-hot TE name would otherwise serialise in one L2 slice)
+    __shared__ u32 s_hot[TEC_HOT_SLOTS];
+    for (int i = threadIdx.x; i < TEC_HOT_SLOTS; i += blockDim.x) s_hot[i] = 0;
+    __syncthreads();
+    auto bump = [&](u32 slot) {
+        if (slot < TEC_HOT_SLOTS) atomicAdd(&s_hot[slot], 1u);
+        else atomicAdd(counts + slot, 1ULL);
+    };
     const u32 n = slow_list[0];
     const u32 counted = (1u << TEC_T_GENE) | (1u << TEC_T_TE) | (1u << TEC_T_SNRNA);
+    u32 n_assigned = 0;
     for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const int64_t u = slow_list[1 + t];
         int c, loc1, loc2;
@@ -589,28 +608,30 @@ bulk_slow_kernel(IndexView iv, StabView sv, int has_stab, const int32_t* __restr
                 const int k = x[p] >> sv.shift;
                 if ((u32)k >= cell.y) continue;
                 const u32 r = (u32)x[p] & ((1u << sv.shift) - 1);
-                u32 sec = cell.x + (u32)k;
+                const u32 prim = cell.x + (u32)k;
+                u32 sec = prim;
+                const PointK pk = make_point(r), pn = make_point(R_NONE);
                 for (;;) {
                     const Sector s = ld_sector(sv.sectors, sec);
-                    u32 last_s;
-                    u32 hit = sector_hits(s, r, R_NONE, last_s);
+                    u32 hit = sector_hits(s, pk, pn);
                     while (hit) {
-                        const int i = __ffs(hit) - 1;
-                        hit &= hit - 1;
-                        const u32 e = sector_slot(s, i);
+                        const u32 low = hit & (0u - hit);
+                        hit ^= low;
+                        const u32 e = (low == HB0) ? sector_slot_c<0>(s) : (low == HB1) ? sector_slot_c<1>(s) : (low == HB2) ? sector_slot_c<2>(s)
+                                      : (low == HB3) ? sector_slot_c<3>(s) : sector_slot_c<4>(s);
                         bool found = false;
                         for (u32 j = 0; j < nd; ++j) found |= (dist[j] == e);
                         if (!found) {
                             if (nd < SLOW_MAXD) dist[nd++] = e; else overflow = true;
                         }
                     }
-                    if (!sector_has_link(s) || r < last_s) break;
-                    sec = sector_link(s);
+                    if (!sector_more(s) || r < sector_last_s(s)) break;
+                    sec = (sec == prim) ? __ldg(sv.ovf_base + (prim >> 7)) + sector_link(s) : sec + 1;
                 }
             }
             if (!overflow) {
                 if (!nd) continue;                                                     // :128 no result
-                atomicAdd(stats + TEC_BS_ASSIGNED, 1ULL);                              // :149
+                n_assigned++;                                                          // :149
                 u32 typemask = sv.all_counted ? counted : 0u;
                 if (!sv.all_counted)
                     for (u32 j = 0; j < nd; ++j) typemask |= 1u << __ldg(sv.slot_type + dist[j]);
@@ -618,7 +639,7 @@ bulk_slow_kernel(IndexView iv, StabView sv, int has_stab, const int32_t* __restr
                     if (typemask & (1u << TEC_T_ENHANCER)) atomicAdd(stats + TEC_BS_CRASH_ENHANCER, 1ULL);
                     continue;
                 }
-                for (u32 j = 0; j < nd; ++j) atomicAdd(counts + dist[j], 1ULL);
+                for (u32 j = 0; j < nd; ++j) bump(dist[j]);
                 continue;
             }
         }
@@ -637,13 +658,13 @@ bulk_slow_kernel(IndexView iv, StabView sv, int has_stab, const int32_t* __restr
             return true;
         });
         if (!typemask) continue;                                                       // :128 no result
-        atomicAdd(stats + TEC_BS_ASSIGNED, 1ULL);                                      // :149
+        n_assigned++;                                                                  // :149
         if (!(typemask & counted)) {
             if (typemask & (1u << TEC_T_ENHANCER)) atomicAdd(stats + TEC_BS_CRASH_ENHANCER, 1ULL);
             continue;
         }
         if (!overflow) {
-            for (u32 i = 0; i < nd; ++i) atomicAdd(counts + dist[i], 1ULL);            // one per distinct ensg
+            for (u32 i = 0; i < nd; ++i) bump(dist[i]);                                // one per distinct ensg
             continue;
         }
         // more distinct ensg than the list holds: count a hit iff no earlier hit (in enumeration
@@ -658,9 +679,16 @@ bulk_slow_kernel(IndexView iv, StabView sv, int has_stab, const int32_t* __restr
                 if (info_ensg(__ldg(iv.info + fj)) == e) { dup = true; return false; }
                 return true;
             });
-            if (!dup) atomicAdd(counts + e, 1ULL);
+            if (!dup) bump(e);
             ++h;
             return true;
         });
+    }
+    const u64 a_sum = warp_sum((u64)n_assigned);
+    if ((threadIdx.x & 31) == 0 && a_sum) atomicAdd(stats + TEC_BS_ASSIGNED, a_sum);
+    __syncthreads();
+    for (int i = threadIdx.x; i < TEC_HOT_SLOTS; i += blockDim.x) {
+        const u32 x = s_hot[i];
+        if (x) atomicAdd(counts + i, (u64)x);
     }
 }

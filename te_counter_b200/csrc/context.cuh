@@ -20,14 +20,30 @@ struct DevIndex {
     u32* st_sectors = nullptr;
     uint2* st_cells = nullptr;            // per chromosome {first sector, number of cells}
     uint8_t* st_slot_type = nullptr;
+    u32* st_ovf_base = nullptr;
     int st_shift = 11, st_all_counted = 1;
     bool has_stab = false;
     size_t stab_bytes = 0;
     int64_t st_primary = 0, st_overflow = 0, st_entries = 0;
     StabView stab_view() const {
         StabView v;
-        v.sectors = st_sectors; v.cells = st_cells; v.slot_type = st_slot_type;
+        v.sectors = st_sectors; v.cells = st_cells; v.slot_type = st_slot_type; v.ovf_base = st_ovf_base;
         v.shift = st_shift; v.all_counted = st_all_counted;
+        return v;
+    }
+    // single-cell cell table (sc.cuh ScTableView)
+    u32* sc_sectors = nullptr;
+    uint2* sc_cells = nullptr;
+    u32* sc_ovf_base = nullptr;
+    u32* sc_pair_key = nullptr;
+    uint8_t* sc_pair_type = nullptr;
+    int sc_shift = 11;
+    bool has_sc_stab = false;
+    size_t sc_stab_bytes = 0;
+    StabView sc_stab_view() const {
+        StabView v;
+        v.sectors = sc_sectors; v.cells = sc_cells; v.slot_type = sc_pair_type; v.ovf_base = sc_ovf_base;
+        v.shift = sc_shift; v.all_counted = 0;
         return v;
     }
     IndexView view() const {
@@ -115,6 +131,7 @@ struct tec_ctx {
     // options (tec_set_option)
     int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 stab-table kernel
     int opt_stab_shift = 11;
+    int opt_sc_algo = -1;                 // -1 auto, 0 exact search only, 1 cell table
     int opt_ctas_per_sm = 2;              // resident CTAs per SM of the fast bulk kernel (512 threads each)
 
     // host staging
@@ -145,7 +162,8 @@ inline void tec_ctx::free_index() {
     DevIndex& ix = idx;
     cudaFree(ix.L); cudaFree(ix.R); cudaFree(ix.pmaxR); cudaFree(ix.info);
     cudaFree(ix.chrom_off); cudaFree(ix.dir); cudaFree(ix.dir_off);
-    cudaFree(ix.st_sectors); cudaFree(ix.st_cells); cudaFree(ix.st_slot_type);
+    cudaFree(ix.st_sectors); cudaFree(ix.st_cells); cudaFree(ix.st_slot_type); cudaFree(ix.st_ovf_base);
+    cudaFree(ix.sc_sectors); cudaFree(ix.sc_cells); cudaFree(ix.sc_ovf_base); cudaFree(ix.sc_pair_key); cudaFree(ix.sc_pair_type);
     ix = DevIndex();
     cudaFree(d_counts);
     d_counts = nullptr;

@@ -172,6 +172,16 @@ template <class T>
 __global__ void sc_gather_kernel(int64_t n, const u32* __restrict__ perm, const T* __restrict__ src, T* __restrict__ dst) {
     SC_LOOP(j, n) dst[j] = src[perm[j]];
 }
+// fragment columns in sorted (cell, umi, i) order: one pass of random reads instead of one per use
+__global__ void sc_gather3_kernel(int64_t n, const u32* __restrict__ perm, const u32* __restrict__ cs, const int32_t* __restrict__ left,
+                                  const int32_t* __restrict__ rite, u32* __restrict__ scs, int32_t* __restrict__ sleft, int32_t* __restrict__ srite) {
+    SC_LOOP(j, n) {
+        const u32 i = perm[j];
+        scs[j] = cs[i];
+        sleft[j] = left[i];
+        srite[j] = rite[i];
+    }
+}
 template <class T>
 __global__ void sc_fill_kernel(int64_t n, T* __restrict__ v, T x) { SC_LOOP(i, n) v[i] = x; }
 
@@ -238,7 +248,7 @@ __global__ void sc_segstat_kernel(int64_t n, int64_t n_wl, const u32* __restrict
             const int64_t bc = (int64_t)bundle[j] * n_wl + c;
             atomicMin(minumi + bc, sumi[j]);
             present[bc] = 1u;
-        } else if (cs[perm[j]] == cs[perm[h]]) {
+        } else if (cs[j] == cs[h]) {                                                  // cs in sorted order
             n_seen++;                                                                  // :452-454
         } else {
             atomicAdd(raw + c, 1u);                                                    // :459-462
@@ -349,41 +359,106 @@ struct ScOut {
     u32* overflow;
 };
 
-// one fragment (cell, chrom:strand, left, rite): te_count.py:607-686
-__device__ void sc_count_fragment(const IndexView& iv, int strand_mode, const u32* __restrict__ ensg_of_slot,
-                                  u32 cell, u32 cs, int left, int rite, const ScOut& o) {
+// single-cell cell table: same layout as the bulk table (stab_build.h) over the intervals
+// [L-1, R+1) -- left in [L-1, R] or rite in [L, R+1] (te_count.py:645/:648) is a stab query of that
+// interval at left or at rite-1 -- with one slot per distinct (ensg, strand) pair.
+struct ScTableView {
+    StabView sv;                 // sectors / cells / ovf_base / shift (slot_type unused)
+    const u32* pair_key;         // slot -> ensg slot << 3 | strand code
+    const uint8_t* pair_type;    // slot -> TEC_T_*
+    int present;
+};
+
+// Result of one fragment (cell, chrom:strand, left, rite), te_count.py:607-686: the (ensg, cell)
+// increments it causes are returned to the caller, which appends them warp-aggregated.
+struct FragOut {
+    u32 n;                       // number of keys
+    u32 key[SC_MAX_PAIRS];       // ensg ids
+    bool hit, assigned, crash, spilled;
+};
+
+__device__ __forceinline__ void sc_append_direct(const ScOut& o, u64 v) {
+    const u32 at = atomicAdd(o.n_pairs, 1u);
+    if (at < o.cap_pairs) o.pairs[at] = v; else *o.overflow = 1u;
+}
+
+__device__ void sc_count_fragment(const IndexView& iv, const ScTableView& tv, int strand_mode, const u32* __restrict__ ensg_of_slot,
+                                  u32 cell, u32 cs, int left, int rite, const ScOut& o, FragOut& out) {
+    out.n = 0; out.hit = out.assigned = out.crash = out.spilled = false;
     const int c = (int)(cs >> 2);
     const u32 rs = cs & 3u;
     if (c >= iv.n_chrom) return;                                                       // :614
-    u32 typemask = 0, np = 0, pairs[SC_MAX_PAIRS];
-    bool over = false, missing = false;
-    sc_for_each_hit(iv, c, left, rite, [&](int64_t fi) {
-        const u32 w = __ldg(iv.info + fi);
-        typemask |= 1u << info_type(w);
-        const u32 fs = info_strand(w);
-        missing |= fs == 7u;
-        const u32 key = (info_ensg(w) << 3) | fs;                                      // (ensg, strand) of :661
-        bool found = false;
-        for (u32 i = 0; i < np; ++i) found |= pairs[i] == key;
-        if (!found) { if (np < SC_MAX_PAIRS) pairs[np++] = key; else over = true; }
-    });
+    u32 typemask = 0, np = 0;
+    u32* pairs = out.key;
+    bool over = false, missing = false, exact = true;
+    if (tv.present && left >= 0 && left < rite) {
+        // for left < rite every feature that passes a point test is also in the bucket range (:619-621)
+        exact = false;
+        const uint2 cellr = __ldg(tv.sv.cells + c);
+        const int x[2] = {left, rite - 1};
+        for (int p = 0; p < 2 && !over; ++p) {
+            const int k = x[p] >> tv.sv.shift;
+            if ((u32)k >= cellr.y) continue;
+            if (p == 1 && x[1] == x[0]) continue;
+            const u32 r = (u32)x[p] & ((1u << tv.sv.shift) - 1);
+            const u32 prim = cellr.x + (u32)k;
+            u32 sec = prim;
+            const PointK pk = make_point(r), pn = make_point(R_NONE);
+            for (;;) {
+                const Sector sct = ld_sector(tv.sv.sectors, sec);
+                u32 hit = sector_hits(sct, pk, pn);
+                while (hit) {
+                    const u32 low = hit & (0u - hit);
+                    hit ^= low;
+                    const u32 slot = (low == HB0) ? sector_slot_c<0>(sct) : (low == HB1) ? sector_slot_c<1>(sct) : (low == HB2) ? sector_slot_c<2>(sct)
+                                     : (low == HB3) ? sector_slot_c<3>(sct) : sector_slot_c<4>(sct);
+                    const u32 key = __ldg(tv.pair_key + slot);
+                    bool found = false;
+                    for (u32 i = 0; i < np; ++i) found |= pairs[i] == key;
+                    if (!found) {
+                        if (np < SC_MAX_PAIRS) {
+                            pairs[np++] = key;
+                            typemask |= 1u << __ldg(tv.pair_type + slot);
+                            missing |= (key & 7u) == 7u;
+                        } else over = true;
+                    }
+                }
+                if (!sector_more(sct) || r < sector_last_s(sct)) break;
+                sec = (sec == prim) ? __ldg(tv.sv.ovf_base + (prim >> 7)) + sector_link(sct) : sec + 1;
+            }
+        }
+        if (over) { exact = true; typemask = 0; np = 0; over = false; missing = false; }
+    }
+    if (exact) {
+        sc_for_each_hit(iv, c, left, rite, [&](int64_t fi) {
+            const u32 w = __ldg(iv.info + fi);
+            typemask |= 1u << info_type(w);
+            const u32 fs = info_strand(w);
+            missing |= fs == 7u;
+            const u32 key = (info_ensg(w) << 3) | fs;                                  // (ensg, strand) of :661
+            bool found = false;
+            for (u32 i = 0; i < np; ++i) found |= pairs[i] == key;
+            if (!found) { if (np < SC_MAX_PAIRS) pairs[np++] = key; else over = true; }
+        });
+    }
     if (!typemask) return;
-    atomicAdd(o.cell_hits + cell, 1u);                                                 // :653-655
-    if (missing) { atomicAdd(o.stats + TEC_SS_CRASH_STRAND, 1ULL); return; }           // :661 KeyError
+    out.hit = true;                                                                    // :653-655
+    if (missing) { out.crash = true; return; }                                         // :661 KeyError
     const bool gene = typemask & (1u << TEC_T_GENE);
     if (!gene && !(typemask & ((1u << TEC_T_TE) | (1u << TEC_T_ENHANCER)))) return;    // :684
-    atomicAdd(o.stats + TEC_SS_ASSIGNED, 1ULL);                                        // :686
-    auto emit = [&](u32 key) {
-        if (gene && strand_mode && rs != (key & 7u)) return;                           // :665
-        const u32 at = atomicAdd(o.n_pairs, 1u);
-        if (at < o.cap_pairs) o.pairs[at] = ((u64)ensg_of_slot[key >> 3] << 32) | cell;
-        else *o.overflow = 1u;
-    };
+    out.assigned = true;                                                               // :686
     if (!over) {
-        for (u32 i = 0; i < np; ++i) emit(pairs[i]);
+        u32 m = 0;
+        for (u32 i = 0; i < np; ++i) {
+            const u32 key = pairs[i];
+            if (gene && strand_mode && rs != (key & 7u)) continue;                     // :665
+            pairs[m++] = ensg_of_slot[key >> 3];
+        }
+        out.n = m;
         return;
     }
-    // more distinct pairs than the list holds: emit a hit iff no earlier hit has the same pair
+    // more distinct pairs than the list holds: append directly, a hit iff no earlier hit has the same pair
+    out.spilled = true;
     int h = 0;
     sc_for_each_hit(iv, c, left, rite, [&](int64_t fi) {
         const u32 w = __ldg(iv.info + fi);
@@ -395,49 +470,85 @@ __device__ void sc_count_fragment(const IndexView& iv, int strand_mode, const u3
             const u32 w2 = __ldg(iv.info + fj);
             if (((info_ensg(w2) << 3) | info_strand(w2)) == key) dup = true;
         });
-        if (!dup) emit(key);
+        if (!dup && !(gene && strand_mode && rs != (key & 7u)))
+            sc_append_direct(o, ((u64)ensg_of_slot[key >> 3] << 32) | cell);
         ++h;
     });
 }
 
-// one thread per winning segment: its fragments (te_count.py:603-606) are counted on the spot
-__global__ void sc_part3_kernel(int64_t n, IndexView iv, int strand_mode, const u32* __restrict__ ensg_of_slot,
-                                const u32* __restrict__ perm, const u32* __restrict__ scell,
-                                const u32* __restrict__ shead_pos, const u32* __restrict__ khead_pos, const u32* __restrict__ winner_at,
-                                const u32* __restrict__ cs, const int32_t* __restrict__ left, const int32_t* __restrict__ rite, ScOut o) {
-    SC_LOOP(j, n) {
-        if (shead_pos[j] != (u32)j || winner_at[khead_pos[j]] != (u32)j) continue;
-        const u32 cell = scell[j];
-        const u32 ih = perm[j];
-        const u32 cs0 = cs[ih];
-        sc_count_fragment(iv, strand_mode, ensg_of_slot, cell, cs0, left[ih], rite[ih], o);
+// one thread per winning segment; all columns are in sorted (cell, umi, i) order.  The increments of
+// a warp's fragments are appended with one atomic per warp.
+__global__ void sc_part3_kernel(int64_t n, IndexView iv, ScTableView tv, int strand_mode, const u32* __restrict__ ensg_of_slot,
+                                const u32* __restrict__ scell, const u32* __restrict__ shead_pos, const u32* __restrict__ khead_pos,
+                                const u32* __restrict__ winner_at, const u32* __restrict__ cs, const int32_t* __restrict__ left,
+                                const int32_t* __restrict__ rite, ScOut o) {
+    const int lane = threadIdx.x & 31;
+    u32 n_assigned = 0, n_crash = 0;
+    const int64_t n_round = ((n + 31) / 32) * 32;                // whole warps stay in the loop together
+    SC_LOOP(j, n_round) {
+        FragOut fo;
+        fo.n = 0;
+        const bool win = j < n && shead_pos[j] == (u32)j && winner_at[khead_pos[j]] == (u32)j;
+        u32 cell = 0;
+        if (win) {
+            cell = scell[j];
+            const u32 cs0 = cs[j];
+            sc_count_fragment(iv, tv, strand_mode, ensg_of_slot, cell, cs0, left[j], rite[j], o, fo);
+            if (fo.hit) atomicAdd(o.cell_hits + cell, 1u);
+            n_assigned += fo.assigned;
+            n_crash += fo.crash;
+        }
+        // warp-aggregated append of the head fragments' increments
+        u32 incl = fo.n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (total) {
+            u32 base = 0;
+            if (lane == 31) base = atomicAdd(o.n_pairs, total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - fo.n;
+            for (u32 i = 0; i < fo.n; ++i) {
+                if (base + i < o.cap_pairs) o.pairs[base + i] = ((u64)fo.key[i] << 32) | cell;
+                else *o.overflow = 1u;
+            }
+        }
+        if (!win) continue;
         // other chrom:strand values of the line: the distinct fragment whose first occurrence is latest
+        const u32 cs0 = cs[j];
         int64_t e = j + 1;
         while (e < n && shead_pos[e] != (u32)e) ++e;
         for (int64_t a = e - 1; a > j; --a) {
-            const u32 ia = perm[a];
-            const u32 csa = cs[ia];
+            const u32 csa = cs[a];
             if (csa == cs0) continue;
-            const int la = left[ia], ra = rite[ia];
+            const int la = left[a], ra = rite[a];
             bool first = true;                       // first occurrence of this exact fragment?
-            for (int64_t b = j + 1; b < a && first; ++b) {
-                const u32 ib = perm[b];
-                first = !(cs[ib] == csa && left[ib] == la && rite[ib] == ra);
-            }
+            for (int64_t b = j + 1; b < a && first; ++b)
+                first = !(cs[b] == csa && left[b] == la && rite[b] == ra);
             if (!first) continue;
             bool later = false;                      // a later first occurrence with the same chrom:strand wins
             for (int64_t b = a + 1; b < e && !later; ++b) {
-                const u32 ib = perm[b];
-                if (cs[ib] != csa) continue;
+                if (cs[b] != csa) continue;
                 bool fb = true;
-                for (int64_t d = j + 1; d < b && fb; ++d) {
-                    const u32 id = perm[d];
-                    fb = !(cs[id] == csa && left[id] == left[ib] && rite[id] == rite[ib]);
-                }
+                for (int64_t d = j + 1; d < b && fb; ++d)
+                    fb = !(cs[d] == csa && left[d] == left[b] && rite[d] == rite[b]);
                 later = fb;
             }
-            if (!later) sc_count_fragment(iv, strand_mode, ensg_of_slot, cell, csa, la, ra, o);
+            if (later) continue;
+            FragOut f2;
+            sc_count_fragment(iv, tv, strand_mode, ensg_of_slot, cell, csa, la, ra, o, f2);
+            if (f2.hit) atomicAdd(o.cell_hits + cell, 1u);
+            n_assigned += f2.assigned;
+            n_crash += f2.crash;
+            for (u32 i = 0; i < f2.n; ++i) sc_append_direct(o, ((u64)f2.key[i] << 32) | cell);
         }
+    }
+    const u64 a_sum = warp_sum((u64)n_assigned), c_sum = warp_sum((u64)n_crash);
+    if (lane == 0) {
+        if (a_sum) atomicAdd(o.stats + TEC_SS_ASSIGNED, a_sum);
+        if (c_sum) atomicAdd(o.stats + TEC_SS_CRASH_STRAND, c_sum);
     }
 }
 
@@ -680,6 +791,13 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         A.release(ck); A.release(perm1);
         TEC_CUDA(A.get(&sumi, (size_t)N));
         sc_gather_kernel<u64><<<SC_GRID(N)>>>(N, perm, s->umi, sumi);
+        u32* scs = nullptr;
+        int32_t *sleft = nullptr, *srite = nullptr;
+        TEC_CUDA(A.get(&scs, (size_t)N));
+        TEC_CUDA(A.get(&sleft, (size_t)N));
+        TEC_CUDA(A.get(&srite, (size_t)N));
+        sc_gather3_kernel<<<SC_GRID(N)>>>(N, perm, s->cs, s->left, s->rite, scs, sleft, srite);
+        ctx->launches++;
         u32 *prev = nullptr, *khead = nullptr;
         TEC_CUDA(A.get(&prev, (size_t)N));
         TEC_CUDA(A.get(&khead, (size_t)N));
@@ -747,7 +865,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         TEC_CUDA(cudaMemsetAsync(first_i, 0xFF, (size_t)W * 4, ctx->stream));
         TEC_CUDA(cudaMemsetAsync(present, 0, (size_t)(n_b * W + 1) * 4, ctx->stream));
         TEC_CUDA(cudaMemsetAsync(minumi, 0xFF, (size_t)(n_b * W) * 8, ctx->stream));
-        sc_segstat_kernel<<<SC_GRID(N)>>>(N, W, perm, scell, sumi, s->cs, shead, bundle, raw, first_i, minumi, present, s->d_stats);
+        sc_segstat_kernel<<<SC_GRID(N)>>>(N, W, perm, scell, sumi, scs, shead, bundle, raw, first_i, minumi, present, s->d_stats);
         ctx->launches += 2;
         // ---- Part 2: the maxcells + pad cells with the most raw reads, ties by first appearance
         u64 *ckey = nullptr, *ckey_s = nullptr;
@@ -798,8 +916,12 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
             TEC_CUDA(cudaMemcpyAsync(s->d_stats, h_stats_before, sizeof(h_stats_before), cudaMemcpyHostToDevice, ctx->stream));
             ScOut o;
             o.pairs = pairs; o.n_pairs = d_np; o.cap_pairs = (u32)cap_pairs; o.cell_hits = hits; o.stats = s->d_stats; o.overflow = d_over;
-            sc_part3_kernel<<<SC_GRID(N)>>>(N, ctx->idx.view(), s->strand, d_ensg_of_slot, perm, scell, shead, khead, winner_at,
-                                            s->cs, s->left, s->rite, o);
+            ScTableView tv;
+            tv.sv = ctx->idx.sc_stab_view();
+            tv.pair_key = ctx->idx.sc_pair_key; tv.pair_type = ctx->idx.sc_pair_type;
+            tv.present = (ctx->idx.has_sc_stab && ctx->opt_sc_algo != 0) ? 1 : 0;
+            sc_part3_kernel<<<SC_GRID(N)>>>(N, ctx->idx.view(), tv, s->strand, d_ensg_of_slot, scell, shead, khead, winner_at,
+                                            scs, sleft, srite, o);
             ctx->launches++;
             u32 h_over = 0;
             TEC_CUDA(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -812,7 +934,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         }
         // release what Part 3 no longer needs before sorting the pair list
         A.release(winner_at); A.release(minumi); A.release(present); A.release(bundle); A.release(shead); A.release(khead);
-        A.release(sumi); A.release(scell); A.release(perm);
+        A.release(sumi); A.release(scell); A.release(perm); A.release(scs); A.release(sleft); A.release(srite);
         // ---- triples: sort (ensg, cell) keys, run-length encode
         if (h_npairs) {
             TEC_CUDA(A.get(&pairs_sorted, (size_t)h_npairs));

@@ -6,37 +6,45 @@
 // directory in front of it:
 //
 //   sector of cell k of chromosome c  =  sectors[cell_base[c] + k]          (8 x u32)
-//   entry i (at most 6 per sector)    =  one interval of one ensg, clipped to the cell:
-//        slot_i   16 bits   w[i/2] >> 16*(i&1)                              (w0..w2)
-//        pos_i    22 bits   bit string w3..w7 at bit offset 22*i:  s | (len-1) << 11
-//                           s = interval start - cell start, len = clipped length
-//   header   28 bits   w7 >> 4:   code (3 bits: 0..6 = number of entries, 7 = 6 entries + link)
-//                                 | dup (1 bit: two entries of this sector carry the same ensg)
-//                                 | link (24 bits: sector index of the overflow sector)
+//   entry i (at most 5 per sector)    =  one interval [s, e] of one ensg, clipped to the cell,
+//                                        cell-relative, both ends inclusive (11-bit values)
+//        w0 = s0 | s1 << 16     w1 = s2 | s3 << 16     w2 = s4 | header << 16
+//        w3 = e0 | e1 << 16     w4 = e2 | e3 << 16     w5 = e4 | slot4  << 16
+//        w6 = slot0 | slot1 << 16                       w7 = slot2 | slot3 << 16
+//   header (16 bits): bit 0 "more" (the cell's list continues in an overflow sector),
+//                     bits 1..5 "twin" mask: entry i has the same ensg as another entry of this
+//                     sector; bit order e4, e2, e0, e3, e1 (the order the kernel's hit mask
+//                     compacts to),
+//                     bits 6..15 link: first overflow sector of this cell, relative to
+//                     ovf_base[cell >> 7] (primary sectors only; an overflow sector's
+//                     continuation is simply the next sector)
+//   unused entries have s = 2047, e = 0 (never contain a point).
+//
+// The 16-bit lanes are what makes the kernel's test cheap: with X = r * 0x10001 + 0x80008000,
+// bit 15 of each lane of (X - w_s) says r >= s and of (w_e + 0x80008000 - r * 0x10001) says e >= r,
+// i.e. one add per word tests two entries (SIMD within a register; the adds run on either the
+// integer or the FMA pipe, which matters because the kernel is integer-ALU bound).
 //
 // Intervals of the same ensg are merged per chromosome first (union of [L, R)), so one ensg never
-// has two overlapping or touching entries; entries are sorted by start.  A cell with more than 6
-// entries keeps its first 6 in the primary sector and links to overflow sectors (same format,
-// stored after the primary cells); a query only follows the link when its point is >= the start
-// of the last entry of the sector, i.e. when the overflow can actually contain a hit.
+// has two overlapping or touching entries; entries are sorted by start.  A cell with more than 5
+// entries continues in overflow sectors (same format, stored after the primary cells, consecutive
+// per cell); a query only follows when its point is >= the start of the 5th entry, i.e. when the
+// overflow can actually contain a hit.
 //
 // "slot" is the rank of an ensg in hotness order (most feature rows first): the kernel keeps the
 // counters of the first slots in shared memory.  Feature types are looked up per slot
 // (slot_type), which requires ensg -> type to be a function (checked; otherwise no table).
-//
-// Footprint on the hg38-like synthetic index (5.9 M features, shift 11): 1.51 M primary sectors
-// (48 MB) + overflow; sized to stay L2 resident on B200 beside the streamed records.
 #pragma once
 #include <stdint.h>
 #include <algorithm>
 #include <string>
 #include <vector>
 
-#define STAB_ENTRIES 6
-#define STAB_POS_BITS 22
+#define STAB_ENTRIES 5
 #define STAB_MAX_SHIFT 11
 #define STAB_MAX_SLOTS 65535
-#define STAB_MAX_SECTORS (1u << 24)
+#define STAB_BLOCK_SHIFT 7               // ovf_base granularity: 128 primary sectors
+#define STAB_MAX_LINK 1023u
 
 struct StabTable {
     int shift = 11;
@@ -44,10 +52,11 @@ struct StabTable {
     int all_counted = 1;                 // every type is gene / TE / snRNA: the type rule is always true
     std::vector<int64_t> cell_base;      // n_chrom + 1
     std::vector<uint32_t> sectors;       // 8 words per sector: primary cells, then overflow sectors
+    std::vector<uint32_t> ovf_base;      // per block of 256 primary sectors: first overflow sector
     std::vector<uint8_t> slot_type;      // n_slots
     int64_t n_primary = 0, n_overflow = 0, n_entries = 0, n_merged = 0, max_chain = 0, n_dup = 0;
     std::string why_not;                 // non-empty: no table (limits) -> the exact kernel is used
-    size_t bytes() const { return sectors.size() * 4 + cell_base.size() * 8 + slot_type.size(); }
+    size_t bytes() const { return (sectors.size() + ovf_base.size()) * 4 + cell_base.size() * 8 + slot_type.size(); }
 };
 
 struct StabEntry {
@@ -55,24 +64,20 @@ struct StabEntry {
     uint32_t s, len, slot;
 };
 
-inline void stab_pack_sector(uint32_t* w, const StabEntry* e, int n, bool has_link, uint32_t link) {
-    for (int i = 0; i < 8; ++i) w[i] = 0;
-    uint64_t lo = 0, hi = 0, top = 0;            // 160-bit string w3..w7 as lo (64) | hi (64) | top (32)
+inline void stab_pack_sector(uint32_t* w, const StabEntry* e, int n, bool more, uint32_t link) {
+    uint32_t sv[6], ev[6], sl[5];
+    for (int i = 0; i < 6; ++i) { sv[i] = 2047u; ev[i] = 0u; }
+    for (int i = 0; i < 5; ++i) sl[i] = 0xFFFFu;
+    static const int twin_bit[5] = {2, 4, 1, 3, 0};          // entry -> bit of the compacted hit mask
+    uint32_t twin = 0;
     for (int i = 0; i < n; ++i) {
-        w[i >> 1] |= (e[i].slot & 0xFFFFu) << (16 * (i & 1));
-        const uint64_t pos = (uint64_t)e[i].s | ((uint64_t)(e[i].len - 1) << 11);
-        const int off = STAB_POS_BITS * i;
-        if (off < 64) { lo |= pos << off; if (off + STAB_POS_BITS > 64) hi |= pos >> (64 - off); }
-        else if (off < 128) { hi |= pos << (off - 64); if (off + STAB_POS_BITS > 128) top |= pos >> (128 - off); }
-        else top |= pos << (off - 128);
+        sv[i] = e[i].s; ev[i] = e[i].s + e[i].len - 1; sl[i] = e[i].slot & 0xFFFFu;
+        for (int j = 0; j < n; ++j) if (j != i && e[i].slot == e[j].slot) twin |= 1u << twin_bit[i];
     }
-    bool dup = false;
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j < i; ++j) dup |= e[i].slot == e[j].slot;
-    const uint32_t header = (has_link ? 7u : (uint32_t)n) | (dup ? 8u : 0u) | (link << 4);
-    top |= (uint64_t)header << 4;                // bit 132 of the string = bit 4 of w7
-    w[3] = (uint32_t)lo; w[4] = (uint32_t)(lo >> 32); w[5] = (uint32_t)hi; w[6] = (uint32_t)(hi >> 32);
-    w[7] = (uint32_t)top;
+    const uint32_t header = (more ? 1u : 0u) | (twin << 1) | (link << 6);
+    w[0] = sv[0] | sv[1] << 16; w[1] = sv[2] | sv[3] << 16; w[2] = sv[4] | header << 16;
+    w[3] = ev[0] | ev[1] << 16; w[4] = ev[2] | ev[3] << 16; w[5] = ev[4] | sl[4] << 16;
+    w[6] = sl[0] | sl[1] << 16; w[7] = sl[2] | sl[3] << 16;
 }
 
 // L, R sorted by L inside each chromosome; slot[f] < n_slots and type[f] < 8 per feature.
@@ -102,7 +107,7 @@ inline void stab_build(StabTable& t, int n_chrom, const int64_t* chrom_off, cons
         t.cell_base[(size_t)c + 1] = t.cell_base[(size_t)c] + (((int64_t)maxc >> shift) + 1);
     }
     t.n_primary = t.cell_base[(size_t)n_chrom];
-    if ((uint64_t)t.n_primary >= STAB_MAX_SECTORS) { t.why_not = "too many cells for the 24-bit link"; return; }
+    if ((uint64_t)t.n_primary >= 0xFFFFFFF0ull) { t.why_not = "too many cells"; return; }
     // entries: per chromosome, per slot union of [L, R), clipped to cells
     struct Iv { uint32_t slot; int32_t L, R; };
     std::vector<Iv> iv;
@@ -134,62 +139,68 @@ inline void stab_build(StabTable& t, int n_chrom, const int64_t* chrom_off, cons
         return a.slot < b.slot;
     });
     t.n_entries = (int64_t)ent.size();
-    // overflow sectors needed
+    // overflow sectors: consecutive per cell, cells in order; links are relative to the block base
     int64_t n_over = 0;
-    for (size_t i = 0; i < ent.size();) {
-        size_t j = i;
-        while (j < ent.size() && ent[j].cell == ent[i].cell) ++j;
-        const int64_t n = (int64_t)(j - i);
-        if (n > STAB_ENTRIES) n_over += (n - 1) / STAB_ENTRIES;
-        t.max_chain = std::max(t.max_chain, (n + STAB_ENTRIES - 1) / STAB_ENTRIES);
-        i = j;
+    t.ovf_base.assign((size_t)((t.n_primary >> STAB_BLOCK_SHIFT) + 2), 0);
+    {
+        int64_t blk = -1;
+        for (size_t i = 0; i < ent.size();) {
+            size_t j = i;
+            while (j < ent.size() && ent[j].cell == ent[i].cell) ++j;
+            const int64_t n = (int64_t)(j - i), b = ent[i].cell >> STAB_BLOCK_SHIFT;
+            while (blk < b) t.ovf_base[(size_t)++blk] = (uint32_t)(t.n_primary + n_over);
+            if (n > STAB_ENTRIES) n_over += (n - 1) / STAB_ENTRIES;
+            t.max_chain = std::max(t.max_chain, (n + STAB_ENTRIES - 1) / STAB_ENTRIES);
+            i = j;
+        }
+        while (blk + 1 < (int64_t)t.ovf_base.size()) t.ovf_base[(size_t)++blk] = (uint32_t)(t.n_primary + n_over);
     }
     t.n_overflow = n_over;
-    if ((uint64_t)(t.n_primary + n_over) >= STAB_MAX_SECTORS) { t.why_not = "too many sectors for the 24-bit link"; return; }
+    if ((uint64_t)(t.n_primary + n_over) >= 0xFFFFFFF0ull) { t.why_not = "too many sectors"; return; }
     t.sectors.assign((size_t)(t.n_primary + n_over) * 8, 0);
+    for (int64_t c = 0; c < t.n_primary; ++c) stab_pack_sector(&t.sectors[(size_t)c * 8], nullptr, 0, false, 0);
     int64_t next_over = t.n_primary;
     for (size_t i = 0; i < ent.size();) {
         size_t j = i;
         while (j < ent.size() && ent[j].cell == ent[i].cell) ++j;
         int64_t sec = ent[i].cell;
+        const uint32_t base = t.ovf_base[(size_t)(ent[i].cell >> STAB_BLOCK_SHIFT)];
         for (size_t k = i; k < j; k += STAB_ENTRIES) {
             const int n = (int)std::min<size_t>(STAB_ENTRIES, j - k);
             const bool more = k + STAB_ENTRIES < j;
-            const int64_t link = more ? next_over++ : 0;
-            stab_pack_sector(&t.sectors[(size_t)sec * 8], &ent[k], n, more, (uint32_t)link);
-            if (t.sectors[(size_t)sec * 8 + 7] & 0x80u) t.n_dup++;
-            sec = link;
+            uint32_t link = 0;
+            if (more && k == i) {                    // primary sector: relative link
+                if ((uint64_t)next_over - base > STAB_MAX_LINK) { t.why_not = "overflow link out of range"; t.sectors.clear(); return; }
+                link = (uint32_t)(next_over - base);
+            }
+            stab_pack_sector(&t.sectors[(size_t)sec * 8], &ent[k], n, more, link);
+            if (t.sectors[(size_t)sec * 8 + 2] & 0x3E0000u) t.n_dup++;
+            if (more) sec = next_over++;
         }
         i = j;
     }
 }
 
 // S(x) as sorted distinct slots (host-side reader mirroring the kernel; tests and tools)
-inline std::vector<uint32_t> stab_lookup(const StabTable& t, int c, int64_t x) {
+inline std::vector<uint32_t> stab_lookup(const StabTable& t, int c, int64_t x, int* n_sectors = nullptr) {
     std::vector<uint32_t> s;
+    if (n_sectors) *n_sectors = 0;
     if (x < 0) return s;
     const int64_t cell = x >> t.shift;
     if (cell >= t.cell_base[(size_t)c + 1] - t.cell_base[(size_t)c]) return s;
     const uint32_t r = (uint32_t)(x & (((int64_t)1 << t.shift) - 1));
-    int64_t sec = t.cell_base[(size_t)c] + cell;
+    const int64_t prim = t.cell_base[(size_t)c] + cell;
+    int64_t sec = prim;
     for (;;) {
         const uint32_t* w = &t.sectors[(size_t)sec * 8];
-        const uint32_t header = w[7] >> 4;
-        const bool has_link = (header & 7u) == 7u;
-        const int n = has_link ? STAB_ENTRIES : (int)(header & 7u);
-        uint32_t last_s = 0;
-        for (int i = 0; i < n; ++i) {
-            const int off = STAB_POS_BITS * i;
-            uint64_t bits = 0;                       // 64-bit window of the string starting at word 3 + off / 32
-            const int wi = 3 + off / 32;
-            bits = (uint64_t)w[wi] | (wi + 1 < 8 ? (uint64_t)w[wi + 1] << 32 : 0);
-            const uint32_t pos = (uint32_t)(bits >> (off % 32)) & ((1u << STAB_POS_BITS) - 1);
-            const uint32_t st = pos & 2047u, lm1 = pos >> 11;
-            last_s = st;
-            if (r - st <= lm1) s.push_back((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+        if (n_sectors) ++*n_sectors;
+        const uint32_t header = w[2] >> 16;
+        for (int i = 0; i < STAB_ENTRIES; ++i) {
+            const uint32_t st = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu, en = (w[3 + (i >> 1)] >> (16 * (i & 1))) & 0xFFFFu;
+            if (st <= r && r <= en) s.push_back(i < 4 ? (w[6 + (i >> 1)] >> (16 * (i & 1))) & 0xFFFFu : w[5] >> 16);
         }
-        if (!has_link || r < last_s) break;
-        sec = header >> 4;
+        if (!(header & 1u) || r < (w[2] & 0xFFFFu)) break;
+        sec = (sec == prim) ? (int64_t)t.ovf_base[(size_t)(prim >> STAB_BLOCK_SHIFT)] + (header >> 6) : sec + 1;
     }
     std::sort(s.begin(), s.end());
     s.erase(std::unique(s.begin(), s.end()), s.end());

@@ -205,6 +205,8 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
                 cells[(size_t)c] = make_uint2((unsigned)st.cell_base[(size_t)c], (unsigned)(st.cell_base[(size_t)c + 1] - st.cell_base[(size_t)c]));
             TEC_CUDA(cudaMalloc(&ix.st_cells, cells.size() * sizeof(uint2)));
             TEC_CUDA(cudaMalloc(&ix.st_slot_type, st.slot_type.size()));
+            TEC_CUDA(cudaMalloc(&ix.st_ovf_base, st.ovf_base.size() * 4));
+            TEC_CUDA(cudaMemcpyAsync(ix.st_ovf_base, st.ovf_base.data(), st.ovf_base.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
             if (!st.sectors.empty())
                 TEC_CUDA(cudaMemcpyAsync(ix.st_sectors, st.sectors.data(), st.sectors.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
             TEC_CUDA(cudaMemcpyAsync(ix.st_cells, cells.data(), cells.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
@@ -214,6 +216,48 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
             ix.st_primary = st.n_primary; ix.st_overflow = st.n_overflow; ix.st_entries = st.n_entries;
         } else {
             ctx->err = "cell table not built: " + st.why_not;      // informational; exact kernel is used
+        }
+    }
+    // cell table of the single-cell Part 3: intervals [L-1, R+1), one slot per (ensg, strand) pair
+    {
+        std::vector<uint32_t> pkey((size_t)nf), uniq;
+        for (int64_t i = 0; i < nf; ++i) pkey[(size_t)i] = (fslot[(size_t)i] << 3) | info_strand(info[(size_t)i]);
+        uniq = pkey;
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        if (uniq.size() <= STAB_MAX_SLOTS) {
+            std::vector<uint32_t> pslot((size_t)nf);
+            std::vector<int32_t> L1((size_t)nf), R1((size_t)nf);
+            std::vector<uint8_t> ptype(std::max<size_t>(uniq.size(), 1), 0);
+            for (int64_t i = 0; i < nf; ++i) {
+                const uint32_t ps = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), pkey[(size_t)i]) - uniq.begin());
+                pslot[(size_t)i] = ps;
+                ptype[ps] = type_code[i];
+                L1[(size_t)i] = std::max(L[i] - 1, 0);
+                // a feature whose bucket range is empty (R//bs < L//bs) is never a candidate (genelist.py:367-380)
+                R1[(size_t)i] = (floordiv(R[i], bucket_size) < L[i] / bucket_size) ? L1[(size_t)i] : R[i] + 1;
+            }
+            StabTable st;
+            stab_build(st, n_chrom, chrom_off, L1.data(), R1.data(), pslot.data(), type_code, (int)uniq.size(), ctx->opt_stab_shift);
+            if (st.why_not.empty()) {
+                std::vector<uint2> cells((size_t)std::max(n_chrom, 1));
+                for (int c = 0; c < n_chrom; ++c)
+                    cells[(size_t)c] = make_uint2((unsigned)st.cell_base[(size_t)c], (unsigned)(st.cell_base[(size_t)c + 1] - st.cell_base[(size_t)c]));
+                TEC_CUDA(cudaMalloc(&ix.sc_sectors, std::max<size_t>(st.sectors.size(), 8) * 4));
+                TEC_CUDA(cudaMalloc(&ix.sc_cells, cells.size() * sizeof(uint2)));
+                TEC_CUDA(cudaMalloc(&ix.sc_ovf_base, st.ovf_base.size() * 4));
+                TEC_CUDA(cudaMalloc(&ix.sc_pair_key, std::max<size_t>(uniq.size(), 1) * 4));
+                TEC_CUDA(cudaMalloc(&ix.sc_pair_type, ptype.size()));
+                if (!st.sectors.empty())
+                    TEC_CUDA(cudaMemcpyAsync(ix.sc_sectors, st.sectors.data(), st.sectors.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                TEC_CUDA(cudaMemcpyAsync(ix.sc_cells, cells.data(), cells.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+                TEC_CUDA(cudaMemcpyAsync(ix.sc_ovf_base, st.ovf_base.data(), st.ovf_base.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                if (!uniq.empty())
+                    TEC_CUDA(cudaMemcpyAsync(ix.sc_pair_key, uniq.data(), uniq.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                TEC_CUDA(cudaMemcpyAsync(ix.sc_pair_type, ptype.data(), ptype.size(), cudaMemcpyHostToDevice, ctx->stream));
+                TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+                ix.sc_shift = st.shift; ix.has_sc_stab = true; ix.sc_stab_bytes = st.bytes();
+            }
         }
     }
     // per-feature counters + statistics block
@@ -264,7 +308,7 @@ static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, 
             bulk_count_cell_kernel<false><<<blocks, BULK_THREADS, 0, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, ctx->d_slow_list);
         ctx->launches++;
         TEC_CUDA(cudaGetLastError());
-        const int sblocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)ctx->n_sm * 8);
+        const int sblocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)ctx->n_sm * 4);
         if (ctx->paired)
             bulk_slow_kernel<true><<<sblocks, 256, 0, ctx->stream>>>(iv, sv, 1, start, end, chrom, counts, stats, ctx->d_slow_list);
         else
@@ -376,6 +420,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "bulk_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "bulk_algo: -1, 0 or 1"); ctx->opt_bulk_algo = (int)value; }
     else if (k == "stab_shift") { if (value < 8 || value > STAB_MAX_SHIFT) TEC_FAIL(TEC_ERR_ARG, "stab_shift: 8..11"); ctx->opt_stab_shift = (int)value; }
+    else if (k == "sc_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "sc_algo: -1, 0 or 1"); ctx->opt_sc_algo = (int)value; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else TEC_FAIL(TEC_ERR_ARG, "tec_set_option: unknown key " + k);
     return TEC_OK;
@@ -386,6 +431,8 @@ extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
     const std::string k(key);
     if (k == "has_stab") return ctx->idx.has_stab ? 1 : 0;
     if (k == "stab_bytes") return (int64_t)ctx->idx.stab_bytes;
+    if (k == "has_sc_stab") return ctx->idx.has_sc_stab ? 1 : 0;
+    if (k == "sc_stab_bytes") return (int64_t)ctx->idx.sc_stab_bytes;
     if (k == "n_sm") return ctx->n_sm;
     if (k == "n_features") return ctx->idx.n_feat;
     if (k == "last_slow_units") {          // units the last fast-kernel launch handed to the exact kernel

@@ -58,14 +58,46 @@ def check_against_oracle(engine, idx, r, qual, strand, n_wl, bundle_keys, maxcel
     return out
 
 
+@pytest.mark.parametrize("algo", [0, 1])
 @pytest.mark.parametrize("strand", [False, True])
 @pytest.mark.parametrize("bundle_keys,maxcells,pad", [(10_000_000, 50, 20), (700, 50, 20), (64, 20, 5), (5, 200, 1000)])
-def test_sc_matches_oracle_seeded(engine, strand, bundle_keys, maxcells, pad):
+def test_sc_matches_oracle_seeded(engine, strand, bundle_keys, maxcells, pad, algo):
+    """algo 0 = Part 3 by exact search only, 1 = cell table (exact search for degenerate fragments)."""
     idx = synth.synth_index(11, n_te=30000, n_exon=9000, n_gene=600, chrom_len=3_000_000, n_chrom=3)
     r = synth.synth_sc_reads(12, idx, 30000, n_whitelist=300, n_cells=60, umis_per_cell=40)
+    engine.set_option("sc_algo", algo)
     engine.upload_index(idx)
+    assert engine.get_info("has_sc_stab") == 1
     out = check_against_oracle(engine, idx, r, 20, strand, 300, bundle_keys, maxcells, pad, chunks=3)
+    engine.set_option("sc_algo", -1)
     assert out["stats"]["assigned"] > 20
+
+
+def test_sc_fragment_edge_geometry(engine):
+    """Fragments that touch feature ends by exactly one base, sit on bucket and cell borders, start
+    at 0, or are degenerate (end <= start): the 1-bp-wider inclusive tests of te_count.py:645/:648."""
+    from te_counter_b200.index import GlbIndex
+    L = np.array([0, 1000, 2047, 2048, 9999, 10000, 19990, 30000, 30000, 40960], np.int32)
+    R = np.array([50, 2047, 2100, 4096, 10000, 10050, 20010, 30100, 30100, 45000], np.int32)
+    n = len(L)
+    idx = GlbIndex(["1"], np.zeros(n, np.int32), L, R, np.arange(n, dtype=np.int32) % 7,
+                   np.array([1, 2, 2, 1, 2, 2, 1, 2, 2, 1], np.uint8), np.array([0, 1, 0, 1, 0, 1, 0, 1, 0, 1], np.uint8),
+                   ["e%d" % i for i in range(7)])
+    starts, ends = [], []
+    for a, b in zip(L.tolist(), R.tolist()):
+        for d in (-2, -1, 0, 1, 2):
+            starts += [max(0, a + d), max(0, b + d), max(0, a + d - 90), max(0, b + d)]
+            ends += [max(0, a + d) + 90, max(0, b + d) + 90, max(0, a + d), max(0, b + d)]      # the last one: end == start
+    m = len(starts)
+    r = {"start": np.array(starts, np.int32), "end": np.array(ends, np.int32), "chrom": np.zeros(m, np.uint16),
+         "mapq": np.full(m, 60, np.uint8), "flag": np.zeros(m, np.uint8),
+         "cell": (np.arange(m) % 3).astype(np.uint32), "umi": ((np.arange(m, dtype=np.uint64) + np.uint64(1)) << np.uint64(30))}
+    for algo in (0, 1):
+        engine.set_option("sc_algo", algo)
+        engine.upload_index(idx)
+        for strand in (False, True):
+            check_against_oracle(engine, idx, r, 20, strand, 3, 10_000_000, 3, 0)
+    engine.set_option("sc_algo", -1)
 
 
 def test_sc_many_places_per_key(engine):

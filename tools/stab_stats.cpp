@@ -22,10 +22,8 @@ int main(int argc, char** argv) {
         int c = rng() % n_chrom; int64_t lo = off[c], hi = off[c + 1]; if (hi == lo) continue;
         int64_t f = lo + rng() % (hi - lo); int64_t x = (it & 1) ? L[f] + (int64_t)(rng() % 200) - 100 : R[f] + (int64_t)(rng() % 5) - 2; if (it % 7 == 0) x = rng() % 250000000; if (it % 11 == 0) x = (x >> shift) << shift;
         if (it >= 30000) {  // follow-rate sample only
-            if (x < 0 || (x >> shift) >= t.cell_base[c + 1] - t.cell_base[c]) continue;
-            const uint32_t* w = &t.sectors[(size_t)(t.cell_base[c] + (x >> shift)) * 8];
-            uint32_t h = w[7] >> 4; total++;
-            if ((h & 7u) == 7u) { int n = 6; int o = 22 * (n - 1); int wi = 3 + o / 32; uint64_t b = (uint64_t)w[wi] | (wi + 1 < 8 ? (uint64_t)w[wi + 1] << 32 : 0); uint32_t ls = (uint32_t)(b >> (o % 32)) & 2047u; if ((uint32_t)(x & ((1 << shift) - 1)) >= ls) follow++; }
+            int ns = 0; stab_lookup(t, c, x, &ns);
+            if (ns) { total++; if (ns > 1) follow++; }
             continue;
         }
         std::set<uint32_t> want;
