@@ -352,12 +352,17 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     bpr = BYTES_PER_RECORD[wl] + INDEX_BYTES_PER_FEATURE * idx.n_features / float(n_rec)
     achieved = n_rec * bpr / (kern_ms / 1e3) / 1e9
+    traffic = None          # DRAM bytes per launch from the committed ncu capture, scaled to this launch size
+    tp = os.path.join(ROOT, "profiles", "r01_bulk_ncu_traffic.json")
+    if paired and os.path.exists(tp):
+        t = json.load(open(tp))
+        traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["records_per_launch"] * n_rec
     line = {"metric": "reads_per_sec", "value": value, "unit": "records/s", "n_gpus": world, "steps": K,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(args, n_rec, world), "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "bulk_count_cell_kernel<%s> (+ bulk_slow_kernel on flagged units)" % ("paired" if paired else "single"),
                          "cell_table_bytes": eng.get_info("stab_bytes"), "slow_units_per_launch": eng.get_info("last_slow_units"),
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_record": bpr},

@@ -33,11 +33,7 @@ SC_CELL_PAD = 1000               # te_count.py:502  `maxcells+1000`
 
 
 def _open_alignment(filename):
-    try:
-        import pysam
-    except ImportError:
-        from . import bam as _bam           # native BGZF/BAM + SAM reader (no pysam in this image)
-        return _bam.AlignmentFile(filename, 'r')
+    import pysam                            # BAM decoding stays with pysam, as in the reference (te_count.py:11)
     return pysam.AlignmentFile(filename, 'r')
 
 
