@@ -382,19 +382,21 @@ def run_ours_sc(args, rank, world, local, dev):
     import torch
     import torch.distributed as dist
     from te_counter_b200 import _lib, synth
-    if world > 1:
-        raise SystemExit("sc workload: multi-GPU sharding by cell is not wired yet (DESIGN.md, next)")
-    n_rec = args.records or CONFIG_RECORDS["sc"]
+    from te_counter_b200 import dist as tdist
+    n_cfg = args.records or CONFIG_RECORDS["sc"]
+    n_rec = n_cfg if args.scaling == "weak" else n_cfg // world
     n_wl, maxcells, pad, bundle_keys = 100_000, 10_000, 1000, 10_000_000
     idx = make_index(args.index_scale)
     eng = _lib.Engine(local)
     eng.upload_index(idx)
+    # this rank's slice of the coordinate-sorted file: `parts` consecutive genome slices
     parts = max(1, (n_rec + 124_999_999) // 125_000_000)
     names = ("start", "end", "chrom", "mapq", "flag", "cell", "umi")
     chunks = {k: [] for k in names}
     for p in range(parts):
         n_p = n_rec // parts + (1 if p < n_rec % parts else 0)
-        r = synth.synth_sc_reads(synth.SEED, idx, n_p, n_whitelist=n_wl, device=dev, as_numpy=False, part=(p, parts))
+        r = synth.synth_sc_reads(synth.SEED, idx, n_p, n_whitelist=n_wl, device=dev, as_numpy=False,
+                                 part=(rank * parts + p, parts * world))
         for k in names:
             chunks[k].append(r[k])
         del r
@@ -409,6 +411,8 @@ def run_ours_sc(args, rank, world, local, dev):
     def step():
         eng.sc_begin(20, strand, n_wl)
         eng.sc_push_dev(n_rec, *ptrs)
+        if world > 1:
+            tdist.sc_exchange_by_cell(eng, dev)             # all-to-all by cell over NCCL
         nt, nh = eng.sc_finalize(bundle_keys, maxcells, pad)
         sel = eng.sc_select(maxcells, nh)
         return nt, nh, sel
@@ -416,6 +420,8 @@ def run_ours_sc(args, rank, world, local, dev):
     for _ in range(max(3, args.warmup)):
         step()
     eng.sync()
+    if world > 1:
+        dist.barrier()
     K = args.steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
@@ -431,12 +437,22 @@ def run_ours_sc(args, rank, world, local, dev):
     e1.record(ext)
     eng.sync()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
     launches = eng.launch_count() - l0
     ms_step = e0.elapsed_time(e1) / K
-    value = n_rec / (ms_step / 1e3)
+    if world > 1:
+        # the exchange runs on torch's stream and the step has host synchronisation points: take the wall clock
+        # of the timed region (barrier + synchronize on both sides), max over ranks
+        t = torch.tensor([max(ms_step, (t1 - t0) * 1e3 / K)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    value = n_rec * world / (ms_step / 1e3)
     ensg, cell, count, hcell, hcount, st = eng.sc_fetch(nt, nh)
+    if world > 1:
+        args.no_e2e = args.no_cpu = True
 
     e2e = None
     if not args.no_e2e:
@@ -500,6 +516,8 @@ def run_ours_sc(args, rank, world, local, dev):
     peak, peak_src = load_peaks()
     bpr = BYTES_PER_RECORD["sc"] + INDEX_BYTES_PER_FEATURE * idx.n_features / float(n_rec)
     achieved = n_rec * bpr / (ms_step / 1e3) / 1e9
+    if world > 1:
+        dist.barrier()
     line = {"metric": "reads_per_sec", "value": value, "unit": "records/s", "n_gpus": world, "steps": K,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -516,8 +534,11 @@ def run_ours_sc(args, rank, world, local, dev):
                       "segments": int(st[_lib.SS_SEGMENTS]), "bundles": int(st[_lib.SS_BUNDLES]),
                       "valid": int(st[_lib.SS_VALID]), "assigned": int(st[_lib.SS_ASSIGNED]),
                       "triples": int(nt), "hit_cells": int(nh), "selected": int(len(sel))}}
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
     eng.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

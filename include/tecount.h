@@ -171,6 +171,24 @@ int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcells, int64_t
  * stats[TEC_SC_NSTATS].  Any pointer may be NULL. */
 int tec_sc_fetch(tec_ctx* ctx, int32_t* ensg, uint32_t* cell, int64_t* count,
                  uint32_t* hit_cell, int64_t* hit_count, int64_t* stats);
+/* ---- single cell on several GPUs (one process per GPU) -------------------------
+ * The (cell, UMI) collapse is per cell, so after Part 1's filter the survivors are exchanged by cell
+ * (all-to-all, done by the caller on the exported device columns), each carrying its position in
+ * the job-wide survivor order.  tec_sc_finalize then runs the same pipeline per rank and calls the
+ * collective at the few points that are global: the bundle boundaries of te_count.py:377 (a running
+ * count over the whole file), the per-cell raw counts and first appearances behind the top-cell
+ * choice (:502), the per-bundle cell presence behind the held-line rule (:528), the per-cell hit
+ * counts (:653) and the statistics.  Triples stay on the rank that owns the cell.
+ *   fn(user, dev_ptr, count, dtype, op): in-place all-reduce of a device buffer over the ranks;
+ *   dtype 0 u32, 1 u64, 2 i64; op 0 sum, 1 min, 2 max; returns 0 on success. */
+typedef int (*tec_allreduce_fn)(void* user, void* dev_ptr, int64_t count, int dtype, int op);
+int tec_sc_set_collective(tec_ctx* ctx, tec_allreduce_fn fn, void* user, int rank, int world);
+/* device pointers of the survivor columns after the pushes (cs = chrom << 2 | strand code) */
+int tec_sc_export_dev(tec_ctx* ctx, int64_t* n, void** cell, void** umi, void** left, void** rite, void** cs);
+/* replace the survivors by the exchanged ones (device pointers), ascending in gidx */
+int tec_sc_import_dev(tec_ctx* ctx, int64_t n, const uint32_t* cell, const uint64_t* umi, const int32_t* left,
+                      const int32_t* rite, const uint32_t* cs, const uint64_t* gidx);
+
 /* sc_save_result's choice of rows (te_count.py:724-733): hit cells by count descending, ties by
  * ascending id, at most maxcells.  cells_out must hold min(maxcells, n_hit_cells) entries. */
 int tec_sc_select(tec_ctx* ctx, int64_t maxcells, uint32_t* cells_out, int64_t* n_out);

@@ -53,7 +53,12 @@ SIGNATURES = {
     "tec_sc_finalize": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_i64p, _c_i64p]),
     "tec_sc_fetch": (ctypes.c_int, [_vp, _c_i32p, _c_u32p, _c_i64p, _c_u32p, _c_i64p, _c_i64p]),
     "tec_sc_select": (ctypes.c_int, [_vp, ctypes.c_int64, _c_u32p, _c_i64p]),
+    "tec_sc_set_collective": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int]),
+    "tec_sc_export_dev": (ctypes.c_int, [_vp, _c_i64p] + [ctypes.POINTER(_vp)] * 5),
+    "tec_sc_import_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int)
 
 _lib = None
 
@@ -225,6 +230,36 @@ class Engine:
                                            ctypes.cast(hcount.ctypes.data, _c_i64p),
                                            ctypes.cast(stats.ctypes.data, _c_i64p)))
         return ensg, cell, count, hcell, hcount, stats
+
+    def sc_set_collective(self, fn, rank, world):
+        """fn(dev_ptr, count, dtype, op) -> None: in-place all-reduce over the ranks (dist.py)."""
+        if fn is None:
+            self._coll = None
+            self._check(self._lib.tec_sc_set_collective(self._h, None, None, 0, 1))
+            return
+
+        def _cb(_user, ptr, count, dtype, op):
+            try:
+                fn(ptr, count, dtype, op)
+                return 0
+            except Exception:          # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        self._coll = ALLREDUCE_FN(_cb)                    # keep the trampoline alive
+        self._check(self._lib.tec_sc_set_collective(self._h, ctypes.cast(self._coll, _vp), None, int(rank), int(world)))
+
+    def sc_export_dev(self):
+        """(n, {column: device pointer}) of the survivors held after the pushes."""
+        n = ctypes.c_int64(0)
+        p = [_vp() for _ in range(5)]
+        self._check(self._lib.tec_sc_export_dev(self._h, ctypes.byref(n), *[ctypes.byref(x) for x in p]))
+        return n.value, dict(zip(("cell", "umi", "left", "rite", "cs"), [x.value or 0 for x in p]))
+
+    def sc_import_dev(self, n, cell, umi, left, rite, cs, gidx):
+        """device pointers (ints) of the exchanged survivors, ascending in gidx"""
+        self._check(self._lib.tec_sc_import_dev(self._h, int(n), cell, umi, left, rite, cs, gidx))
 
     def sc_select(self, maxcells, n_hit_cells):
         out = np.zeros(max(1, min(int(maxcells), int(n_hit_cells))), dtype=np.uint32)

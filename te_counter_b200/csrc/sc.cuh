@@ -40,6 +40,12 @@ struct ScState {
     int32_t* rite = nullptr;
     u32* cs = nullptr;              // chrom << 2 | strand code (0 '+', 1 '-', 2 'NA')
     int64_t n = 0, cap = 0;
+    u64* gidx = nullptr;            // multi-GPU: position of each survivor in the whole job's survivor order
+    int64_t gidx_cap = 0;
+    bool has_gidx = false;
+    tec_allreduce_fn coll = nullptr;    // multi-GPU: all-reduce over the ranks' device buffers
+    void* coll_user = nullptr;
+    int rank = 0, world = 1;
     u64* d_stats = nullptr;         // TEC_SC_NSTATS
     // per-push scratch
     u32* pos = nullptr;
@@ -65,7 +71,7 @@ static void sc_free_results(tec_ctx* ctx, ScState* s) {
 
 inline void tec_ctx::free_sc() {
     if (!sc) return;
-    cudaFree(sc->cell); cudaFree(sc->umi); cudaFree(sc->left); cudaFree(sc->rite); cudaFree(sc->cs);
+    cudaFree(sc->cell); cudaFree(sc->umi); cudaFree(sc->left); cudaFree(sc->rite); cudaFree(sc->cs); cudaFree(sc->gidx);
     cudaFree(sc->d_stats); cudaFree(sc->pos); cudaFree(sc->cub_tmp);
     sc_free_results(this, sc);
     delete sc;
@@ -107,7 +113,7 @@ struct MaxU32 { __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { 
 struct MaxI32 { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
 struct SumU32 { __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a + b; } };
 
-#define SC_GRID(n) (int)std::min<int64_t>(((n) + 255) / 256, (int64_t)ctx->n_sm * 16), 256, 0, ctx->stream
+#define SC_GRID(n) (int)std::max<int64_t>(1, std::min<int64_t>(((n) + 255) / 256, (int64_t)ctx->n_sm * 16)), 256, 0, ctx->stream
 #define SC_LOOP(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
 
 // ------------------------------------------------------------------------------------ Part 1: filter
@@ -211,6 +217,9 @@ __global__ void sc_find_kernel(int64_t len, int64_t pos, int64_t s, const u32* _
     }
 }
 
+// position of survivor i in the job-wide survivor order (multi-GPU: gidx; one GPU: i itself)
+__device__ __forceinline__ int64_t sc_pos(const u64* __restrict__ gidx, u32 i) { return gidx ? (int64_t)gidx[i] : (int64_t)i; }
+
 __device__ __forceinline__ int sc_bundle_of(const int64_t* __restrict__ bstart, int n_b, int64_t i) {
     int lo = 0, hi = n_b;                     // last b with bstart[b] <= i
     while (hi - lo > 1) {
@@ -220,20 +229,34 @@ __device__ __forceinline__ int sc_bundle_of(const int64_t* __restrict__ bstart, 
     return lo;
 }
 
+// multi-GPU bundle boundary search: histogram of the first-in-bundle records (bundle start S) whose
+// position falls in [lo, lo + n_bins * width)
+__global__ void sc_newkey_hist_kernel(int64_t n, const u64* __restrict__ gidx, const u32* __restrict__ prev, int64_t S, int64_t lo,
+                                      int64_t width, int n_bins, u64* __restrict__ hist) {
+    SC_LOOP(i, n) {
+        const int64_t g = (int64_t)gidx[i];
+        if (g < lo) continue;
+        const int64_t b = (g - lo) / width;
+        if (b >= n_bins) continue;
+        const u32 p = prev[i];
+        if (p == SC_NONE || (int64_t)gidx[p] < S) atomicAdd(hist + b, 1ULL);
+    }
+}
+
 // segment heads: (cell, umi, bundle) changes
-__global__ void sc_seghead_kernel(int64_t n, const u32* __restrict__ perm, const u32* __restrict__ khead_pos,
+__global__ void sc_seghead_kernel(int64_t n, const u32* __restrict__ perm, const u64* __restrict__ gidx, const u32* __restrict__ khead_pos,
                                   const int64_t* __restrict__ bstart, int n_b, u32* __restrict__ bundle, u32* __restrict__ shead_pos) {
     SC_LOOP(j, n) {
-        const u32 b = (u32)sc_bundle_of(bstart, n_b, perm[j]);
+        const u32 b = (u32)sc_bundle_of(bstart, n_b, sc_pos(gidx, perm[j]));
         bundle[j] = b;
         bool head = (j == 0) || khead_pos[j] == (u32)j;
-        if (!head) head = (u32)sc_bundle_of(bstart, n_b, perm[j - 1]) != b;
+        if (!head) head = (u32)sc_bundle_of(bstart, n_b, sc_pos(gidx, perm[j - 1])) != b;
         shead_pos[j] = head ? (u32)j : 0u;
     }
 }
 
 // per element: already-seen / raw counts (te_count.py:444-473), per (bundle, cell) tables
-__global__ void sc_segstat_kernel(int64_t n, int64_t n_wl, const u32* __restrict__ perm, const u32* __restrict__ scell, const u64* __restrict__ sumi,
+__global__ void sc_segstat_kernel(int64_t n, int64_t n_wl, const u32* __restrict__ perm, const u64* __restrict__ gidx, const u32* __restrict__ scell, const u64* __restrict__ sumi,
                                   const u32* __restrict__ cs, const u32* __restrict__ shead_pos, const u32* __restrict__ bundle,
                                   u32* __restrict__ raw, u32* __restrict__ first_i, u64* __restrict__ minumi, u32* __restrict__ present,
                                   u64* __restrict__ stats) {
@@ -244,7 +267,7 @@ __global__ void sc_segstat_kernel(int64_t n, int64_t n_wl, const u32* __restrict
         if (h == (u32)j) {
             n_seg++;
             atomicAdd(raw + c, 1u);                                                    // :471-473
-            atomicMin(first_i + c, perm[j]);
+            atomicMin(first_i + c, (u32)sc_pos(gidx, perm[j]));
             const int64_t bc = (int64_t)bundle[j] * n_wl + c;
             atomicMin(minumi + bc, sumi[j]);
             present[bc] = 1u;
@@ -582,7 +605,7 @@ extern "C" int tec_sc_begin(tec_ctx* ctx, int qual, int strand, int64_t n_whitel
     ScState* s = ctx->sc;
     sc_free_results(ctx, s);
     s->qual = qual; s->strand = strand ? 1 : 0; s->n_wl = n_whitelist;
-    s->n = 0; s->units = 0; s->active = true; s->finalized = false;
+    s->n = 0; s->units = 0; s->active = true; s->finalized = false; s->has_gidx = false;
     if (!s->d_stats) TEC_CUDA(cudaMalloc(&s->d_stats, TEC_SC_NSTATS * 8));
     TEC_CUDA(cudaMemsetAsync(s->d_stats, 0, TEC_SC_NSTATS * 8, ctx->stream));
     memset(s->stats, 0, sizeof(s->stats));
@@ -706,6 +729,130 @@ extern "C" int tec_sc_push(tec_ctx* ctx, int64_t n_rec, const int32_t* start, co
     return TEC_OK;
 }
 
+// all-reduce of a device buffer over the ranks (no-op on one GPU); dtype 0 u32, 1 u64, 2 i64; op 0 sum, 1 min, 2 max
+static int sc_allreduce(tec_ctx* ctx, void* dev, int64_t count, int dtype, int op) {
+    ScState* s = ctx->sc;
+    if (s->world <= 1 || !s->coll) return TEC_OK;
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (s->coll(s->coll_user, dev, count, dtype, op) != 0) TEC_FAIL(TEC_ERR_STATE, "single-cell collective callback failed");
+    return TEC_OK;
+}
+
+#define SC_HIST_BINS 16384
+
+// bundle starts in job-wide survivor positions, identical on every rank (te_count.py:377)
+static int sc_bundles_global(tec_ctx* ctx, ScArena& A, int64_t N, const u32* prev, int64_t bundle_keys, std::vector<int64_t>& bstart, int64_t& g_end) {
+    ScState* s = ctx->sc;
+    u64* hist = nullptr;
+    TEC_CUDA(A.get(&hist, SC_HIST_BINS + 1));
+    // G = number of survivors of the whole job
+    u64 h_last = 0;
+    if (N) TEC_CUDA(cudaMemcpyAsync(&h_last, s->gidx + N - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    u64 h_end = N ? h_last + 1 : 0;
+    TEC_CUDA(cudaMemcpyAsync(hist, &h_end, 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = sc_allreduce(ctx, hist, 1, 1, 2);
+    if (rc) return rc;
+    TEC_CUDA(cudaMemcpyAsync(&h_end, hist, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int64_t G = (int64_t)h_end;
+    g_end = G;
+    std::vector<u64> h_hist(SC_HIST_BINS);
+    int64_t S = 0;
+    while (S < G) {
+        bstart.push_back(S);
+        int64_t lo = S, span = G - S, need = bundle_keys;
+        bool found = false;
+        for (;;) {
+            const int64_t width = (span + SC_HIST_BINS - 1) / SC_HIST_BINS;
+            TEC_CUDA(cudaMemsetAsync(hist, 0, SC_HIST_BINS * 8, ctx->stream));
+            if (N) sc_newkey_hist_kernel<<<SC_GRID(N)>>>(N, s->gidx, prev, S, lo, width, SC_HIST_BINS, hist);
+            ctx->launches++;
+            rc = sc_allreduce(ctx, hist, SC_HIST_BINS, 1, 0);
+            if (rc) return rc;
+            TEC_CUDA(cudaMemcpyAsync(h_hist.data(), hist, SC_HIST_BINS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+            int b = 0;
+            int64_t cum = 0;
+            for (; b < SC_HIST_BINS; ++b) {
+                if (cum + (int64_t)h_hist[(size_t)b] >= need) break;
+                cum += (int64_t)h_hist[(size_t)b];
+            }
+            if (b == SC_HIST_BINS) break;                        // fewer than bundle_keys keys left: last bundle
+            if (width == 1) { S = lo + b + 1; found = true; break; }
+            need -= cum;
+            lo += (int64_t)b * width;
+            span = width;
+        }
+        if (!found) break;
+    }
+    A.release(hist);
+    return TEC_OK;
+}
+
+// ---- multi-GPU plumbing (te_counter_b200/dist.py drives it)
+extern "C" int tec_sc_set_collective(tec_ctx* ctx, tec_allreduce_fn fn, void* user, int rank, int world) {
+    if (!ctx) return TEC_ERR_ARG;
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) TEC_FAIL(TEC_ERR_ARG, "tec_sc_set_collective: bad arguments");
+    if (!ctx->sc) ctx->sc = new ScState();
+    ctx->sc->coll = world > 1 ? fn : nullptr;
+    ctx->sc->coll_user = user;
+    ctx->sc->rank = rank;
+    ctx->sc->world = world;
+    return TEC_OK;
+}
+
+extern "C" int tec_sc_export_dev(tec_ctx* ctx, int64_t* n, void** cell, void** umi, void** left, void** rite, void** cs) {
+    if (!ctx) return TEC_ERR_ARG;
+    ScState* s = ctx->sc;
+    if (!s || !s->active) TEC_FAIL(TEC_ERR_STATE, "tec_sc_export_dev: tec_sc_begin not called");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n) *n = s->n;
+    if (cell) *cell = s->cell;
+    if (umi) *umi = s->umi;
+    if (left) *left = s->left;
+    if (rite) *rite = s->rite;
+    if (cs) *cs = s->cs;
+    return TEC_OK;
+}
+
+extern "C" int tec_sc_import_dev(tec_ctx* ctx, int64_t n, const uint32_t* cell, const uint64_t* umi, const int32_t* left,
+                                 const int32_t* rite, const uint32_t* cs, const uint64_t* gidx) {
+    if (!ctx) return TEC_ERR_ARG;
+    ScState* s = ctx->sc;
+    if (!s || !s->active) TEC_FAIL(TEC_ERR_STATE, "tec_sc_import_dev: tec_sc_begin not called");
+    if (n < 0 || n >= (int64_t)0x7FFFFFF0) TEC_FAIL(TEC_ERR_ARG, "tec_sc_import_dev: bad record count");
+    if (n && (!cell || !umi || !left || !rite || !cs || !gidx)) TEC_FAIL(TEC_ERR_ARG, "tec_sc_import_dev: null array");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n > s->cap) {
+        const int64_t cap = n + 1024;
+        TEC_CUDA(sc_grow(&s->cell, 0, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->umi, 0, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->left, 0, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->rite, 0, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->cs, 0, cap, ctx->stream));
+        s->cap = cap;
+    }
+    if (n > s->gidx_cap) {
+        TEC_CUDA(sc_grow(&s->gidx, 0, n + 1024, ctx->stream));
+        s->gidx_cap = n + 1024;
+    }
+    if (n) {
+        TEC_CUDA(cudaMemcpyAsync(s->cell, cell, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        TEC_CUDA(cudaMemcpyAsync(s->umi, umi, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        TEC_CUDA(cudaMemcpyAsync(s->left, left, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        TEC_CUDA(cudaMemcpyAsync(s->rite, rite, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        TEC_CUDA(cudaMemcpyAsync(s->cs, cs, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        TEC_CUDA(cudaMemcpyAsync(s->gidx, gidx, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->n = n;
+    s->has_gidx = true;
+    return TEC_OK;
+}
+
 static int ceil_log2_i64(int64_t x) { int b = 0; while ((int64_t(1) << b) < x) ++b; return b; }
 
 template <class K, class V>
@@ -762,7 +909,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         TEC_CUDA(cudaMemcpyAsync(d_ensg_of_slot, ctx->ensg_of_slot.data(), ctx->ensg_of_slot.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     u64* pairs_sorted = nullptr;
     u32 h_npairs = 0;
-    if (N > 0) {
+    if (N > 0 || s->world > 1) {          // with several ranks every rank walks the same sequence of collectives
         // ---- key groups: stable LSD sort of i by umi, then by cell
         u64* d_or = nullptr;
         TEC_CUDA(A.get(&d_or, 1));
@@ -808,7 +955,13 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         // ---- bundle boundaries (te_count.py:377): a bundle closes after the survivor that brings
         //      its number of distinct keys to bundle_keys
         std::vector<int64_t> bstart;
-        {
+        int64_t g_end = N;
+        const u64* gidx = s->has_gidx ? s->gidx : nullptr;
+        if (gidx) {
+            rc = sc_bundles_global(ctx, A, N, prev, bundle_keys, bstart, g_end);
+            if (rc) return rc;
+            if (g_end >= (int64_t)0xFFFFFFF0) TEC_FAIL(TEC_ERR_LIMIT, "single-cell path: more than 2^32 surviving records in the job");
+        } else {
             const int64_t WIN = std::max<int64_t>(int64_t(1) << 22, std::min<int64_t>(4 * bundle_keys, int64_t(1) << 28));
             u32 *f = nullptr, *found = nullptr;
             TEC_CUDA(A.get(&f, (size_t)std::min(WIN, N)));
@@ -843,7 +996,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
             A.release(f);
         }
         n_b = (int64_t)bstart.size();
-        bstart.push_back(N);
+        bstart.push_back(g_end);
         if (n_b * W > (int64_t(1) << 31)) TEC_FAIL(TEC_ERR_LIMIT, "single-cell path: bundles x whitelist exceeds 2^31 table entries");
         int64_t* d_bstart = nullptr;
         TEC_CUDA(A.get(&d_bstart, bstart.size()));
@@ -854,7 +1007,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         u64* minumi = nullptr;
         TEC_CUDA(A.get(&bundle, (size_t)N));
         TEC_CUDA(A.get(&shead, (size_t)N));
-        sc_seghead_kernel<<<SC_GRID(N)>>>(N, perm, khead, d_bstart, (int)n_b, bundle, shead);
+        sc_seghead_kernel<<<SC_GRID(N)>>>(N, perm, gidx, khead, d_bstart, (int)n_b, bundle, shead);
         rc = sc_incl_scan(ctx, shead, N, MaxU32());
         if (rc) return rc;
         TEC_CUDA(A.get(&raw, (size_t)W));
@@ -865,7 +1018,13 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         TEC_CUDA(cudaMemsetAsync(first_i, 0xFF, (size_t)W * 4, ctx->stream));
         TEC_CUDA(cudaMemsetAsync(present, 0, (size_t)(n_b * W + 1) * 4, ctx->stream));
         TEC_CUDA(cudaMemsetAsync(minumi, 0xFF, (size_t)(n_b * W) * 8, ctx->stream));
-        sc_segstat_kernel<<<SC_GRID(N)>>>(N, W, perm, scell, sumi, scs, shead, bundle, raw, first_i, minumi, present, s->d_stats);
+        sc_segstat_kernel<<<SC_GRID(N)>>>(N, W, perm, gidx, scell, sumi, scs, shead, bundle, raw, first_i, minumi, present, s->d_stats);
+        rc = sc_allreduce(ctx, raw, W, 0, 0);
+        if (rc) return rc;
+        rc = sc_allreduce(ctx, first_i, W, 0, 1);
+        if (rc) return rc;
+        rc = sc_allreduce(ctx, present, n_b * W + 1, 0, 2);
+        if (rc) return rc;
         ctx->launches += 2;
         // ---- Part 2: the maxcells + pad cells with the most raw reads, ties by first appearance
         u64 *ckey = nullptr, *ckey_s = nullptr;
@@ -966,8 +1125,10 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
             ctx->launches += 8;
         }
     }
-    // ---- hit cells, ascending id (self.barcodes after Part 3)
+    // ---- hit cells, ascending id (self.barcodes after Part 3); with several ranks every rank gets all of them
     {
+        int rc0 = sc_allreduce(ctx, hits, W, 0, 0);
+        if (rc0) return rc0;
         u32 *nz = nullptr;
         TEC_CUDA(A.get(&nz, (size_t)W + 1));
         TEC_CUDA(cudaMemsetAsync(nz, 0, (size_t)(W + 1) * 4, ctx->stream));
@@ -993,6 +1154,21 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
     s->stats[TEC_SS_UNITS] = s->units;
     s->stats[TEC_SS_BUNDLES] = n_b;
     s->stats[TEC_SS_SURVIVORS] = N;
+    if (s->world > 1 && s->coll) {
+        // job-wide statistics: sums over the ranks, except the two that are already global
+        u64 tmp[TEC_SC_NSTATS];
+        for (int i = 0; i < TEC_SC_NSTATS; ++i) tmp[i] = (u64)s->stats[i];
+        tmp[TEC_SS_RAW_BARCODES] = 0; tmp[TEC_SS_BUNDLES] = 0;
+        u64* d_tmp = nullptr;
+        TEC_CUDA(A.get(&d_tmp, TEC_SC_NSTATS));
+        TEC_CUDA(cudaMemcpyAsync(d_tmp, tmp, sizeof(tmp), cudaMemcpyHostToDevice, ctx->stream));
+        int rc1 = sc_allreduce(ctx, d_tmp, TEC_SC_NSTATS, 1, 0);
+        if (rc1) return rc1;
+        TEC_CUDA(cudaMemcpyAsync(tmp, d_tmp, sizeof(tmp), cudaMemcpyDeviceToHost, ctx->stream));
+        TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < TEC_SC_NSTATS; ++i)
+            if (i != TEC_SS_RAW_BARCODES && i != TEC_SS_BUNDLES) s->stats[i] = (int64_t)tmp[i];
+    }
     s->finalized = true;
     if (n_triples) *n_triples = s->n_triples;
     if (n_hit_cells) *n_hit_cells = s->n_hit;

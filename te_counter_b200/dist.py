@@ -49,3 +49,107 @@ def allreduce_counts_host(counts, stats, group=None):
     dist.all_reduce(t, group=group)
     out = t.numpy()
     return out[:len(counts)].copy(), out[len(counts):].copy()
+
+
+# ------------------------------------------------------------------------------------ single cell
+# One process per GPU.  Each rank pushes its slice of the (coordinate-sorted) file; the survivors of
+# Part 1's filter are then exchanged by cell id (all-to-all) with their position in the job-wide
+# survivor order, and tec_sc_finalize runs per rank, calling back into `allreduce` at the points
+# that are global (include/tecount.h).  Triples stay with the rank that owns the cell and are
+# concatenated at the end ("allgather-merge"): cells are disjoint, so no counts are added.
+_TORCH_DT = {0: ("<u4", "int32"), 1: ("<u8", "int64"), 2: ("<i8", "int64")}
+
+
+def _dev_tensor(ptr, n, typestr, device):
+    import torch
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype={"<i4": torch.int32, "<i8": torch.int64}[typestr], device=device)
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
+
+
+def make_allreduce(device, group=None):
+    """The callback for Engine.sc_set_collective.  NCCL: reduces the device buffer in place; any
+    other backend (gloo in the CPU-side tests): staged through host memory."""
+    import torch
+    import torch.distributed as dist
+    ops = {0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX}
+    on_gpu = dist.get_backend(group) == "nccl"
+
+    def allreduce(ptr, count, dtype, op):
+        if count == 0:
+            return
+        if dtype == 0:                                   # u32: widen (MIN / MAX must be unsigned)
+            t32 = _dev_tensor(ptr, count, "<i4", device)
+            t = t32.to(torch.int64) & 0xFFFFFFFF
+        else:                                            # u64 / i64 values stay below 2^63
+            t32 = None
+            t = _dev_tensor(ptr, count, "<i8", device)
+        if on_gpu:
+            dist.all_reduce(t, op=ops[op], group=group)
+            r = t
+        else:
+            h = t.cpu()
+            dist.all_reduce(h, op=ops[op], group=group)
+            r = h.to(device)
+        if t32 is not None:
+            t32.copy_((((r + 2 ** 31) % 2 ** 32) - 2 ** 31).to(torch.int32))       # back to the u32 bit pattern
+        elif r is not t:
+            t.copy_(r)
+        torch.cuda.synchronize(device)
+
+    return allreduce
+
+
+def sc_exchange_by_cell(engine, device, group=None):
+    """All-to-all of the survivors by owner rank (cell id % world) + job-wide positions; installs
+    the received records in the engine.  Returns the number of records this rank now owns."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    on_gpu = dist.get_backend(group) == "nccl"
+    n, p = engine.sc_export_dev()
+    cols = {"cell": _dev_tensor(p["cell"], n, "<i4", device), "umi": _dev_tensor(p["umi"], n, "<i8", device),
+            "left": _dev_tensor(p["left"], n, "<i4", device), "rite": _dev_tensor(p["rite"], n, "<i4", device),
+            "cs": _dev_tensor(p["cs"], n, "<i4", device)}
+    counts = [None] * world
+    dist.all_gather_object(counts, int(n), group=group)
+    base = sum(counts[:rank])
+    cols["gidx"] = base + torch.arange(n, dtype=torch.int64, device=device)
+    dest = (cols["cell"].to(torch.int64) & 0xFFFFFFFF) % world
+    order = torch.argsort(dest, stable=True)
+    send = torch.bincount(dest, minlength=world).tolist()
+    recv_all = [None] * world
+    dist.all_gather_object(recv_all, send, group=group)
+    recv = [recv_all[r][rank] for r in range(world)]
+    out = {}
+    for k, t in cols.items():
+        src = t[order].contiguous()
+        if on_gpu:
+            dst = torch.empty(sum(recv), dtype=t.dtype, device=device)
+            dist.all_to_all_single(dst, src, recv, send, group=group)
+        else:                                             # gloo has no all-to-all: gather everything, keep my part
+            parts = [None] * world
+            dist.all_gather_object(parts, [x.cpu() for x in torch.split(src, send)], group=group)
+            dst = torch.cat([parts[r][rank] for r in range(world)]).to(device)
+        out[k] = dst
+    o2 = torch.argsort(out["gidx"])
+    out = {k: v[o2].contiguous() for k, v in out.items()}
+    torch.cuda.synchronize(device)
+    n2 = int(out["gidx"].numel())
+    engine.sc_import_dev(n2, *[out[k].data_ptr() for k in ("cell", "umi", "left", "rite", "cs", "gidx")])
+    engine.sc_set_collective(make_allreduce(device, group), rank, world)
+    return n2
+
+
+def sc_gather_triples(ensg, cell, count, group=None):
+    """Concatenate the ranks' (ensg, cell, count) triples and sort by (ensg, cell): the job's
+    final_results.  Every rank gets the full list (numpy arrays)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    dist.all_gather_object(parts, (np.asarray(ensg), np.asarray(cell), np.asarray(count)), group=group)
+    e = np.concatenate([q[0] for q in parts])
+    c = np.concatenate([q[1] for q in parts])
+    v = np.concatenate([q[2] for q in parts])
+    o = np.lexsort((c, e))
+    return e[o], c[o], v[o]
