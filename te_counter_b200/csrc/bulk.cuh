@@ -187,12 +187,7 @@ struct StabView {
 };
 
 #define STAB_MAXD 4
-#define TEC_HOT_SLOTS 4096
-#define BULK_THREADS 512
-#ifndef BULK_MIN_CTAS
-#define BULK_MIN_CTAS 2
-#endif
-#define BULK_WARPS (BULK_THREADS / 32)
+#define TEC_HOT_SLOTS 4096        // shared-memory counters when not every ensg fits (and in the slow kernel)
 #define BULK_QCAP 64             // deferred-unit ring per warp (entries)
 #define R_NONE 0x7FFFu           // "no point in this sector": fails the e >= r test of every entry
 
@@ -319,28 +314,46 @@ struct QEnt {
     u32 pb;         // points in B
 };
 
+template <int WARPS>
 struct BulkShared {
-    u32 hot[TEC_HOT_SLOTS];
     u64 stats[TEC_BULK_NSTATS];
-    QEnt q[BULK_WARPS][BULK_QCAP];
-    u32 qu[BULK_WARPS][BULK_QCAP];       // unit index inside the launch (for the slow flag)
+    QEnt q[WARPS][BULK_QCAP];
+    u32 qu[WARPS][BULK_QCAP];            // unit index inside the launch (for the slow flag)
 };
 
-// +1 for entry I of the sector when its hit bit is set: predicated reductions, no branches
-template <int I>
-__device__ __forceinline__ void bump_entry(u32 hit, const Sector& s, u32 hot_addr, u64* __restrict__ counts, u32 one) {
+// +1 for entry I of the sector when its hit bit is set.  Counters of the first n_hot slots live in
+// shared memory; ALLHOT: every ensg does, so the global path disappears from the kernel.
+template <int I, bool ALLHOT>
+__device__ __forceinline__ void bump_entry(u32 hit, const Sector& s, u32 hot_addr, u32 n_hot, u64* __restrict__ counts, u32 one) {
     const u32 slot = sector_slot_c<I>(s);
-    asm volatile("{\n\t.reg .pred p, q, r;\n\t.reg .b32 t;\n\t"
-                 "and.b32 t, %0, %1;\n\t"
-                 "setp.ne.u32 p, t, 0;\n\t"
-                 "setp.lt.u32 q, %2, %3;\n\t"
-                 "and.pred r, p, q;\n\t"
-                 "@r red.shared.add.u32 [%4], %6;\n\t"
-                 "not.pred q, q;\n\t"
-                 "and.pred r, p, q;\n\t"
-                 "@r red.global.add.u64 [%5], %7;\n\t}"
-                 :: "r"(hit), "n"(I == 0 ? HB0 : I == 1 ? HB1 : I == 2 ? HB2 : I == 3 ? HB3 : HB4), "r"(slot), "n"(TEC_HOT_SLOTS), "r"(hot_addr + slot * 4u), "l"(counts + slot),
-                    "r"(one), "l"((u64)one) : "memory");
+    const u32 bit = I == 0 ? HB0 : I == 1 ? HB1 : I == 2 ? HB2 : I == 3 ? HB3 : HB4;
+    if (ALLHOT) {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                     "and.b32 t, %0, %1;\n\t"
+                     "setp.ne.u32 p, t, 0;\n\t"
+                     "@p red.shared.add.u32 [%2], %3;\n\t}"
+                     :: "r"(hit), "r"(bit), "r"(hot_addr + slot * 4u), "r"(one) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p, q, r;\n\t.reg .b32 t;\n\t"
+                     "and.b32 t, %0, %1;\n\t"
+                     "setp.ne.u32 p, t, 0;\n\t"
+                     "setp.lt.u32 q, %2, %3;\n\t"
+                     "and.pred r, p, q;\n\t"
+                     "@r red.shared.add.u32 [%4], %6;\n\t"
+                     "not.pred q, q;\n\t"
+                     "and.pred r, p, q;\n\t"
+                     "@r red.global.add.u64 [%5], %7;\n\t}"
+                     :: "r"(hit), "r"(bit), "r"(slot), "r"(n_hot), "r"(hot_addr + slot * 4u), "l"(counts + slot),
+                        "r"(one), "l"((u64)one) : "memory");
+    }
+}
+template <bool ALLHOT>
+__device__ __forceinline__ void bump_sector(u32 hit, const Sector& s, u32 hot_addr, u32 n_hot, u64* __restrict__ counts, u32 one) {
+    bump_entry<0, ALLHOT>(hit, s, hot_addr, n_hot, counts, one);
+    bump_entry<1, ALLHOT>(hit, s, hot_addr, n_hot, counts, one);
+    bump_entry<2, ALLHOT>(hit, s, hot_addr, n_hot, counts, one);
+    bump_entry<3, ALLHOT>(hit, s, hot_addr, n_hot, counts, one);
+    bump_entry<4, ALLHOT>(hit, s, hot_addr, n_hot, counts, one);
 }
 
 // slow list: word 0 = number of flagged units, then their indices (capacity = units of the launch).
@@ -391,8 +404,9 @@ __device__ __forceinline__ int points_rmax(u32 p) {
 // A unit that needs exactly two sectors: two cells (kind 1), or a cell and its first overflow sector
 // (kind 0).  Straight-line code for a full warp of such units; anything longer (a third sector, two
 // hit entries with the same ensg inside one sector) goes to the exact kernel.
+template <bool ALLHOT>
 __device__ __forceinline__ bool bulk_deferred(const StabView& sv, const QEnt e, bool live,
-                                              u32 hot_addr, u64* __restrict__ counts, u64* __restrict__ stats,
+                                              u32 hot_addr, u32 n_hot, u64* __restrict__ counts, u64* __restrict__ stats,
                                               u32& n_assigned, u32 one) {
     if (!live) return false;
     const u32 kind = e.secA >> 24, prim = e.secA & 0xFFFFFFu;
@@ -414,30 +428,26 @@ __device__ __forceinline__ bool bulk_deferred(const StabView& sv, const QEnt e, 
     hitB = drop_if_in_a<2>(hitA, hitB, A, B);
     hitB = drop_if_in_a<3>(hitA, hitB, A, B);
     hitB = drop_if_in_a<4>(hitA, hitB, A, B);
-    bump_entry<0>(hitA, A, hot_addr, counts, one);
-    bump_entry<1>(hitA, A, hot_addr, counts, one);
-    bump_entry<2>(hitA, A, hot_addr, counts, one);
-    bump_entry<3>(hitA, A, hot_addr, counts, one);
-    bump_entry<4>(hitA, A, hot_addr, counts, one);
-    bump_entry<0>(hitB, B, hot_addr, counts, one);
-    bump_entry<1>(hitB, B, hot_addr, counts, one);
-    bump_entry<2>(hitB, B, hot_addr, counts, one);
-    bump_entry<3>(hitB, B, hot_addr, counts, one);
-    bump_entry<4>(hitB, B, hot_addr, counts, one);
+    bump_sector<ALLHOT>(hitA, A, hot_addr, n_hot, counts, one);
+    bump_sector<ALLHOT>(hitB, B, hot_addr, n_hot, counts, one);
     return false;
 }
 
 // One warp per 32 consecutive units, grid-stride; the next warp-tile's records are requested before
 // the current one is looked up.
-template <bool PAIRED>
-__global__ void __launch_bounds__(BULK_THREADS, BULK_MIN_CTAS)
+// NT threads per CTA; the first n_hot ensg slots are counted in dynamic shared memory (ALLHOT: all of them,
+// one CTA of 1024 threads per SM; otherwise TEC_HOT_SLOTS of them, two CTAs of 512 threads per SM).
+template <bool PAIRED, int NT, bool ALLHOT>
+__global__ void __launch_bounds__(NT, 2048 / NT / 2)
 bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
                        const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                        const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ mapq,
                        const uint8_t* __restrict__ flag, u64* __restrict__ counts, u64* __restrict__ stats,
-                       u32* __restrict__ slow_list) {
-    __shared__ BulkShared sh;
-    for (int i = threadIdx.x; i < TEC_HOT_SLOTS; i += blockDim.x) sh.hot[i] = 0;
+                       u32* __restrict__ slow_list, u32 n_hot) {
+    constexpr int BULK_WARPS = NT / 32;
+    __shared__ BulkShared<BULK_WARPS> sh;
+    extern __shared__ __align__(16) u32 s_hot_dyn[];
+    for (u32 i = threadIdx.x; i < n_hot; i += blockDim.x) s_hot_dyn[i] = 0;
     if (threadIdx.x < TEC_BULK_NSTATS) sh.stats[threadIdx.x] = 0;
     __syncthreads();
     u32 n_assigned = 0, n_lowq = 0, n_badchrom = 0, n_qcfail = 0;
@@ -449,7 +459,7 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
     const u32 cmask = (1u << shift) - 1;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
-    const u32 hot_addr = (u32)__cvta_generic_to_shared(&sh.hot[0]);
+    const u32 hot_addr = (u32)__cvta_generic_to_shared(&s_hot_dyn[0]);
     // the increment as a run-time value: a literal 1 makes ptxas pick ATOMS.POPC.INC, which needs a
     // converged warp and therefore a branch around every reduction
     const u32 one = (u32)(n_units > 0);
@@ -520,11 +530,7 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
                 bool count_it = true;
                 if (!sv.all_counted) count_it = bulk_type_rule(sv, sector_typemask(sv, s, hit), stats);
                 if (count_it) {
-                    bump_entry<0>(hit, s, hot_addr, counts, one);
-                    bump_entry<1>(hit, s, hot_addr, counts, one);
-                    bump_entry<2>(hit, s, hot_addr, counts, one);
-                    bump_entry<3>(hit, s, hot_addr, counts, one);
-                    bump_entry<4>(hit, s, hot_addr, counts, one);
+                    bump_sector<ALLHOT>(hit, s, hot_addr, n_hot, counts, one);
                 }
             }
         }
@@ -541,7 +547,7 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
             __syncwarp();
             if (q_count >= 32) {
                 const u32 at = (q_head + lane) & (BULK_QCAP - 1);
-                const bool sl = bulk_deferred(sv, ring[at], true, hot_addr, counts, stats, n_assigned, one);
+                const bool sl = bulk_deferred<ALLHOT>(sv, ring[at], true, hot_addr, n_hot, counts, stats, n_assigned, one);
                 flag_slow_warp(slow_list, sl, ring_u[at], lt_mask);
                 q_head = (q_head + 32) & (BULK_QCAP - 1);
                 q_count -= 32;
@@ -552,7 +558,7 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
     }
     if (q_count) {
         const u32 at = (q_head + lane) & (BULK_QCAP - 1);
-        const bool sl = bulk_deferred(sv, ring[at], (u32)lane < q_count, hot_addr, counts, stats, n_assigned, one);
+        const bool sl = bulk_deferred<ALLHOT>(sv, ring[at], (u32)lane < q_count, hot_addr, n_hot, counts, stats, n_assigned, one);
         flag_slow_warp(slow_list, sl, ring_u[at], lt_mask);
     }
     u64 v[4] = {n_assigned, n_lowq, n_badchrom, n_qcfail};
@@ -565,8 +571,8 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
     if (threadIdx.x >= TEC_BS_ASSIGNED && threadIdx.x < TEC_BS_ASSIGNED + 4 && sh.stats[threadIdx.x])
         atomicAdd(stats + threadIdx.x, sh.stats[threadIdx.x]);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + TEC_BS_UNITS, (u64)n_units);
-    for (int i = threadIdx.x; i < TEC_HOT_SLOTS; i += blockDim.x) {
-        const u32 x = sh.hot[i];
+    for (u32 i = threadIdx.x; i < n_hot; i += blockDim.x) {
+        const u32 x = s_hot_dyn[i];
         if (x) atomicAdd(counts + i, (u64)x);
     }
 }

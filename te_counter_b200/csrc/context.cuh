@@ -111,6 +111,7 @@ struct DevCache {
 struct tec_ctx {
     int device = 0;
     int n_sm = 148;
+    int smem_optin = 227 * 1024;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -131,6 +132,7 @@ struct tec_ctx {
     // options (tec_set_option)
     int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 stab-table kernel
     int opt_stab_shift = 11;
+    int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
     int opt_sc_algo = -1;                 // -1 auto, 0 exact search only, 1 cell table
     int opt_ctas_per_sm = 2;              // resident CTAs per SM of the fast bulk kernel (512 threads each)
 

@@ -38,6 +38,7 @@ extern "C" int tec_create(int device, tec_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(TEC_ERR_CUDA);
     ctx->n_sm = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TEC_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TEC_ERR_CUDA);
     for (int i = 0; i < 2; ++i) {
@@ -301,11 +302,25 @@ static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, 
         }
         TEC_CUDA(cudaMemsetAsync(ctx->d_slow_list, 0, 4, ctx->stream));
         StabView sv = ctx->idx.stab_view();
-        const int blocks = (int)std::min<int64_t>((n_tiles + BULK_WARPS - 1) / BULK_WARPS, (int64_t)ctx->n_sm * ctx->opt_ctas_per_sm);
-        if (ctx->paired)
-            bulk_count_cell_kernel<true><<<blocks, BULK_THREADS, 0, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, ctx->d_slow_list);
-        else
-            bulk_count_cell_kernel<false><<<blocks, BULK_THREADS, 0, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, ctx->d_slow_list);
+        // every ensg counter in shared memory when they fit beside the rings (one 1024-thread CTA per SM);
+        // otherwise the TEC_HOT_SLOTS hottest ones (two 512-thread CTAs per SM)
+        const size_t all_bytes = (size_t)ctx->idx.n_ensg * 4;
+        const bool allhot = ctx->opt_all_hot != 0 && all_bytes + 44 * 1024 <= (size_t)ctx->smem_optin;
+        const int nt = allhot ? 1024 : 512;
+        const u32 n_hot = allhot ? (u32)ctx->idx.n_ensg : (u32)std::min<int64_t>(TEC_HOT_SLOTS, ctx->idx.n_ensg);
+        const size_t dyn = std::max<size_t>((size_t)n_hot * 4, 16);
+        const int per_sm = allhot ? 1 : ctx->opt_ctas_per_sm;
+        const int blocks = (int)std::min<int64_t>((n_tiles + nt / 32 - 1) / (nt / 32), (int64_t)ctx->n_sm * per_sm);
+#define TEC_LAUNCH_CELL(P, NT, AH)                                                                                         \
+        do {                                                                                                               \
+            auto kfn = bulk_count_cell_kernel<P, NT, AH>;                                                                  \
+            TEC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                    \
+            kfn<<<blocks, NT, dyn, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, \
+                                                  ctx->d_slow_list, n_hot);                                               \
+        } while (0)
+        if (ctx->paired) { if (allhot) TEC_LAUNCH_CELL(true, 1024, true); else TEC_LAUNCH_CELL(true, 512, false); }
+        else { if (allhot) TEC_LAUNCH_CELL(false, 1024, true); else TEC_LAUNCH_CELL(false, 512, false); }
+#undef TEC_LAUNCH_CELL
         ctx->launches++;
         TEC_CUDA(cudaGetLastError());
         const int sblocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)ctx->n_sm * 4);
@@ -421,6 +436,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     if (k == "bulk_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "bulk_algo: -1, 0 or 1"); ctx->opt_bulk_algo = (int)value; }
     else if (k == "stab_shift") { if (value < 8 || value > STAB_MAX_SHIFT) TEC_FAIL(TEC_ERR_ARG, "stab_shift: 8..11"); ctx->opt_stab_shift = (int)value; }
     else if (k == "sc_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "sc_algo: -1, 0 or 1"); ctx->opt_sc_algo = (int)value; }
+    else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else TEC_FAIL(TEC_ERR_ARG, "tec_set_option: unknown key " + k);
     return TEC_OK;

@@ -66,6 +66,25 @@ def test_bulk_dense_overlaps_and_gapped_reads(engine, algo):
     engine.set_option("bulk_algo", -1)
 
 
+@pytest.mark.parametrize("all_hot", [0, 1])
+@pytest.mark.parametrize("paired", [False, True])
+def test_bulk_counter_placement(engine, paired, all_hot):
+    """all_hot 1: every ensg counter in shared memory (1024-thread CTAs); 0: the 4096 hottest only."""
+    idx = synth.synth_index(9, n_te=40000, n_exon=30000, n_gene=6000, n_te_names=900, chrom_len=4_000_000, n_chrom=3)
+    r = synth.synth_bulk_reads(19, idx, 80000, paired=paired, edge_frac=0.02)
+    engine.set_option("all_hot", all_hot)
+    engine.upload_index(idx)
+    engine.bulk_begin(paired, 20)
+    engine.bulk_push(len(r["start"]), r["start"], r["end"], r["chrom"], r["mapq"], r["flag"])
+    counts, st = engine.bulk_finish()
+    engine.set_option("all_hot", 1)
+    oc, os_ = te_oracle.bulk_count(H.oracle_index(idx), paired, 20, r["start"].tolist(), r["end"].tolist(),
+                                   r["chrom"].tolist(), r["mapq"].tolist(), r["flag"].tolist())
+    assert counts.tolist() == oc
+    assert (st[_lib.BS_ASSIGNED], st[_lib.BS_LOWQ], st[_lib.BS_BADCHROM], st[_lib.BS_QCFAIL]) == \
+        (os_["assigned"], os_["lowq"], os_["badchrom"], os_["qcfail"])
+
+
 def test_bulk_deep_pileup_overflow_path(engine):
     """> BULK_MAX_DISTINCT distinct ensg under one read: the O(h^2) re-walk path."""
     n = 40
