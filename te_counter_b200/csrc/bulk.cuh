@@ -480,14 +480,17 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
         if (un < n_u) nxt = bulk_load<PAIRED>(un, start, end, chrom, mapq, flag, pol);
         // ---- filter (te_count.py:78-102 / :203-218)
         const int c = cur.c, loc1 = cur.loc1, loc2 = cur.loc2;
-        bool look = false;
-        if (u < n_u) {
-            if (cur.fl & reject2) n_qcfail++;                                              // :81-86 / :204
-            else if ((int)cur.q < qual) n_lowq++;                                          // :88 / :208
-            else if (PAIRED && (cur.fl & TEC_F_NAME_MISMATCH)) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);   // :92-94
-            else if (c >= iv.n_chrom) n_badchrom++;                                        // :100 / :216
-            else look = true;
-        }
+        // first failing test wins, as in the reference's if / continue chain; branch-free counters
+        const bool live = u < n_u;
+        const bool f_qc = (cur.fl & reject2) != 0;                                         // :81-86 / :204
+        const bool f_lq = (int)cur.q < qual;                                               // :88 / :208
+        const bool f_nm = PAIRED && (cur.fl & TEC_F_NAME_MISMATCH);                        // :92-94
+        const bool f_bc = c >= iv.n_chrom;                                                 // :100 / :216
+        n_qcfail += live & f_qc;
+        n_lowq += live & !f_qc & f_lq;
+        n_badchrom += live & !(f_qc | f_lq | f_nm) & f_bc;
+        if (PAIRED && live && !(f_qc | f_lq) && f_nm) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);
+        const bool look = live & !(f_qc | f_lq | f_nm | f_bc);
         // ---- which sector(s)
         QEnt qe;
         qe.secA = qe.secB = 0; qe.pa = qe.pb = R_NONE | (R_NONE << 16);
@@ -580,7 +583,7 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
 // Units flagged by the fast kernel: bucket-edge candidates take the exact search (counters in slot
 // space); units with more than STAB_MAXD distinct ensg walk the cell table again with a larger set.
 // One thread per flagged unit.
-#define SLOW_MAXD 32
+#define SLOW_MAXD 8
 #define SLOW_MAXD_EXACT 96
 template <bool PAIRED>
 __global__ void __launch_bounds__(256)
@@ -605,9 +608,11 @@ bulk_slow_kernel(IndexView iv, StabView sv, int has_stab, const int32_t* __restr
         else { c = chrom[u]; loc1 = start[u]; loc2 = end[u]; }
         const bool edge = loc1 < 0 || loc2 + 1 < 0 || (loc1 % iv.bs == 0) || ((loc2 + 1) % iv.bs == 0);
         if (has_stab && !edge) {
-            // same lookup as the fast kernel, distinct slots in a local list
-            u32 nd = 0, dist[SLOW_MAXD];
-            bool overflow = false;
+            // same lookup as the fast kernel, distinct slots in a register set of SLOW_MAXD
+            u32 dist[SLOW_MAXD];
+#pragma unroll
+            for (int i = 0; i < SLOW_MAXD; ++i) dist[i] = 0xFFFFFFFFu;
+            u32 nd = 0;
             const uint2 cell = __ldg(sv.cells + c);
             const int x[2] = {loc1, loc2 - 1};
             for (int p = 0; p < 2; ++p) {
@@ -626,26 +631,32 @@ bulk_slow_kernel(IndexView iv, StabView sv, int has_stab, const int32_t* __restr
                         const u32 e = (low == HB0) ? sector_slot_c<0>(s) : (low == HB1) ? sector_slot_c<1>(s) : (low == HB2) ? sector_slot_c<2>(s)
                                       : (low == HB3) ? sector_slot_c<3>(s) : sector_slot_c<4>(s);
                         bool found = false;
-                        for (u32 j = 0; j < nd; ++j) found |= (dist[j] == e);
+#pragma unroll
+                        for (int j = 0; j < SLOW_MAXD; ++j) found |= (dist[j] == e);
                         if (!found) {
-                            if (nd < SLOW_MAXD) dist[nd++] = e; else overflow = true;
+#pragma unroll
+                            for (int j = 0; j < SLOW_MAXD; ++j) if ((u32)j == nd) dist[j] = e;
+                            ++nd;                                                      // nd > SLOW_MAXD: overflow
                         }
                     }
                     if (!sector_more(s) || r < sector_last_s(s)) break;
                     sec = (sec == prim) ? __ldg(sv.ovf_base + (prim >> 7)) + sector_link(s) : sec + 1;
                 }
             }
-            if (!overflow) {
+            if (nd <= SLOW_MAXD) {
                 if (!nd) continue;                                                     // :128 no result
                 n_assigned++;                                                          // :149
                 u32 typemask = sv.all_counted ? counted : 0u;
-                if (!sv.all_counted)
-                    for (u32 j = 0; j < nd; ++j) typemask |= 1u << __ldg(sv.slot_type + dist[j]);
+                if (!sv.all_counted) {
+#pragma unroll
+                    for (int j = 0; j < SLOW_MAXD; ++j) if ((u32)j < nd) typemask |= 1u << __ldg(sv.slot_type + dist[j]);
+                }
                 if (!(typemask & counted)) {
                     if (typemask & (1u << TEC_T_ENHANCER)) atomicAdd(stats + TEC_BS_CRASH_ENHANCER, 1ULL);
                     continue;
                 }
-                for (u32 j = 0; j < nd; ++j) bump(dist[j]);
+#pragma unroll
+                for (int j = 0; j < SLOW_MAXD; ++j) if ((u32)j < nd) bump(dist[j]);
                 continue;
             }
         }

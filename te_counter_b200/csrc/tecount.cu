@@ -323,7 +323,7 @@ static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, 
 #undef TEC_LAUNCH_CELL
         ctx->launches++;
         TEC_CUDA(cudaGetLastError());
-        const int sblocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)ctx->n_sm * 4);
+        const int sblocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)ctx->n_sm * 8);
         if (ctx->paired)
             bulk_slow_kernel<true><<<sblocks, 256, 0, ctx->stream>>>(iv, sv, 1, start, end, chrom, counts, stats, ctx->d_slow_list);
         else
