@@ -315,7 +315,7 @@ def run_ours(args):
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": n_rec * world / dt, "unit": "records/s", "h2d_bytes_per_step": int(n_rec) * 12,
+        e2e = {"value": n_rec * world / dt, "unit": "records/s", "h2d_bytes_per_step": int(n_rec) * (8 if paired else 12),
                "d2h_bytes_per_step": (idx.n_ensg + _lib.BULK_NSTATS) * 8, "ms_per_step": dt * 1e3,
                "api": "tec_bulk_begin + tec_bulk_push(host SoA, pinned) + tec_bulk_finish"}
         if world == 1:

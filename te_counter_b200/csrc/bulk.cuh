@@ -404,11 +404,12 @@ __device__ __forceinline__ int points_rmax(u32 p) {
 // A unit that needs exactly two sectors: two cells (kind 1), or a cell and its first overflow sector
 // (kind 0).  Straight-line code for a full warp of such units; anything longer (a third sector, two
 // hit entries with the same ensg inside one sector) goes to the exact kernel.
+// returns 0 done, 1 exact kernel (possible double hit of one ensg), 2 needs a third sector (bulk_general)
 template <bool ALLHOT>
-__device__ __forceinline__ bool bulk_deferred(const StabView& sv, const QEnt e, bool live,
-                                              u32 hot_addr, u32 n_hot, u64* __restrict__ counts, u64* __restrict__ stats,
-                                              u32& n_assigned, u32 one) {
-    if (!live) return false;
+__device__ __forceinline__ int bulk_deferred(const StabView& sv, const QEnt e, bool live,
+                                             u32 hot_addr, u32 n_hot, u64* __restrict__ counts, u64* __restrict__ stats,
+                                             u32& n_assigned, u32 one) {
+    if (!live) return 0;
     const u32 kind = e.secA >> 24, prim = e.secA & 0xFFFFFFu;
     const Sector A = ld_sector(sv.sectors, prim);
     const u32 hitA = sector_hits(A, make_point(e.pa & 0xFFFFu), make_point(e.pa >> 16));
@@ -417,12 +418,11 @@ __device__ __forceinline__ bool bulk_deferred(const StabView& sv, const QEnt e, 
     const u32 pB = kind ? e.pb : e.pa;
     const Sector B = ld_sector(sv.sectors, (kind || a_over) ? secB : prim);
     u32 hitB = (kind || a_over) ? sector_hits(B, make_point(pB & 0xFFFFu), make_point(pB >> 16)) : 0u;
-    bool slow = (kind && a_over) || ((kind || a_over) && sector_more(B) && points_rmax(pB) >= (int)sector_last_s(B));
-    slow |= sector_twin_hit(A, hitA) || sector_twin_hit(B, hitB);
-    if (slow) return true;
-    if (!(hitA | hitB)) return false;                                                  // :128 no result
+    if ((kind && a_over) || ((kind || a_over) && sector_more(B) && points_rmax(pB) >= (int)sector_last_s(B))) return 2;
+    if (sector_twin_hit(A, hitA) || sector_twin_hit(B, hitB)) return 1;
+    if (!(hitA | hitB)) return 0;                                                      // :128 no result
     n_assigned++;                                                                      // :149
-    if (!sv.all_counted && !bulk_type_rule(sv, sector_typemask(sv, A, hitA) | sector_typemask(sv, B, hitB), stats)) return false;
+    if (!sv.all_counted && !bulk_type_rule(sv, sector_typemask(sv, A, hitA) | sector_typemask(sv, B, hitB), stats)) return 0;
     hitB = drop_if_in_a<0>(hitA, hitB, A, B);
     hitB = drop_if_in_a<1>(hitA, hitB, A, B);
     hitB = drop_if_in_a<2>(hitA, hitB, A, B);
@@ -430,6 +430,66 @@ __device__ __forceinline__ bool bulk_deferred(const StabView& sv, const QEnt e, 
     hitB = drop_if_in_a<4>(hitA, hitB, A, B);
     bump_sector<ALLHOT>(hitA, A, hot_addr, n_hot, counts, one);
     bump_sector<ALLHOT>(hitB, B, hot_addr, n_hot, counts, one);
+    return 0;
+}
+
+// The general case, a warp of units at a time: walk the sector chains of one or two cells and keep
+// the distinct ensg in a register set.  Returns true when the set overflows (exact kernel).
+#define GEN_MAXD 8
+template <bool ALLHOT>
+__device__ __forceinline__ bool bulk_general(const StabView& sv, const QEnt e, bool live,
+                                             u32 hot_addr, u32 n_hot, u64* __restrict__ counts, u64* __restrict__ stats,
+                                             u32& n_assigned, u32 one) {
+    if (!live) return false;
+    u32 dist[GEN_MAXD];
+#pragma unroll
+    for (int i = 0; i < GEN_MAXD; ++i) dist[i] = 0xFFFFFFFFu;
+    u32 nd = 0;
+    const int n_cell = (e.secA >> 24) ? 2 : 1;
+    for (int ci = 0; ci < n_cell; ++ci) {
+        const u32 prim = ci ? e.secB : (e.secA & 0xFFFFFFu);
+        const u32 pp = ci ? e.pb : e.pa;
+        const PointK pa = make_point(pp & 0xFFFFu), pb = make_point(pp >> 16);
+        const int rmax = points_rmax(pp);
+        u32 sec = prim;
+        for (;;) {
+            const Sector s = ld_sector(sv.sectors, sec);
+            u32 hit = sector_hits(s, pa, pb);
+            while (hit) {
+                const u32 low = hit & (0u - hit);
+                hit ^= low;
+                const u32 w = (low == HB0) ? sector_slot_c<0>(s) : (low == HB1) ? sector_slot_c<1>(s) : (low == HB2) ? sector_slot_c<2>(s)
+                              : (low == HB3) ? sector_slot_c<3>(s) : sector_slot_c<4>(s);
+                bool found = false;
+#pragma unroll
+                for (int j = 0; j < GEN_MAXD; ++j) found |= (dist[j] == w);
+                if (!found) {
+#pragma unroll
+                    for (int j = 0; j < GEN_MAXD; ++j) if ((u32)j == nd) dist[j] = w;
+                    ++nd;
+                }
+            }
+            if (!sector_more(s) || rmax < (int)sector_last_s(s)) break;
+            sec = (sec == prim) ? __ldg(sv.ovf_base + (prim >> 7)) + sector_link(s) : sec + 1;
+        }
+    }
+    if (nd > GEN_MAXD) return true;
+    if (!nd) return false;                                                             // :128 no result
+    n_assigned++;                                                                      // :149
+    if (!sv.all_counted) {
+        u32 typemask = 0;
+#pragma unroll
+        for (int j = 0; j < GEN_MAXD; ++j) if ((u32)j < nd) typemask |= 1u << __ldg(sv.slot_type + dist[j]);
+        if (!bulk_type_rule(sv, typemask, stats)) return false;
+    }
+#pragma unroll
+    for (int j = 0; j < GEN_MAXD; ++j) {
+        if ((u32)j < nd) {
+            const u32 slot = dist[j];
+            if (ALLHOT || slot < n_hot) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hot_addr + slot * 4u), "r"(one) : "memory");
+            else atomicAdd(counts + slot, 1ULL);
+        }
+    }
     return false;
 }
 
@@ -443,7 +503,7 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
                        const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                        const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ mapq,
                        const uint8_t* __restrict__ flag, u64* __restrict__ counts, u64* __restrict__ stats,
-                       u32* __restrict__ slow_list, u32 n_hot) {
+                       u32* __restrict__ slow_list, u32 n_hot, QEnt* __restrict__ g_ring, u32* __restrict__ g_ring_u) {
     constexpr int BULK_WARPS = NT / 32;
     __shared__ BulkShared<BULK_WARPS> sh;
     extern __shared__ __align__(16) u32 s_hot_dyn[];
@@ -466,6 +526,33 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
     QEnt* const ring = sh.q[wib];
     u32* const ring_u = sh.qu[wib];
     u32 q_head = 0, q_count = 0;                     // warp-uniform
+    // second ring (global memory, rarely used): units that need a third sector
+    QEnt* const ring2 = g_ring + (size_t)(blockIdx.x * BULK_WARPS + wib) * BULK_QCAP;
+    u32* const ring2_u = g_ring_u + (size_t)(blockIdx.x * BULK_WARPS + wib) * BULK_QCAP;
+    u32 q2_head = 0, q2_count = 0;
+    // a batch of ring 1: two-sector code; what it cannot finish goes to the slow list or to ring 2
+    auto run_ring1 = [&](bool all) {
+        const u32 at = (q_head + lane) & (BULK_QCAP - 1);
+        const QEnt e = ring[at];
+        const u32 eu = ring_u[at];
+        const int code = bulk_deferred<ALLHOT>(sv, e, all || (u32)lane < q_count, hot_addr, n_hot, counts, stats, n_assigned, one);
+        flag_slow_warp(slow_list, code == 1, eu, lt_mask);
+        const u32 gm = __ballot_sync(0xFFFFFFFFu, code == 2);
+        if (gm) {
+            if (code == 2) {
+                const u32 at2 = (q2_head + q2_count + __popc(gm & lt_mask)) & (BULK_QCAP - 1);
+                ring2[at2] = e;
+                ring2_u[at2] = eu;
+            }
+            q2_count += __popc(gm);
+            __syncwarp();
+        }
+    };
+    auto run_ring2 = [&](bool all) {
+        const u32 at = (q2_head + lane) & (BULK_QCAP - 1);
+        const bool sl = bulk_general<ALLHOT>(sv, ring2[at], all || (u32)lane < q2_count, hot_addr, n_hot, counts, stats, n_assigned, one);
+        flag_slow_warp(slow_list, sl, ring2_u[at], lt_mask);
+    };
     const u32 n_u = (u32)n_units;                     // a launch holds < 2^28 units (TEC_LAUNCH_UNITS)
     const u32 n_tiles = (n_u + 31) >> 5;
     const u32 tile_stride = gridDim.x * BULK_WARPS;
@@ -549,20 +636,27 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
             q_count += __popc(dm);
             __syncwarp();
             if (q_count >= 32) {
-                const u32 at = (q_head + lane) & (BULK_QCAP - 1);
-                const bool sl = bulk_deferred<ALLHOT>(sv, ring[at], true, hot_addr, n_hot, counts, stats, n_assigned, one);
-                flag_slow_warp(slow_list, sl, ring_u[at], lt_mask);
+                run_ring1(true);
                 q_head = (q_head + 32) & (BULK_QCAP - 1);
                 q_count -= 32;
                 __syncwarp();
+                if (q2_count >= 32) {
+                    run_ring2(true);
+                    q2_head = (q2_head + 32) & (BULK_QCAP - 1);
+                    q2_count -= 32;
+                    __syncwarp();
+                }
             }
         }
         cur = nxt;
     }
-    if (q_count) {
-        const u32 at = (q_head + lane) & (BULK_QCAP - 1);
-        const bool sl = bulk_deferred<ALLHOT>(sv, ring[at], (u32)lane < q_count, hot_addr, n_hot, counts, stats, n_assigned, one);
-        flag_slow_warp(slow_list, sl, ring_u[at], lt_mask);
+    if (q_count) run_ring1(false);
+    while (q2_count) {                                // at most two rounds: fewer than 64 entries
+        run_ring2(false);
+        const u32 done = min(q2_count, 32u);
+        q2_head = (q2_head + done) & (BULK_QCAP - 1);
+        q2_count -= done;
+        __syncwarp();
     }
     u64 v[4] = {n_assigned, n_lowq, n_badchrom, n_qcfail};
 #pragma unroll

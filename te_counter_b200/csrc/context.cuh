@@ -128,6 +128,9 @@ struct tec_ctx {
     u64* d_counts = nullptr;              // n_ensg counters (slot order) + TEC_BULK_NSTATS statistics
     u32* d_slow_list = nullptr;           // [0] = count, then unit indices flagged for bulk_slow_kernel
     int64_t slow_cap = 0;                 // words
+    void* d_ring = nullptr;               // per-warp second deferral ring of the fast bulk kernel (QEnt)
+    u32* d_ring_u = nullptr;
+    int64_t ring_cap = 0;                 // entries
     std::vector<int32_t> ensg_of_slot;    // slot = rank of an ensg by number of feature rows
     // options (tec_set_option)
     int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 stab-table kernel
@@ -171,6 +174,8 @@ inline void tec_ctx::free_index() {
     d_counts = nullptr;
     cudaFree(d_slow_list);
     d_slow_list = nullptr;
+    cudaFree(d_ring); cudaFree(d_ring_u);
+    d_ring = nullptr; d_ring_u = nullptr; ring_cap = 0;
     slow_cap = 0;
     has_index = false;
     bulk_active = false;

@@ -311,12 +311,21 @@ static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, 
         const size_t dyn = std::max<size_t>((size_t)n_hot * 4, 16);
         const int per_sm = allhot ? 1 : ctx->opt_ctas_per_sm;
         const int blocks = (int)std::min<int64_t>((n_tiles + nt / 32 - 1) / (nt / 32), (int64_t)ctx->n_sm * per_sm);
+        const int64_t ring_entries = (int64_t)blocks * (nt / 32) * BULK_QCAP;
+        if (ring_entries > ctx->ring_cap) {
+            TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_ring); cudaFree(ctx->d_ring_u);
+            ctx->d_ring = nullptr; ctx->d_ring_u = nullptr; ctx->ring_cap = 0;
+            TEC_CUDA(cudaMalloc(&ctx->d_ring, (size_t)ring_entries * sizeof(QEnt)));
+            TEC_CUDA(cudaMalloc(&ctx->d_ring_u, (size_t)ring_entries * 4));
+            ctx->ring_cap = ring_entries;
+        }
 #define TEC_LAUNCH_CELL(P, NT, AH)                                                                                         \
         do {                                                                                                               \
             auto kfn = bulk_count_cell_kernel<P, NT, AH>;                                                                  \
             TEC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                    \
             kfn<<<blocks, NT, dyn, ctx->stream>>>(iv, sv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats, \
-                                                  ctx->d_slow_list, n_hot);                                               \
+                                                  ctx->d_slow_list, n_hot, (QEnt*)ctx->d_ring, ctx->d_ring_u);            \
         } while (0)
         if (ctx->paired) { if (allhot) TEC_LAUNCH_CELL(true, 1024, true); else TEC_LAUNCH_CELL(true, 512, false); }
         else { if (allhot) TEC_LAUNCH_CELL(false, 1024, true); else TEC_LAUNCH_CELL(false, 512, false); }
@@ -397,7 +406,9 @@ extern "C" int tec_bulk_push(tec_ctx* ctx, int64_t n_rec, const int32_t* start, 
         StageSlot& sl = ctx->stage[s];
         TEC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[s], 0));
         TEC_CUDA(cudaMemcpyAsync(sl.start, start + off, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-        TEC_CUDA(cudaMemcpyAsync(sl.end, end + off, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        // the paired-end rules never look at reference_end (te_count.py:97-98 take both mates' starts)
+        if (!ctx->paired)
+            TEC_CUDA(cudaMemcpyAsync(sl.end, end + off, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
         TEC_CUDA(cudaMemcpyAsync(sl.chrom, chrom + off, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->copy_stream));
         TEC_CUDA(cudaMemcpyAsync(sl.mapq, mapq + off, (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
         TEC_CUDA(cudaMemcpyAsync(sl.flag, flag + off, (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
