@@ -499,19 +499,32 @@ __device__ void sc_count_fragment(const IndexView& iv, const ScTableView& tv, in
     });
 }
 
+// winners compacted into a dense list, so that every lane of sc_part3_kernel has a fragment to count
+__global__ void sc_winflag_kernel(int64_t n, const u32* __restrict__ shead_pos, const u32* __restrict__ khead_pos,
+                                  const u32* __restrict__ winner_at, u32* __restrict__ f) {
+    SC_LOOP(j, n) f[j] = (shead_pos[j] == (u32)j && winner_at[khead_pos[j]] == (u32)j) ? 1u : 0u;
+}
+__global__ void sc_winlist_kernel(int64_t n, const u32* __restrict__ excl, const u32* __restrict__ total, u32* __restrict__ wlist) {
+    SC_LOOP(j, n) {
+        const u32 p = excl[j], nx = (j + 1 < n) ? excl[j + 1] : *total;
+        if (nx != p) wlist[p] = (u32)j;
+    }
+}
+
 // one thread per winning segment; all columns are in sorted (cell, umi, i) order.  The increments of
 // a warp's fragments are appended with one atomic per warp.
-__global__ void sc_part3_kernel(int64_t n, IndexView iv, ScTableView tv, int strand_mode, const u32* __restrict__ ensg_of_slot,
-                                const u32* __restrict__ scell, const u32* __restrict__ shead_pos, const u32* __restrict__ khead_pos,
-                                const u32* __restrict__ winner_at, const u32* __restrict__ cs, const int32_t* __restrict__ left,
+__global__ void sc_part3_kernel(int64_t n, int64_t n_win, const u32* __restrict__ wlist, IndexView iv, ScTableView tv, int strand_mode,
+                                const u32* __restrict__ ensg_of_slot, const u32* __restrict__ scell, const u32* __restrict__ shead_pos,
+                                const u32* __restrict__ cs, const int32_t* __restrict__ left,
                                 const int32_t* __restrict__ rite, ScOut o) {
     const int lane = threadIdx.x & 31;
     u32 n_assigned = 0, n_crash = 0;
-    const int64_t n_round = ((n + 31) / 32) * 32;                // whole warps stay in the loop together
-    SC_LOOP(j, n_round) {
+    const int64_t n_round = ((n_win + 31) / 32) * 32;            // whole warps stay in the loop together
+    SC_LOOP(w, n_round) {
         FragOut fo;
         fo.n = 0;
-        const bool win = j < n && shead_pos[j] == (u32)j && winner_at[khead_pos[j]] == (u32)j;
+        const bool win = w < n_win;
+        const int64_t j = win ? (int64_t)wlist[w] : 0;
         u32 cell = 0;
         if (win) {
             cell = scell[j];
@@ -1062,6 +1075,22 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         u32 *d_np = nullptr, *d_over = nullptr;
         TEC_CUDA(A.get(&d_np, 1));
         TEC_CUDA(A.get(&d_over, 1));
+        // dense list of the winning lines
+        u32 *wflag = nullptr, *wlist = nullptr, *d_nwin = nullptr;
+        TEC_CUDA(A.get(&wflag, (size_t)N + 1));
+        TEC_CUDA(A.get(&d_nwin, 1));
+        sc_winflag_kernel<<<SC_GRID(N)>>>(N, shead, khead, winner_at, wflag);
+        TEC_CUDA(cudaMemsetAsync(wflag + N, 0, 4, ctx->stream));
+        rc = sc_excl_sum(ctx, wflag, wflag, N + 1);
+        if (rc) return rc;
+        u32 h_nwin = 0;
+        TEC_CUDA(cudaMemcpyAsync(&h_nwin, wflag + N, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        TEC_CUDA(cudaMemcpyAsync(d_nwin, wflag + N, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+        TEC_CUDA(A.get(&wlist, (size_t)h_nwin));
+        sc_winlist_kernel<<<SC_GRID(N)>>>(N, wflag, d_nwin, wlist);
+        ctx->launches += 2;
+        A.release(winner_at);
         u64 h_stats_before[TEC_SC_NSTATS];
         TEC_CUDA(cudaMemcpyAsync(h_stats_before, s->d_stats, sizeof(h_stats_before), cudaMemcpyDeviceToHost, ctx->stream));
         TEC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1079,8 +1108,8 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
             tv.sv = ctx->idx.sc_stab_view();
             tv.pair_key = ctx->idx.sc_pair_key; tv.pair_type = ctx->idx.sc_pair_type;
             tv.present = (ctx->idx.has_sc_stab && ctx->opt_sc_algo != 0) ? 1 : 0;
-            sc_part3_kernel<<<SC_GRID(N)>>>(N, ctx->idx.view(), tv, s->strand, d_ensg_of_slot, scell, shead, khead, winner_at,
-                                            scs, sleft, srite, o);
+            sc_part3_kernel<<<SC_GRID(h_nwin)>>>(N, (int64_t)h_nwin, wlist, ctx->idx.view(), tv, s->strand, d_ensg_of_slot, scell, shead,
+                                                 scs, sleft, srite, o);
             ctx->launches++;
             u32 h_over = 0;
             TEC_CUDA(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1092,7 +1121,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
             cap_pairs = std::min<int64_t>(std::max<int64_t>((int64_t)h_npairs + 1024, cap_pairs * 2), (int64_t)0xFFFFFFF0);
         }
         // release what Part 3 no longer needs before sorting the pair list
-        A.release(winner_at); A.release(minumi); A.release(present); A.release(bundle); A.release(shead); A.release(khead);
+        A.release(wflag); A.release(wlist); A.release(minumi); A.release(present); A.release(bundle); A.release(shead); A.release(khead);
         A.release(sumi); A.release(scell); A.release(perm); A.release(scs); A.release(sleft); A.release(srite);
         // ---- triples: sort (ensg, cell) keys, run-length encode
         if (h_npairs) {
