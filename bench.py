@@ -408,13 +408,22 @@ def run_ours_sc(args, rank, world, local, dev):
     ext = torch.cuda.ExternalStream(eng.stream, device=dev)
     strand = True
 
+    phase = {}
+
     def step():
+        ta = time.perf_counter()
         eng.sc_begin(20, strand, n_wl)
         eng.sc_push_dev(n_rec, *ptrs)
+        if os.environ.get("TEC_DIST_TIMING"):
+            eng.sync()
+        tb = time.perf_counter()
         if world > 1:
             tdist.sc_exchange_by_cell(eng, dev)             # all-to-all by cell over NCCL
+        tc = time.perf_counter()
         nt, nh = eng.sc_finalize(bundle_keys, maxcells, pad)
         sel = eng.sc_select(maxcells, nh)
+        td = time.perf_counter()
+        phase.update(push=tb - ta, exchange=tc - tb, finalize=td - tc)
         return nt, nh, sel
 
     for _ in range(max(3, args.warmup)):
@@ -534,6 +543,9 @@ def run_ours_sc(args, rank, world, local, dev):
                       "segments": int(st[_lib.SS_SEGMENTS]), "bundles": int(st[_lib.SS_BUNDLES]),
                       "valid": int(st[_lib.SS_VALID]), "assigned": int(st[_lib.SS_ASSIGNED]),
                       "triples": int(nt), "hit_cells": int(nh), "selected": int(len(sel))}}
+    if os.environ.get("TEC_DIST_TIMING"):
+        line["phase_s_last_step"] = phase
+        line["exchange_s_total"] = dict(tdist.TIMING)
     if rank == 0:
         print(json.dumps(line))
     eng.close()

@@ -100,11 +100,25 @@ def make_allreduce(device, group=None):
     return allreduce
 
 
+TIMING = {}          # phase -> seconds of the last sc_exchange_by_cell (set TEC_DIST_TIMING=1)
+
+
 def sc_exchange_by_cell(engine, device, group=None):
     """All-to-all of the survivors by owner rank (cell id % world) + job-wide positions; installs
     the received records in the engine.  Returns the number of records this rank now owns."""
+    import os
+    import time
     import torch
     import torch.distributed as dist
+    timing = bool(os.environ.get("TEC_DIST_TIMING"))
+
+    def mark(name, t0):
+        if timing:
+            torch.cuda.synchronize(device)
+            TIMING[name] = TIMING.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
+    tm = time.perf_counter()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     on_gpu = dist.get_backend(group) == "nccl"
     n, p = engine.sc_export_dev()
@@ -115,12 +129,15 @@ def sc_exchange_by_cell(engine, device, group=None):
     dist.all_gather_object(counts, int(n), group=group)
     base = sum(counts[:rank])
     cols["gidx"] = base + torch.arange(n, dtype=torch.int64, device=device)
-    dest = (cols["cell"].to(torch.int64) & 0xFFFFFFFF) % world
-    order = torch.argsort(dest, stable=True)
-    send = torch.bincount(dest, minlength=world).tolist()
+    tm = mark("export+counts", tm)
+    # cell ids are below 2^31 (whitelist positions), so the int32 view is the id itself
+    dest = (cols["cell"] % world).to(torch.uint8)
+    order = torch.argsort(dest, stable=True)               # one 8-bit radix pass
+    send = torch.bincount(dest.to(torch.int64), minlength=world).tolist()
     recv_all = [None] * world
     dist.all_gather_object(recv_all, send, group=group)
     recv = [recv_all[r][rank] for r in range(world)]
+    tm = mark("partition", tm)
     out = {}
     for k, t in cols.items():
         src = t[order].contiguous()
@@ -132,12 +149,14 @@ def sc_exchange_by_cell(engine, device, group=None):
             dist.all_gather_object(parts, [x.cpu() for x in torch.split(src, send)], group=group)
             dst = torch.cat([parts[r][rank] for r in range(world)]).to(device)
         out[k] = dst
-    o2 = torch.argsort(out["gidx"])
-    out = {k: v[o2].contiguous() for k, v in out.items()}
+    tm = mark("all_to_all", tm)
+    # Each rank's file slice precedes the next rank's, every sender sends in file order and the
+    # received parts are laid out by source rank: the result is already ascending in gidx.
     torch.cuda.synchronize(device)
     n2 = int(out["gidx"].numel())
     engine.sc_import_dev(n2, *[out[k].data_ptr() for k in ("cell", "umi", "left", "rite", "cs", "gidx")])
     engine.sc_set_collective(make_allreduce(device, group), rank, world)
+    mark("import", tm)
     return n2
 
 
