@@ -13,6 +13,7 @@
 //   common path.
 #pragma once
 #include "common.cuh"
+#include "stab_build.h"
 
 // number of features of chromosome [lo, lo+n) with L <= x, through the coarse directory
 __device__ __forceinline__ int upper_bound_L(const IndexView& iv, int c, int64_t lo, int n, int x) {
@@ -590,9 +591,14 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
             else {
                 const uint2 cell = __ldg(sv.cells + c);
                 const int xa = loc1, xb = loc2 - 1;
-                const int ka = xa >> shift, kb = xb >> shift;                    // arithmetic shift: negative stays negative
+                int ka = xa >> shift, kb = xb >> shift;                          // arithmetic shift: negative stays negative
                 const bool va = (u32)ka < cell.y, vb = (u32)kb < cell.y;         // negative -> huge -> false
-                const u32 ra = (u32)xa & cmask, rb = (u32)xb & cmask;
+                u32 ra = (u32)xa & cmask, rb = (u32)xb & cmask;
+                if (va && vb && ka != kb) {
+                    // neighbouring cells: the lower cell's list reaches STAB_EXT bp into the upper one
+                    if (kb == ka + 1 && rb < STAB_EXT) { kb = ka; rb += cmask + 1; }
+                    else if (ka == kb + 1 && ra < STAB_EXT) { ka = kb; ra += cmask + 1; }
+                }
                 if (va && vb && ka != kb) {
                     qe.secA = (cell.x + (u32)ka) | (1u << 24);
                     qe.secB = cell.x + (u32)kb;

@@ -25,6 +25,11 @@
 // i.e. one add per word tests two entries (SIMD within a register; the adds run on either the
 // integer or the FMA pipe, which matters because the kernel is integer-ALU bound).
 //
+// Every cell's list also covers the first STAB_EXT bp of the next cell (relative positions up to
+// 2^shift + STAB_EXT - 1 still fit the 16-bit lanes), so that the two points of a read pair that
+// lies across a cell border are answered by ONE sector; a single point is always looked up in the
+// cell it falls in, where the extension is invisible.
+//
 // Intervals of the same ensg are merged per chromosome first (union of [L, R)), so one ensg never
 // has two overlapping or touching entries; entries are sorted by start.  A cell with more than 5
 // entries continues in overflow sectors (same format, stored after the primary cells, consecutive
@@ -41,6 +46,7 @@
 #include <vector>
 
 #define STAB_ENTRIES 5
+#define STAB_EXT 256                     // a cell's entries also cover the first STAB_EXT bp of the next cell
 #define STAB_MAX_SHIFT 11
 #define STAB_MAX_SLOTS 65535
 #define STAB_BLOCK_SHIFT 7               // ovf_base granularity: 128 primary sectors
@@ -125,9 +131,11 @@ inline void stab_build(StabTable& t, int n_chrom, const int64_t* chrom_off, cons
             size_t j = i + 1;
             while (j < iv.size() && iv[j].slot == s && iv[j].L <= b) { b = std::max<int64_t>(b, iv[j].R); ++j; }
             t.n_merged++;
-            for (int64_t k = a >> shift; k <= (b - 1) >> shift; ++k) {
+            const int64_t n_cells_c = t.cell_base[(size_t)c + 1] - t.cell_base[(size_t)c];
+            for (int64_t k = std::max<int64_t>(0, (a - STAB_EXT) >> shift); k <= (b - 1) >> shift && k < n_cells_c; ++k) {
                 const int64_t c0 = k << shift;
-                const int64_t lo = std::max(a, c0), hi = std::min(b, c0 + csize);
+                const int64_t lo = std::max(a, c0), hi = std::min(b, c0 + csize + STAB_EXT);
+                if (hi <= lo) continue;
                 ent.push_back({t.cell_base[(size_t)c] + k, (uint32_t)(lo - c0), (uint32_t)(hi - lo), s});
             }
             i = j;
