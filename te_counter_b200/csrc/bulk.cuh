@@ -110,7 +110,7 @@ bulk_count_kernel(IndexView iv, int64_t n_units, int qual,
             loc1 = start[u];                                                           // :213
             loc2 = end[u];                                                             // :214
         }
-        if (c >= iv.n_chrom) { st.badchrom++; continue; }                              // :100 / :216
+        if (!chrom_in_index(iv, c)) { st.badchrom++; continue; }                       // :100 / :216
 
         u32 typemask = 0, nd = 0, dist[BULK_MAX_DISTINCT];
         bool overflow = false;
@@ -573,7 +573,10 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
         const bool f_qc = (cur.fl & reject2) != 0;                                         // :81-86 / :204
         const bool f_lq = (int)cur.q < qual;                                               // :88 / :208
         const bool f_nm = PAIRED && (cur.fl & TEC_F_NAME_MISMATCH);                        // :92-94
-        const bool f_bc = c >= iv.n_chrom;                                                 // :100 / :216
+        // cells[] has one entry per chromosome plus a sentinel; chromosomes that are not keys of the
+        // bucket hash (no feature) have zero cells
+        const uint2 cell = __ldg(sv.cells + min((u32)c, (u32)iv.n_chrom));
+        const bool f_bc = cell.y == 0;                                                     // :100 / :216
         n_qcfail += live & f_qc;
         n_lowq += live & !f_qc & f_lq;
         n_badchrom += live & !(f_qc | f_lq | f_nm) & f_bc;
@@ -589,7 +592,6 @@ bulk_count_cell_kernel(IndexView iv, StabView sv, int64_t n_units, int qual,
                                             : ((loc1 % bs == 0) || ((loc2 + 1) % bs == 0));
             if (edge) slow = true;
             else {
-                const uint2 cell = __ldg(sv.cells + c);
                 const int xa = loc1, xb = loc2 - 1;
                 int ka = xa >> shift, kb = xb >> shift;                          // arithmetic shift: negative stays negative
                 const bool va = (u32)ka < cell.y, vb = (u32)kb < cell.y;         // negative -> huge -> false

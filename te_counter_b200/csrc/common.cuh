@@ -30,11 +30,15 @@ struct IndexView {
     const int64_t* chrom_off;   // n_chrom + 1
     const u32* dir;
     const int64_t* dir_off;     // n_chrom + 1
+    const uint8_t* chrom_valid; // n_chrom: the chromosome is a key of genelist.buckets (it has a feature in some bucket)
     int n_chrom;
     int shift;
     int bs;                     // bucket size (10000)
     int n_ensg;
 };
+
+// te_count.py:100 / :216 / :614  `chrom not in buckets`
+__device__ __forceinline__ bool chrom_in_index(const IndexView& iv, int c) { return c < iv.n_chrom && __ldg(iv.chrom_valid + c) != 0; }
 
 // Python-style floor division by a positive divisor (te_count.py:106 `(loc1-1)//bucket_size`).
 __host__ __device__ __forceinline__ int floordiv(int a, int b) {

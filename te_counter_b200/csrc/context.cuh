@@ -14,6 +14,7 @@ struct DevIndex {
     int64_t* chrom_off = nullptr;
     u32* dir = nullptr;
     int64_t* dir_off = nullptr;
+    uint8_t* chrom_valid = nullptr;
     int n_chrom = 0, n_ensg = 0, bs = 10000, shift = 9;
     int64_t n_feat = 0, n_dir = 0;
     // cell table (stab_build.h); absent when the index exceeds its limits
@@ -49,7 +50,7 @@ struct DevIndex {
     IndexView view() const {
         IndexView v;
         v.L = L; v.R = R; v.pmaxR = pmaxR; v.info = info; v.chrom_off = chrom_off;
-        v.dir = dir; v.dir_off = dir_off; v.n_chrom = n_chrom; v.shift = shift; v.bs = bs; v.n_ensg = n_ensg;
+        v.dir = dir; v.dir_off = dir_off; v.chrom_valid = chrom_valid; v.n_chrom = n_chrom; v.shift = shift; v.bs = bs; v.n_ensg = n_ensg;
         return v;
     }
 };
@@ -166,7 +167,7 @@ inline void tec_ctx::free_stage() {
 inline void tec_ctx::free_index() {
     DevIndex& ix = idx;
     cudaFree(ix.L); cudaFree(ix.R); cudaFree(ix.pmaxR); cudaFree(ix.info);
-    cudaFree(ix.chrom_off); cudaFree(ix.dir); cudaFree(ix.dir_off);
+    cudaFree(ix.chrom_off); cudaFree(ix.dir); cudaFree(ix.dir_off); cudaFree(ix.chrom_valid);
     cudaFree(ix.st_sectors); cudaFree(ix.st_cells); cudaFree(ix.st_slot_type); cudaFree(ix.st_ovf_base);
     cudaFree(ix.sc_sectors); cudaFree(ix.sc_cells); cudaFree(ix.sc_ovf_base); cudaFree(ix.sc_pair_key); cudaFree(ix.sc_pair_type);
     ix = DevIndex();

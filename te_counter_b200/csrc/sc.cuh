@@ -410,7 +410,7 @@ __device__ void sc_count_fragment(const IndexView& iv, const ScTableView& tv, in
     out.n = 0; out.hit = out.assigned = out.crash = out.spilled = false;
     const int c = (int)(cs >> 2);
     const u32 rs = cs & 3u;
-    if (c >= iv.n_chrom) return;                                                       // :614
+    if (!chrom_in_index(iv, c)) return;                                                // :614
     u32 typemask = 0, np = 0;
     u32* pairs = out.key;
     bool over = false, missing = false, exact = true;

@@ -171,6 +171,11 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
         }
         dir_off[(size_t)c + 1] = dir_off[(size_t)c] + ((int64_t)(maxL >> shift) + 2);
     }
+    // a chromosome is "in the index" iff it is a key of genelist.buckets: some feature of it falls in a bucket
+    std::vector<uint8_t> chrom_valid((size_t)std::max(n_chrom, 1), 0);
+    for (int c = 0; c < n_chrom; ++c)
+        for (int64_t i = chrom_off[c]; i < chrom_off[c + 1] && !chrom_valid[(size_t)c]; ++i)
+            if (floordiv(R[i] + bucket_size, bucket_size) > L[i] / bucket_size) chrom_valid[(size_t)c] = 1;
     const int64_t n_dir = dir_off[(size_t)n_chrom];
     ix.n_chrom = n_chrom; ix.n_feat = nf; ix.n_ensg = n_ensg; ix.bs = bucket_size; ix.shift = shift; ix.n_dir = n_dir;
     const size_t nfa = (size_t)std::max<int64_t>(nf, 1);
@@ -181,6 +186,8 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
     TEC_CUDA(cudaMalloc(&ix.chrom_off, ((size_t)n_chrom + 1) * 8));
     TEC_CUDA(cudaMalloc(&ix.dir_off, ((size_t)n_chrom + 1) * 8));
     TEC_CUDA(cudaMalloc(&ix.dir, (size_t)std::max<int64_t>(n_dir, 1) * 4));
+    TEC_CUDA(cudaMalloc(&ix.chrom_valid, chrom_valid.size()));
+    TEC_CUDA(cudaMemcpyAsync(ix.chrom_valid, chrom_valid.data(), chrom_valid.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (nf) {
         TEC_CUDA(cudaMemcpyAsync(ix.L, L, nfa * 4, cudaMemcpyHostToDevice, ctx->stream));
         TEC_CUDA(cudaMemcpyAsync(ix.R, R, nfa * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -201,9 +208,10 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
         stab_build(st, n_chrom, chrom_off, L, R, fslot.data(), type_code, n_ensg, ctx->opt_stab_shift);
         if (st.why_not.empty()) {
             TEC_CUDA(cudaMalloc(&ix.st_sectors, std::max<size_t>(st.sectors.size(), 8) * 4));
-            std::vector<uint2> cells((size_t)std::max(n_chrom, 1));
+            std::vector<uint2> cells((size_t)n_chrom + 1, make_uint2(0u, 0u));      // + sentinel for ids outside the index
             for (int c = 0; c < n_chrom; ++c)
-                cells[(size_t)c] = make_uint2((unsigned)st.cell_base[(size_t)c], (unsigned)(st.cell_base[(size_t)c + 1] - st.cell_base[(size_t)c]));
+                if (chrom_valid[(size_t)c])
+                    cells[(size_t)c] = make_uint2((unsigned)st.cell_base[(size_t)c], (unsigned)(st.cell_base[(size_t)c + 1] - st.cell_base[(size_t)c]));
             TEC_CUDA(cudaMalloc(&ix.st_cells, cells.size() * sizeof(uint2)));
             TEC_CUDA(cudaMalloc(&ix.st_slot_type, st.slot_type.size()));
             TEC_CUDA(cudaMalloc(&ix.st_ovf_base, st.ovf_base.size() * 4));
