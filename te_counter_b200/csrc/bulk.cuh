@@ -329,11 +329,10 @@ __device__ __forceinline__ void bump_entry(u32 hit, const Sector& s, u32 hot_add
     const u32 slot = sector_slot_c<I>(s);
     const u32 bit = I == 0 ? HB0 : I == 1 ? HB1 : I == 2 ? HB2 : I == 3 ? HB3 : HB4;
     if (ALLHOT) {
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                     "and.b32 t, %0, %1;\n\t"
-                     "setp.ne.u32 p, t, 0;\n\t"
-                     "@p red.shared.add.u32 [%2], %3;\n\t}"
-                     :: "r"(hit), "r"(bit), "r"(hot_addr + slot * 4u), "r"(one) : "memory");
+        // unconditional reduction: entries that were not hit add to a per-lane scratch word behind the
+        // counters, so there is no branch (ptxas never predicates a shared-memory reduction)
+        const u32 addr = (hit & bit) ? (hot_addr + slot * 4u) : (hot_addr + (n_hot + (threadIdx.x & 31)) * 4u);
+        asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(one) : "memory");
     } else {
         asm volatile("{\n\t.reg .pred p, q, r;\n\t.reg .b32 t;\n\t"
                      "and.b32 t, %0, %1;\n\t"

@@ -313,10 +313,10 @@ static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, 
         // every ensg counter in shared memory when they fit beside the rings (one 1024-thread CTA per SM);
         // otherwise the TEC_HOT_SLOTS hottest ones (two 512-thread CTAs per SM)
         const size_t all_bytes = (size_t)ctx->idx.n_ensg * 4;
-        const bool allhot = ctx->opt_all_hot != 0 && all_bytes + 44 * 1024 <= (size_t)ctx->smem_optin;
+        const bool allhot = ctx->opt_all_hot != 0 && all_bytes + 45 * 1024 <= (size_t)ctx->smem_optin;
         const int nt = allhot ? 1024 : 512;
         const u32 n_hot = allhot ? (u32)ctx->idx.n_ensg : (u32)std::min<int64_t>(TEC_HOT_SLOTS, ctx->idx.n_ensg);
-        const size_t dyn = std::max<size_t>((size_t)n_hot * 4, 16);
+        const size_t dyn = (size_t)n_hot * 4 + 128;            // + one scratch word per lane (bump_entry)
         const int per_sm = allhot ? 1 : ctx->opt_ctas_per_sm;
         const int blocks = (int)std::min<int64_t>((n_tiles + nt / 32 - 1) / (nt / 32), (int64_t)ctx->n_sm * per_sm);
         const int64_t ring_entries = (int64_t)blocks * (nt / 32) * BULK_QCAP;
