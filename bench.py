@@ -388,6 +388,9 @@ def run_ours_sc(args, rank, world, local, dev):
     n_wl, maxcells, pad, bundle_keys = 100_000, 10_000, 1000, 10_000_000
     idx = make_index(args.index_scale)
     eng = _lib.Engine(local)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     eng.upload_index(idx)
     # this rank's slice of the coordinate-sorted file: `parts` consecutive genome slices
     parts = max(1, (n_rec + 124_999_999) // 125_000_000)

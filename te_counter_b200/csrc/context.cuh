@@ -137,6 +137,7 @@ struct tec_ctx {
     int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 stab-table kernel
     int opt_stab_shift = 11;
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
+    int opt_sc_pack_umi = 1;              // single cell: 2-bit UMI sort keys when every UMI is fixed-length ACGT
     int opt_sc_algo = -1;                 // -1 auto, 0 exact search only, 1 cell table
     int opt_ctas_per_sm = 2;              // resident CTAs per SM of the fast bulk kernel (512 threads each)
 

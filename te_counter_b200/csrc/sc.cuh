@@ -174,6 +174,26 @@ __global__ void sc_or_kernel(int64_t n, const u64* __restrict__ v, u64* __restri
     for (int o = 16; o > 0; o >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicOr(out, acc);
 }
+// UMI codes are 3 bits per character (reads.py: A 1, C 2, G 3, N 4, T 5, 0 = end), left aligned in 63 bits.
+// When every UMI has exactly L characters over {A, C, G, T} the same order is kept by 2 bits per
+// character, and the sort key shrinks from 64 to 32 bits.  Anything else raises *bad.
+__global__ void sc_umi_pack2_kernel(int64_t n, const u64* __restrict__ umi, int L, u32* __restrict__ key32, u32* __restrict__ bad) {
+    bool any_bad = false;
+    SC_LOOP(i, n) {
+        const u64 code = umi[i];
+        u32 k = 0;
+        bool ok = (code & ((1ULL << (3 * (21 - L))) - 1ULL)) == 0;
+        for (int j = 0; j < L; ++j) {
+            const u32 g = (u32)(code >> (3 * (20 - j))) & 7u;
+            const u32 m = g == 1u ? 0u : g == 2u ? 1u : g == 3u ? 2u : 3u;
+            ok &= (g == 1u) | (g == 2u) | (g == 3u) | (g == 5u);
+            k = (k << 2) | m;
+        }
+        key32[i] = k;
+        any_bad |= !ok;
+    }
+    if (__any_sync(0xFFFFFFFFu, any_bad) && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
+}
 template <class T>
 __global__ void sc_gather_kernel(int64_t n, const u32* __restrict__ perm, const T* __restrict__ src, T* __restrict__ dst) {
     SC_LOOP(j, n) dst[j] = src[perm[j]];
@@ -939,8 +959,32 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         TEC_CUDA(A.get(&perm1, (size_t)N));
         TEC_CUDA(A.get(&uk, (size_t)N));
         sc_iota_kernel<<<SC_GRID(N)>>>(N, iota);
-        int rc = sc_sort_pairs(ctx, s->umi, uk, iota, perm1, N, b0, b1);
-        if (rc) return rc;
+        int rc = TEC_OK;
+        // 32-bit keys when every UMI is a fixed-length string over {A, C, G, T} (2 bits per character)
+        bool packed = false;
+        const int umi_len = h_or ? 21 - b0 / 3 : 0;
+        if (ctx->opt_sc_pack_umi && umi_len >= 1 && umi_len <= 16) {
+            u32 *k32 = nullptr, *k32s = nullptr, *d_bad = nullptr;
+            TEC_CUDA(A.get(&k32, (size_t)N));
+            TEC_CUDA(A.get(&k32s, (size_t)N));
+            TEC_CUDA(A.get(&d_bad, 1));
+            TEC_CUDA(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+            sc_umi_pack2_kernel<<<SC_GRID(N)>>>(N, s->umi, umi_len, k32, d_bad);
+            ctx->launches++;
+            u32 h_bad = 0;
+            TEC_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (!h_bad) {
+                rc = sc_sort_pairs(ctx, k32, k32s, iota, perm1, N, 0, 2 * umi_len);
+                if (rc) return rc;
+                packed = true;
+            }
+            A.release(k32); A.release(k32s); A.release(d_bad);
+        }
+        if (!packed) {
+            rc = sc_sort_pairs(ctx, s->umi, uk, iota, perm1, N, b0, b1);
+            if (rc) return rc;
+        }
         A.release(uk); uk = nullptr;
         TEC_CUDA(A.get(&ck, (size_t)N));
         TEC_CUDA(A.get(&scell, (size_t)N));

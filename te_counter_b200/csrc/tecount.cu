@@ -455,6 +455,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     if (k == "bulk_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "bulk_algo: -1, 0 or 1"); ctx->opt_bulk_algo = (int)value; }
     else if (k == "stab_shift") { if (value < 8 || value > STAB_MAX_SHIFT) TEC_FAIL(TEC_ERR_ARG, "stab_shift: 8..11"); ctx->opt_stab_shift = (int)value; }
     else if (k == "sc_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "sc_algo: -1, 0 or 1"); ctx->opt_sc_algo = (int)value; }
+    else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
     else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else TEC_FAIL(TEC_ERR_ARG, "tec_set_option: unknown key " + k);

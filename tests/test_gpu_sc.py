@@ -144,3 +144,26 @@ def test_sc_push_chunking_invariance(engine):
     b = run_engine(engine, r, 20, True, 500, 3000, 40, 10, chunks=7)
     for x, y in zip(a, b):
         assert (x == y).all()
+
+
+def test_sc_umi_key_packing(engine):
+    """Fixed-length ACGT UMIs sort on 2-bit/char 32-bit keys; UMIs with N or mixed lengths fall back
+    to the 3-bit/char 64-bit keys.  Both must give the oracle's answer."""
+    from te_counter_b200.reads import encode_umi
+    rng = np.random.default_rng(7)
+    idx = synth.synth_index(11, n_te=30000, n_exon=9000, n_gene=600, chrom_len=3_000_000, n_chrom=3)
+    engine.upload_index(idx)
+    r = synth.synth_sc_reads(15, idx, 20000, n_whitelist=200, n_cells=40, umis_per_cell=30)
+    for pack in (1, 0):
+        engine.set_option("sc_pack_umi", pack)
+        check_against_oracle(engine, idx, r, 20, True, 200, 900, 30, 10)
+    engine.set_option("sc_pack_umi", 1)
+    # mixed alphabet / lengths: N inside, shorter UMIs, one-character UMIs
+    pool = ["ACGTACGTAC", "ACGTNCGTAC", "ACG", "A", "T", "TTTTTTTTTTTT", "ACGTACGTACG", "NNNN", "CATG", "CATGA"]
+    codes = np.array([encode_umi(u) for u in pool], dtype=np.uint64)
+    r2 = dict(r)
+    r2["umi"] = codes[rng.integers(0, len(pool), size=len(r["umi"]))]
+    check_against_oracle(engine, idx, r2, 20, False, 200, 50, 30, 10)
+    # order check of the packing itself: 3-bit codes and their string order agree with the 2-bit keys
+    us = sorted("".join(rng.choice(list("ACGT"), size=8)) for _ in range(200))
+    assert [encode_umi(u) for u in us] == sorted(encode_umi(u) for u in us)
