@@ -110,9 +110,15 @@ float tec_last_kernel_ms(tec_ctx* ctx);
 /* number of kernel launches issued by this context since creation */
 int64_t tec_launch_count(const tec_ctx* ctx);
 
-/* tuning knobs: "bulk_algo" (-1 auto, 0 exact search kernel, 1 stab-table kernel), "stab_shift"
- * (log2 of the stab-table cell size, used by the next tec_index_upload), "ctas_per_sm".
- * tec_get_info: "has_stab", "stab_bytes", "n_sm", "n_features"; -1 for unknown keys. */
+/* release cached device scratch (the single-cell finalize keeps its temporaries for the next call) */
+int tec_trim(tec_ctx* ctx);
+
+/* tuning knobs: "bulk_algo" (-1 auto, 0 exact search kernel, 1 cell-table kernel), "stab_shift"
+ * (log2 of the cell size, 8..11, used by the next tec_index_upload), "ctas_per_sm", "all_hot" (counters
+ * of every ensg in shared memory when they fit), "sc_algo" (-1 auto, 0 exact search in Part 3, 1 cell
+ * table), "sc_pack_umi" (2-bit UMI sort keys when possible).
+ * tec_get_info: "has_stab", "stab_bytes", "has_sc_stab", "sc_stab_bytes", "n_sm", "n_features",
+ * "stab_primary", "stab_overflow", "stab_entries", "last_slow_units"; -1 for unknown keys. */
 int tec_set_option(tec_ctx* ctx, const char* key, int64_t value);
 int64_t tec_get_info(tec_ctx* ctx, const char* key);
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "tec_stream": (_vp, [_vp]),
     "tec_last_kernel_ms": (ctypes.c_float, [_vp]),
     "tec_launch_count": (ctypes.c_int64, [_vp]),
+    "tec_trim": (ctypes.c_int, [_vp]),
     "tec_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
     "tec_get_info": (ctypes.c_int64, [_vp, ctypes.c_char_p]),
     "tec_index_upload": (ctypes.c_int, [_vp, ctypes.c_int32, _c_i64p, _c_i32p, _c_i32p, _c_i32p, _c_u8p,
@@ -149,6 +150,10 @@ class Engine:
 
     def launch_count(self):
         return int(self._lib.tec_launch_count(self._h))
+
+    def trim(self):
+        """free the device scratch cached by the single-cell finalize"""
+        self._check(self._lib.tec_trim(self._h))
 
     def set_option(self, key, value):
         self._check(self._lib.tec_set_option(self._h, key.encode(), int(value)))

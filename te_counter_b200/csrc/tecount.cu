@@ -90,6 +90,14 @@ extern "C" int tec_host_free(tec_ctx* ctx, void* p) {
     return TEC_OK;
 }
 
+extern "C" int tec_trim(tec_ctx* ctx) {
+    if (!ctx) return TEC_ERR_ARG;
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->cache.trim();
+    return TEC_OK;
+}
+
 extern "C" void* tec_stream(tec_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" float tec_last_kernel_ms(tec_ctx* ctx) {
     if (!ctx || !ctx->timed) return -1.f;
