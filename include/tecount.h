@@ -195,6 +195,14 @@ int tec_sc_export_dev(tec_ctx* ctx, int64_t* n, void** cell, void** umi, void** 
 int tec_sc_import_dev(tec_ctx* ctx, int64_t n, const uint32_t* cell, const uint64_t* umi, const int32_t* left,
                       const int32_t* rite, const uint32_t* cs, const uint64_t* gidx);
 
+/* the same exchange with one buffer: survivors packed as 32-byte records {u64 umi, u64 position,
+ * u32 cell, u32 cs, i32 left, i32 right} grouped by owner rank cell % world (at most 8 ranks), file
+ * order kept inside a group; counts[world] (host) are the group sizes, *records the device buffer.
+ * After the all-to-all (received groups concatenated by source rank) hand the records back with
+ * tec_sc_import_packed_dev. */
+int tec_sc_partition_dev(tec_ctx* ctx, int world, int64_t gidx_base, int64_t* counts, void** records);
+int tec_sc_import_packed_dev(tec_ctx* ctx, int64_t n, const void* records);
+
 /* sc_save_result's choice of rows (te_count.py:724-733): hit cells by count descending, ties by
  * ascending id, at most maxcells.  cells_out must hold min(maxcells, n_hit_cells) entries. */
 int tec_sc_select(tec_ctx* ctx, int64_t maxcells, uint32_t* cells_out, int64_t* n_out);

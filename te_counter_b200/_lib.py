@@ -57,6 +57,8 @@ SIGNATURES = {
     "tec_sc_set_collective": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int]),
     "tec_sc_export_dev": (ctypes.c_int, [_vp, _c_i64p] + [ctypes.POINTER(_vp)] * 5),
     "tec_sc_import_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tec_sc_partition_dev": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, _c_i64p, ctypes.POINTER(_vp)]),
+    "tec_sc_import_packed_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
 }
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int)
@@ -265,6 +267,16 @@ class Engine:
     def sc_import_dev(self, n, cell, umi, left, rite, cs, gidx):
         """device pointers (ints) of the exchanged survivors, ascending in gidx"""
         self._check(self._lib.tec_sc_import_dev(self._h, int(n), cell, umi, left, rite, cs, gidx))
+
+    def sc_partition_dev(self, world, gidx_base):
+        """(counts per owner rank, device pointer of the packed 32-byte records)"""
+        counts = (ctypes.c_int64 * world)()
+        p = _vp()
+        self._check(self._lib.tec_sc_partition_dev(self._h, int(world), int(gidx_base), counts, ctypes.byref(p)))
+        return list(counts), (p.value or 0)
+
+    def sc_import_packed_dev(self, n, records):
+        self._check(self._lib.tec_sc_import_packed_dev(self._h, int(n), records))
 
     def sc_select(self, maxcells, n_hit_cells):
         out = np.zeros(max(1, min(int(maxcells), int(n_hit_cells))), dtype=np.uint32)

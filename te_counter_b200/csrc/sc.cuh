@@ -40,6 +40,7 @@ struct ScState {
     int32_t* rite = nullptr;
     u32* cs = nullptr;              // chrom << 2 | strand code (0 '+', 1 '-', 2 'NA')
     int64_t n = 0, cap = 0;
+    void* packed = nullptr;         // multi-GPU: survivors packed for the exchange (tec_sc_partition_dev)
     u64* gidx = nullptr;            // multi-GPU: position of each survivor in the whole job's survivor order
     int64_t gidx_cap = 0;
     bool has_gidx = false;
@@ -73,6 +74,7 @@ inline void tec_ctx::free_sc() {
     if (!sc) return;
     cudaFree(sc->cell); cudaFree(sc->umi); cudaFree(sc->left); cudaFree(sc->rite); cudaFree(sc->cs); cudaFree(sc->gidx);
     cudaFree(sc->d_stats); cudaFree(sc->pos); cudaFree(sc->cub_tmp);
+    cache.put(sc->packed);
     sc_free_results(this, sc);
     delete sc;
     sc = nullptr;
@@ -249,11 +251,86 @@ __device__ __forceinline__ int sc_bundle_of(const int64_t* __restrict__ bstart, 
     return lo;
 }
 
+// ---- multi-GPU exchange: survivors packed as 32-byte records, grouped by owner rank (cell % world),
+// file order kept inside each group.  One warp owns a contiguous run of `per_warp` survivors.
+struct __align__(16) ScRecord { u64 umi; u64 gidx; u32 cell; u32 cs; int32_t left; int32_t rite; };
+#define SC_MAX_WORLD 8
+
+__global__ void sc_part_count_kernel(int64_t n, int world, int64_t per_warp, int n_warps, const u32* __restrict__ cell, u32* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps; w += (gridDim.x * blockDim.x) >> 5) {
+        u32 cnt[SC_MAX_WORLD];
+#pragma unroll
+        for (int d = 0; d < SC_MAX_WORLD; ++d) cnt[d] = 0;
+        const int64_t lo = (int64_t)w * per_warp, hi = min(n, lo + per_warp);
+        for (int64_t i = lo + lane; i < hi; i += 32) {
+            const int dst = (int)(cell[i] % (u32)world);
+#pragma unroll
+            for (int d = 0; d < SC_MAX_WORLD; ++d) cnt[d] += dst == d;
+        }
+#pragma unroll
+        for (int d = 0; d < SC_MAX_WORLD; ++d) {
+            const u32 t = (u32)warp_sum((u64)cnt[d]);
+            if (lane == 0 && d < world) counts[(size_t)d * n_warps + w] = t;
+        }
+    }
+}
+
+__global__ void sc_part_scatter_kernel(int64_t n, int world, int64_t per_warp, int n_warps, int64_t gidx_base,
+                                       const u32* __restrict__ cell, const u64* __restrict__ umi, const int32_t* __restrict__ left,
+                                       const int32_t* __restrict__ rite, const u32* __restrict__ cs, const u32* __restrict__ offsets,
+                                       ScRecord* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const u32 lt = (1u << lane) - 1u;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps; w += (gridDim.x * blockDim.x) >> 5) {
+        u32 off[SC_MAX_WORLD];
+#pragma unroll
+        for (int d = 0; d < SC_MAX_WORLD; ++d) off[d] = d < world ? offsets[(size_t)d * n_warps + w] : 0u;
+        const int64_t lo = (int64_t)w * per_warp, hi = min(n, lo + per_warp);
+        for (int64_t base = lo; base < hi; base += 32) {
+            const int64_t i = base + lane;
+            const bool live = i < hi;
+            const u32 c = live ? cell[i] : 0u;
+            const int dst = live ? (int)(c % (u32)world) : -1;
+            u32 pos = 0;
+#pragma unroll
+            for (int d = 0; d < SC_MAX_WORLD; ++d) {
+                const u32 m = __ballot_sync(0xFFFFFFFFu, dst == d);
+                if (dst == d) pos = off[d] + __popc(m & lt);
+                off[d] += __popc(m);
+            }
+            if (live) {
+                ScRecord r;
+                r.umi = umi[i]; r.gidx = (u64)(gidx_base + i); r.cell = c; r.cs = cs[i]; r.left = left[i]; r.rite = rite[i];
+                out[pos] = r;
+            }
+        }
+    }
+}
+
+__global__ void sc_unpack_kernel(int64_t n, const ScRecord* __restrict__ in, u32* __restrict__ cell, u64* __restrict__ umi,
+                                 int32_t* __restrict__ left, int32_t* __restrict__ rite, u32* __restrict__ cs, u64* __restrict__ gidx) {
+    SC_LOOP(i, n) {
+        const ScRecord r = in[i];
+        cell[i] = r.cell; umi[i] = r.umi; left[i] = r.left; rite[i] = r.rite; cs[i] = r.cs; gidx[i] = r.gidx;
+    }
+}
+
+// first index with gidx >= x (gidx ascending)
+__global__ void sc_lower_bound_kernel(int64_t n, const u64* __restrict__ gidx, u64 x0, u64 x1, int64_t* __restrict__ out) {
+    if (blockIdx.x || threadIdx.x > 1) return;
+    const u64 x = threadIdx.x ? x1 : x0;
+    int64_t a = 0, b = n;
+    while (a < b) { const int64_t m = (a + b) >> 1; if (gidx[m] < x) a = m + 1; else b = m; }
+    out[threadIdx.x] = a;
+}
+
 // multi-GPU bundle boundary search: histogram of the first-in-bundle records (bundle start S) whose
 // position falls in [lo, lo + n_bins * width)
-__global__ void sc_newkey_hist_kernel(int64_t n, const u64* __restrict__ gidx, const u32* __restrict__ prev, int64_t S, int64_t lo,
+__global__ void sc_newkey_hist_kernel(const int64_t* __restrict__ range, const u64* __restrict__ gidx, const u32* __restrict__ prev, int64_t S, int64_t lo,
                                       int64_t width, int n_bins, u64* __restrict__ hist) {
-    SC_LOOP(i, n) {
+    const int64_t i0 = range[0], n = range[1];          // survivors with lo <= gidx < lo + n_bins * width
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t g = (int64_t)gidx[i];
         if (g < lo) continue;
         const int64_t b = (g - lo) / width;
@@ -791,33 +868,64 @@ static int sc_bundles_global(tec_ctx* ctx, ScArena& A, int64_t N, const u32* pre
     const int64_t G = (int64_t)h_end;
     g_end = G;
     std::vector<u64> h_hist(SC_HIST_BINS);
-    int64_t S = 0;
+    int64_t* d_range = nullptr;
+    TEC_CUDA(A.get(&d_range, 2));
+    // histogram of the first-in-bundle survivors with lo <= position < lo + span (all ranks), into h_hist
+    auto histogram = [&](int64_t S, int64_t lo, int64_t span, int64_t& width) -> int {
+        width = (span + SC_HIST_BINS - 1) / SC_HIST_BINS;
+        TEC_CUDA(cudaMemsetAsync(hist, 0, SC_HIST_BINS * 8, ctx->stream));
+        // only the local survivors inside the window are read (positions are ascending)
+        sc_lower_bound_kernel<<<1, 32, 0, ctx->stream>>>(N, s->gidx, (u64)lo, (u64)(lo + span), d_range);
+        const int64_t guess = std::max<int64_t>(1, std::min<int64_t>(N, span / std::max(1, s->world) * 2 + 65536));
+        sc_newkey_hist_kernel<<<SC_GRID(guess)>>>(d_range, s->gidx, prev, S, lo, width, SC_HIST_BINS, hist);
+        ctx->launches += 2;
+        int rc2 = sc_allreduce(ctx, hist, SC_HIST_BINS, 1, 0);
+        if (rc2) return rc2;
+        TEC_CUDA(cudaMemcpyAsync(h_hist.data(), hist, SC_HIST_BINS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+        return TEC_OK;
+    };
+    int64_t S = 0, last_len = 0;
     while (S < G) {
         bstart.push_back(S);
-        int64_t lo = S, span = G - S, need = bundle_keys;
+        // a bundle is usually about as long as the one before it: look at windows of twice that length
+        int64_t lo = S, need = bundle_keys;
         bool found = false;
-        for (;;) {
-            const int64_t width = (span + SC_HIST_BINS - 1) / SC_HIST_BINS;
-            TEC_CUDA(cudaMemsetAsync(hist, 0, SC_HIST_BINS * 8, ctx->stream));
-            if (N) sc_newkey_hist_kernel<<<SC_GRID(N)>>>(N, s->gidx, prev, S, lo, width, SC_HIST_BINS, hist);
-            ctx->launches++;
-            rc = sc_allreduce(ctx, hist, SC_HIST_BINS, 1, 0);
+        while (lo < G && !found) {
+            int64_t span = last_len ? std::min<int64_t>(G - lo, 2 * last_len) : G - lo;
+            int64_t width = 1;
+            rc = histogram(S, lo, span, width);
             if (rc) return rc;
-            TEC_CUDA(cudaMemcpyAsync(h_hist.data(), hist, SC_HIST_BINS * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            TEC_CUDA(cudaStreamSynchronize(ctx->stream));
             int b = 0;
             int64_t cum = 0;
             for (; b < SC_HIST_BINS; ++b) {
                 if (cum + (int64_t)h_hist[(size_t)b] >= need) break;
                 cum += (int64_t)h_hist[(size_t)b];
             }
-            if (b == SC_HIST_BINS) break;                        // fewer than bundle_keys keys left: last bundle
-            if (width == 1) { S = lo + b + 1; found = true; break; }
-            need -= cum;
-            lo += (int64_t)b * width;
-            span = width;
+            if (b == SC_HIST_BINS) { need -= cum; lo += span; continue; }      // not in this window
+            // narrow down inside bin b
+            for (;;) {
+                if (width == 1) {
+                    const int64_t next = lo + b + 1;
+                    last_len = next - S;
+                    S = next;
+                    found = true;
+                    break;
+                }
+                need -= cum;
+                lo += (int64_t)b * width;
+                span = width;
+                rc = histogram(S, lo, span, width);
+                if (rc) return rc;
+                cum = 0;
+                for (b = 0; b < SC_HIST_BINS; ++b) {
+                    if (cum + (int64_t)h_hist[(size_t)b] >= need) break;
+                    cum += (int64_t)h_hist[(size_t)b];
+                }
+                if (b == SC_HIST_BINS) TEC_FAIL(TEC_ERR_STATE, "single-cell bundle search lost its key");
+            }
         }
-        if (!found) break;
+        if (!found) break;                                       // fewer than bundle_keys keys left: last bundle
     }
     A.release(hist);
     return TEC_OK;
@@ -881,6 +989,73 @@ extern "C" int tec_sc_import_dev(tec_ctx* ctx, int64_t n, const uint32_t* cell, 
         TEC_CUDA(cudaMemcpyAsync(s->gidx, gidx, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->n = n;
+    s->has_gidx = true;
+    return TEC_OK;
+}
+
+static int sc_excl_sum(tec_ctx* ctx, u32* in, u32* out, int64_t n);
+
+// Pack the survivors as 32-byte records grouped by owner rank (cell % world), file order kept inside a
+// group; counts[world] on the host.  The packed buffer lives until the next call / import.
+extern "C" int tec_sc_partition_dev(tec_ctx* ctx, int world, int64_t gidx_base, int64_t* counts, void** records) {
+    if (!ctx) return TEC_ERR_ARG;
+    ScState* s = ctx->sc;
+    if (!s || !s->active) TEC_FAIL(TEC_ERR_STATE, "tec_sc_partition_dev: tec_sc_begin not called");
+    if (world < 1 || world > SC_MAX_WORLD || !counts || !records) TEC_FAIL(TEC_ERR_ARG, "tec_sc_partition_dev: 1..8 ranks");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    const int64_t N = s->n;
+    const int n_warps = (int)std::max<int64_t>(1, std::min<int64_t>((N + 1023) / 1024, (int64_t)ctx->n_sm * 64));
+    const int64_t per_warp = ((N + n_warps - 1) / n_warps + 31) / 32 * 32;
+    ctx->cache.put(s->packed);
+    s->packed = nullptr;
+    TEC_CUDA(ctx->cache.get(&s->packed, (size_t)std::max<int64_t>(N, 1) * sizeof(ScRecord)));
+    u32* cnt = nullptr;
+    ScArena A(ctx->cache);
+    TEC_CUDA(A.get(&cnt, (size_t)world * n_warps + 1));
+    TEC_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)world * n_warps + 1) * 4, ctx->stream));
+    const int blocks = std::max(1, std::min((n_warps + 7) / 8, ctx->n_sm * 8));
+    sc_part_count_kernel<<<blocks, 256, 0, ctx->stream>>>(N, world, per_warp, n_warps, s->cell, cnt);
+    int rc = sc_excl_sum(ctx, cnt, cnt, (int64_t)world * n_warps + 1);
+    if (rc) return rc;
+    sc_part_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(N, world, per_warp, n_warps, gidx_base, s->cell, s->umi, s->left, s->rite,
+                                                           s->cs, cnt, (ScRecord*)s->packed);
+    ctx->launches += 4;
+    std::vector<u32> h((size_t)world + 1);
+    for (int d = 0; d <= world; ++d)
+        TEC_CUDA(cudaMemcpyAsync(&h[(size_t)d], cnt + (size_t)d * n_warps, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < world; ++d) counts[d] = (int64_t)h[(size_t)d + 1] - (int64_t)h[(size_t)d];
+    *records = s->packed;
+    return TEC_OK;
+}
+
+// Install exchanged records (device pointer, 32 bytes each, ascending in position) as this rank's survivors.
+extern "C" int tec_sc_import_packed_dev(tec_ctx* ctx, int64_t n, const void* records) {
+    if (!ctx) return TEC_ERR_ARG;
+    ScState* s = ctx->sc;
+    if (!s || !s->active) TEC_FAIL(TEC_ERR_STATE, "tec_sc_import_packed_dev: tec_sc_begin not called");
+    if (n < 0 || n >= (int64_t)0x7FFFFFF0 || (n && !records)) TEC_FAIL(TEC_ERR_ARG, "tec_sc_import_packed_dev: bad arguments");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n > s->cap) {
+        const int64_t cap = n + 1024;
+        TEC_CUDA(sc_grow(&s->cell, 0, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->umi, 0, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->left, 0, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->rite, 0, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->cs, 0, cap, ctx->stream));
+        s->cap = cap;
+    }
+    if (n > s->gidx_cap) {
+        TEC_CUDA(sc_grow(&s->gidx, 0, n + 1024, ctx->stream));
+        s->gidx_cap = n + 1024;
+    }
+    if (n) sc_unpack_kernel<<<SC_GRID(n)>>>(n, (const ScRecord*)records, s->cell, s->umi, s->left, s->rite, s->cs, s->gidx);
+    ctx->launches++;
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->cache.put(s->packed);
+    s->packed = nullptr;
     s->n = n;
     s->has_gidx = true;
     return TEC_OK;

@@ -121,40 +121,31 @@ def sc_exchange_by_cell(engine, device, group=None):
     tm = time.perf_counter()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     on_gpu = dist.get_backend(group) == "nccl"
-    n, p = engine.sc_export_dev()
-    cols = {"cell": _dev_tensor(p["cell"], n, "<i4", device), "umi": _dev_tensor(p["umi"], n, "<i8", device),
-            "left": _dev_tensor(p["left"], n, "<i4", device), "rite": _dev_tensor(p["rite"], n, "<i4", device),
-            "cs": _dev_tensor(p["cs"], n, "<i4", device)}
+    n, _ = engine.sc_export_dev()
     counts = [None] * world
     dist.all_gather_object(counts, int(n), group=group)
     base = sum(counts[:rank])
-    cols["gidx"] = base + torch.arange(n, dtype=torch.int64, device=device)
-    tm = mark("export+counts", tm)
-    # cell ids are below 2^31 (whitelist positions), so the int32 view is the id itself
-    dest = (cols["cell"] % world).to(torch.uint8)
-    order = torch.argsort(dest, stable=True)               # one 8-bit radix pass
-    send = torch.bincount(dest.to(torch.int64), minlength=world).tolist()
+    tm = mark("counts", tm)
+    # 32-byte records grouped by owner rank, file order kept inside a group (one kernel in the library)
+    send, ptr = engine.sc_partition_dev(world, base)
+    src = _dev_tensor(ptr, n * 4, "<i8", device)                 # 4 x int64 per record
     recv_all = [None] * world
     dist.all_gather_object(recv_all, send, group=group)
     recv = [recv_all[r][rank] for r in range(world)]
     tm = mark("partition", tm)
-    out = {}
-    for k, t in cols.items():
-        src = t[order].contiguous()
-        if on_gpu:
-            dst = torch.empty(sum(recv), dtype=t.dtype, device=device)
-            dist.all_to_all_single(dst, src, recv, send, group=group)
-        else:                                             # gloo has no all-to-all: gather everything, keep my part
-            parts = [None] * world
-            dist.all_gather_object(parts, [x.cpu() for x in torch.split(src, send)], group=group)
-            dst = torch.cat([parts[r][rank] for r in range(world)]).to(device)
-        out[k] = dst
+    if on_gpu:
+        dst = torch.empty(sum(recv) * 4, dtype=torch.int64, device=device)
+        dist.all_to_all_single(dst, src, [x * 4 for x in recv], [x * 4 for x in send], group=group)
+    else:                                                         # gloo has no all-to-all: gather everything, keep my part
+        parts = [None] * world
+        dist.all_gather_object(parts, [x.cpu() for x in torch.split(src, [x * 4 for x in send])], group=group)
+        dst = torch.cat([parts[r][rank] for r in range(world)]).to(device)
+    torch.cuda.synchronize(device)
     tm = mark("all_to_all", tm)
     # Each rank's file slice precedes the next rank's, every sender sends in file order and the
-    # received parts are laid out by source rank: the result is already ascending in gidx.
-    torch.cuda.synchronize(device)
-    n2 = int(out["gidx"].numel())
-    engine.sc_import_dev(n2, *[out[k].data_ptr() for k in ("cell", "umi", "left", "rite", "cs", "gidx")])
+    # received parts are laid out by source rank: the records are already ascending in position.
+    n2 = int(dst.numel() // 4)
+    engine.sc_import_packed_dev(n2, dst.data_ptr())
     engine.sc_set_collective(make_allreduce(device, group), rank, world)
     mark("import", tm)
     return n2
