@@ -179,8 +179,8 @@ int tec_sc_fetch(tec_ctx* ctx, int32_t* ensg, uint32_t* cell, int64_t* count,
                  uint32_t* hit_cell, int64_t* hit_count, int64_t* stats);
 /* ---- single cell on several GPUs (one process per GPU) -------------------------
  * The (cell, UMI) collapse is per cell, so after Part 1's filter the survivors are exchanged by cell
- * (all-to-all, done by the caller on the exported device columns), each carrying its position in
- * the job-wide survivor order.  tec_sc_finalize then runs the same pipeline per rank and calls the
+ * (all-to-all, done by the caller on the packed records of tec_sc_partition_dev), each carrying its
+ * position in the job-wide survivor order.  tec_sc_finalize then runs the same pipeline per rank and calls the
  * collective at the few points that are global: the bundle boundaries of te_count.py:377 (a running
  * count over the whole file), the per-cell raw counts and first appearances behind the top-cell
  * choice (:502), the per-bundle cell presence behind the held-line rule (:528), the per-cell hit
@@ -189,13 +189,10 @@ int tec_sc_fetch(tec_ctx* ctx, int32_t* ensg, uint32_t* cell, int64_t* count,
  *   dtype 0 u32, 1 u64, 2 i64; op 0 sum, 1 min, 2 max; returns 0 on success. */
 typedef int (*tec_allreduce_fn)(void* user, void* dev_ptr, int64_t count, int dtype, int op);
 int tec_sc_set_collective(tec_ctx* ctx, tec_allreduce_fn fn, void* user, int rank, int world);
-/* device pointers of the survivor columns after the pushes (cs = chrom << 2 | strand code) */
-int tec_sc_export_dev(tec_ctx* ctx, int64_t* n, void** cell, void** umi, void** left, void** rite, void** cs);
-/* replace the survivors by the exchanged ones (device pointers), ascending in gidx */
-int tec_sc_import_dev(tec_ctx* ctx, int64_t n, const uint32_t* cell, const uint64_t* umi, const int32_t* left,
-                      const int32_t* rite, const uint32_t* cs, const uint64_t* gidx);
+/* number of survivors held after the pushes */
+int tec_sc_survivors(tec_ctx* ctx, int64_t* n);
 
-/* the same exchange with one buffer: survivors packed as 32-byte records {u64 umi, u64 position,
+/* the exchange: survivors packed as 32-byte records {u64 umi, u64 position,
  * u32 cell, u32 cs, i32 left, i32 right} grouped by owner rank cell % world (at most 8 ranks), file
  * order kept inside a group; counts[world] (host) are the group sizes, *records the device buffer.
  * After the all-to-all (received groups concatenated by source rank) hand the records back with

@@ -55,8 +55,7 @@ SIGNATURES = {
     "tec_sc_fetch": (ctypes.c_int, [_vp, _c_i32p, _c_u32p, _c_i64p, _c_u32p, _c_i64p, _c_i64p]),
     "tec_sc_select": (ctypes.c_int, [_vp, ctypes.c_int64, _c_u32p, _c_i64p]),
     "tec_sc_set_collective": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int]),
-    "tec_sc_export_dev": (ctypes.c_int, [_vp, _c_i64p] + [ctypes.POINTER(_vp)] * 5),
-    "tec_sc_import_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tec_sc_survivors": (ctypes.c_int, [_vp, _c_i64p]),
     "tec_sc_partition_dev": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, _c_i64p, ctypes.POINTER(_vp)]),
     "tec_sc_import_packed_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
 }
@@ -257,16 +256,11 @@ class Engine:
         self._coll = ALLREDUCE_FN(_cb)                    # keep the trampoline alive
         self._check(self._lib.tec_sc_set_collective(self._h, ctypes.cast(self._coll, _vp), None, int(rank), int(world)))
 
-    def sc_export_dev(self):
-        """(n, {column: device pointer}) of the survivors held after the pushes."""
+    def sc_survivors(self):
+        """number of survivors held after the pushes"""
         n = ctypes.c_int64(0)
-        p = [_vp() for _ in range(5)]
-        self._check(self._lib.tec_sc_export_dev(self._h, ctypes.byref(n), *[ctypes.byref(x) for x in p]))
-        return n.value, dict(zip(("cell", "umi", "left", "rite", "cs"), [x.value or 0 for x in p]))
-
-    def sc_import_dev(self, n, cell, umi, left, rite, cs, gidx):
-        """device pointers (ints) of the exchanged survivors, ascending in gidx"""
-        self._check(self._lib.tec_sc_import_dev(self._h, int(n), cell, umi, left, rite, cs, gidx))
+        self._check(self._lib.tec_sc_survivors(self._h, ctypes.byref(n)))
+        return n.value
 
     def sc_partition_dev(self, world, gidx_base):
         """(counts per owner rank, device pointer of the packed 32-byte records)"""

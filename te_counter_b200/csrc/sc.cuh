@@ -36,9 +36,8 @@ struct ScState {
     // survivors, in file order
     u32* cell = nullptr;
     u64* umi = nullptr;
-    int32_t* left = nullptr;
-    int32_t* rite = nullptr;
-    u32* cs = nullptr;              // chrom << 2 | strand code (0 '+', 1 '-', 2 'NA')
+    uint4* frag = nullptr;          // {cs = chrom << 2 | strand code (0 '+', 1 '-', 2 'NA'), left, rite, 0}: one 16-byte
+                                    // record, so the gather into sorted order is one random read per survivor
     int64_t n = 0, cap = 0;
     void* packed = nullptr;         // multi-GPU: survivors packed for the exchange (tec_sc_partition_dev)
     u64* gidx = nullptr;            // multi-GPU: position of each survivor in the whole job's survivor order
@@ -72,7 +71,7 @@ static void sc_free_results(tec_ctx* ctx, ScState* s) {
 
 inline void tec_ctx::free_sc() {
     if (!sc) return;
-    cudaFree(sc->cell); cudaFree(sc->umi); cudaFree(sc->left); cudaFree(sc->rite); cudaFree(sc->cs); cudaFree(sc->gidx);
+    cudaFree(sc->cell); cudaFree(sc->umi); cudaFree(sc->frag); cudaFree(sc->gidx);
     cudaFree(sc->d_stats); cudaFree(sc->pos); cudaFree(sc->cub_tmp);
     cache.put(sc->packed);
     sc_free_results(this, sc);
@@ -146,8 +145,7 @@ __global__ void sc_scatter_kernel(int64_t n, int strand, int64_t base, const u32
                                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                                   const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ flag,
                                   const u32* __restrict__ cell, const u64* __restrict__ umi,
-                                  u32* __restrict__ o_cell, u64* __restrict__ o_umi, int32_t* __restrict__ o_left,
-                                  int32_t* __restrict__ o_rite, u32* __restrict__ o_cs) {
+                                  u32* __restrict__ o_cell, u64* __restrict__ o_umi, uint4* __restrict__ o_frag) {
     SC_LOOP(r, n) {
         const u32 p = keep_pos[r];
         const u32 nxt = (r + 1 < n) ? keep_pos[r + 1] : *keep_last;
@@ -155,10 +153,8 @@ __global__ void sc_scatter_kernel(int64_t n, int strand, int64_t base, const u32
         const int64_t o = base + p;
         o_cell[o] = cell[r];
         o_umi[o] = umi[r];
-        o_left[o] = start[r];                                                          // :434
-        o_rite[o] = end[r];                                                            // :435
         const u32 sc = strand ? ((flag[r] & TEC_F_REVERSE) ? 1u : 0u) : 2u;            // :437-438
-        o_cs[o] = ((u32)chrom[r] << 2) | sc;
+        o_frag[o] = make_uint4(((u32)chrom[r] << 2) | sc, (u32)start[r], (u32)end[r], 0u);   // :434-435
     }
 }
 
@@ -201,13 +197,13 @@ __global__ void sc_gather_kernel(int64_t n, const u32* __restrict__ perm, const 
     SC_LOOP(j, n) dst[j] = src[perm[j]];
 }
 // fragment columns in sorted (cell, umi, i) order: one pass of random reads instead of one per use
-__global__ void sc_gather3_kernel(int64_t n, const u32* __restrict__ perm, const u32* __restrict__ cs, const int32_t* __restrict__ left,
-                                  const int32_t* __restrict__ rite, u32* __restrict__ scs, int32_t* __restrict__ sleft, int32_t* __restrict__ srite) {
+__global__ void sc_gather3_kernel(int64_t n, const u32* __restrict__ perm, const uint4* __restrict__ frag,
+                                  u32* __restrict__ scs, int32_t* __restrict__ sleft, int32_t* __restrict__ srite) {
     SC_LOOP(j, n) {
-        const u32 i = perm[j];
-        scs[j] = cs[i];
-        sleft[j] = left[i];
-        srite[j] = rite[i];
+        const uint4 f = __ldg(frag + perm[j]);
+        scs[j] = f.x;
+        sleft[j] = (int32_t)f.y;
+        srite[j] = (int32_t)f.z;
     }
 }
 template <class T>
@@ -277,9 +273,8 @@ __global__ void sc_part_count_kernel(int64_t n, int world, int64_t per_warp, int
 }
 
 __global__ void sc_part_scatter_kernel(int64_t n, int world, int64_t per_warp, int n_warps, int64_t gidx_base,
-                                       const u32* __restrict__ cell, const u64* __restrict__ umi, const int32_t* __restrict__ left,
-                                       const int32_t* __restrict__ rite, const u32* __restrict__ cs, const u32* __restrict__ offsets,
-                                       ScRecord* __restrict__ out) {
+                                       const u32* __restrict__ cell, const u64* __restrict__ umi, const uint4* __restrict__ frag,
+                                       const u32* __restrict__ offsets, ScRecord* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
     for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps; w += (gridDim.x * blockDim.x) >> 5) {
@@ -301,7 +296,8 @@ __global__ void sc_part_scatter_kernel(int64_t n, int world, int64_t per_warp, i
             }
             if (live) {
                 ScRecord r;
-                r.umi = umi[i]; r.gidx = (u64)(gidx_base + i); r.cell = c; r.cs = cs[i]; r.left = left[i]; r.rite = rite[i];
+                const uint4 f = frag[i];
+                r.umi = umi[i]; r.gidx = (u64)(gidx_base + i); r.cell = c; r.cs = f.x; r.left = (int32_t)f.y; r.rite = (int32_t)f.z;
                 out[pos] = r;
             }
         }
@@ -309,10 +305,10 @@ __global__ void sc_part_scatter_kernel(int64_t n, int world, int64_t per_warp, i
 }
 
 __global__ void sc_unpack_kernel(int64_t n, const ScRecord* __restrict__ in, u32* __restrict__ cell, u64* __restrict__ umi,
-                                 int32_t* __restrict__ left, int32_t* __restrict__ rite, u32* __restrict__ cs, u64* __restrict__ gidx) {
+                                 uint4* __restrict__ frag, u64* __restrict__ gidx) {
     SC_LOOP(i, n) {
         const ScRecord r = in[i];
-        cell[i] = r.cell; umi[i] = r.umi; left[i] = r.left; rite[i] = r.rite; cs[i] = r.cs; gidx[i] = r.gidx;
+        cell[i] = r.cell; umi[i] = r.umi; frag[i] = make_uint4(r.cs, (u32)r.left, (u32)r.rite, 0u); gidx[i] = r.gidx;
     }
 }
 
@@ -767,14 +763,12 @@ static int sc_ingest_dev(tec_ctx* ctx, int64_t n, const int32_t* start, const in
         const int64_t cap = std::max<int64_t>(s->n + h_total, s->cap + s->cap / 2 + 1024);
         TEC_CUDA(sc_grow(&s->cell, s->n, cap, ctx->stream));
         TEC_CUDA(sc_grow(&s->umi, s->n, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->left, s->n, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->rite, s->n, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->cs, s->n, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->frag, s->n, cap, ctx->stream));
         s->cap = cap;
     }
     if (h_total) {
         sc_scatter_kernel<<<SC_GRID(n)>>>(n, s->strand, s->n, keep, total, start, end, chrom, flag, cell, umi,
-                                          s->cell, s->umi, s->left, s->rite, s->cs);
+                                          s->cell, s->umi, s->frag);
         ctx->launches++;
     }
     TEC_CUDA(cudaGetLastError());
@@ -943,54 +937,12 @@ extern "C" int tec_sc_set_collective(tec_ctx* ctx, tec_allreduce_fn fn, void* us
     return TEC_OK;
 }
 
-extern "C" int tec_sc_export_dev(tec_ctx* ctx, int64_t* n, void** cell, void** umi, void** left, void** rite, void** cs) {
+// number of survivors held after the pushes
+extern "C" int tec_sc_survivors(tec_ctx* ctx, int64_t* n) {
     if (!ctx) return TEC_ERR_ARG;
     ScState* s = ctx->sc;
-    if (!s || !s->active) TEC_FAIL(TEC_ERR_STATE, "tec_sc_export_dev: tec_sc_begin not called");
-    TEC_CUDA(cudaSetDevice(ctx->device));
-    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!s || !s->active) TEC_FAIL(TEC_ERR_STATE, "tec_sc_survivors: tec_sc_begin not called");
     if (n) *n = s->n;
-    if (cell) *cell = s->cell;
-    if (umi) *umi = s->umi;
-    if (left) *left = s->left;
-    if (rite) *rite = s->rite;
-    if (cs) *cs = s->cs;
-    return TEC_OK;
-}
-
-extern "C" int tec_sc_import_dev(tec_ctx* ctx, int64_t n, const uint32_t* cell, const uint64_t* umi, const int32_t* left,
-                                 const int32_t* rite, const uint32_t* cs, const uint64_t* gidx) {
-    if (!ctx) return TEC_ERR_ARG;
-    ScState* s = ctx->sc;
-    if (!s || !s->active) TEC_FAIL(TEC_ERR_STATE, "tec_sc_import_dev: tec_sc_begin not called");
-    if (n < 0 || n >= (int64_t)0x7FFFFFF0) TEC_FAIL(TEC_ERR_ARG, "tec_sc_import_dev: bad record count");
-    if (n && (!cell || !umi || !left || !rite || !cs || !gidx)) TEC_FAIL(TEC_ERR_ARG, "tec_sc_import_dev: null array");
-    TEC_CUDA(cudaSetDevice(ctx->device));
-    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (n > s->cap) {
-        const int64_t cap = n + 1024;
-        TEC_CUDA(sc_grow(&s->cell, 0, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->umi, 0, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->left, 0, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->rite, 0, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->cs, 0, cap, ctx->stream));
-        s->cap = cap;
-    }
-    if (n > s->gidx_cap) {
-        TEC_CUDA(sc_grow(&s->gidx, 0, n + 1024, ctx->stream));
-        s->gidx_cap = n + 1024;
-    }
-    if (n) {
-        TEC_CUDA(cudaMemcpyAsync(s->cell, cell, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        TEC_CUDA(cudaMemcpyAsync(s->umi, umi, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        TEC_CUDA(cudaMemcpyAsync(s->left, left, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        TEC_CUDA(cudaMemcpyAsync(s->rite, rite, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        TEC_CUDA(cudaMemcpyAsync(s->cs, cs, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        TEC_CUDA(cudaMemcpyAsync(s->gidx, gidx, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
-    s->n = n;
-    s->has_gidx = true;
     return TEC_OK;
 }
 
@@ -1018,8 +970,8 @@ extern "C" int tec_sc_partition_dev(tec_ctx* ctx, int world, int64_t gidx_base, 
     sc_part_count_kernel<<<blocks, 256, 0, ctx->stream>>>(N, world, per_warp, n_warps, s->cell, cnt);
     int rc = sc_excl_sum(ctx, cnt, cnt, (int64_t)world * n_warps + 1);
     if (rc) return rc;
-    sc_part_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(N, world, per_warp, n_warps, gidx_base, s->cell, s->umi, s->left, s->rite,
-                                                           s->cs, cnt, (ScRecord*)s->packed);
+    sc_part_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(N, world, per_warp, n_warps, gidx_base, s->cell, s->umi, s->frag,
+                                                           cnt, (ScRecord*)s->packed);
     ctx->launches += 4;
     std::vector<u32> h((size_t)world + 1);
     for (int d = 0; d <= world; ++d)
@@ -1042,16 +994,14 @@ extern "C" int tec_sc_import_packed_dev(tec_ctx* ctx, int64_t n, const void* rec
         const int64_t cap = n + 1024;
         TEC_CUDA(sc_grow(&s->cell, 0, cap, ctx->stream));
         TEC_CUDA(sc_grow(&s->umi, 0, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->left, 0, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->rite, 0, cap, ctx->stream));
-        TEC_CUDA(sc_grow(&s->cs, 0, cap, ctx->stream));
+        TEC_CUDA(sc_grow(&s->frag, 0, cap, ctx->stream));
         s->cap = cap;
     }
     if (n > s->gidx_cap) {
         TEC_CUDA(sc_grow(&s->gidx, 0, n + 1024, ctx->stream));
         s->gidx_cap = n + 1024;
     }
-    if (n) sc_unpack_kernel<<<SC_GRID(n)>>>(n, (const ScRecord*)records, s->cell, s->umi, s->left, s->rite, s->cs, s->gidx);
+    if (n) sc_unpack_kernel<<<SC_GRID(n)>>>(n, (const ScRecord*)records, s->cell, s->umi, s->frag, s->gidx);
     ctx->launches++;
     TEC_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->cache.put(s->packed);
@@ -1175,7 +1125,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         TEC_CUDA(A.get(&scs, (size_t)N));
         TEC_CUDA(A.get(&sleft, (size_t)N));
         TEC_CUDA(A.get(&srite, (size_t)N));
-        sc_gather3_kernel<<<SC_GRID(N)>>>(N, perm, s->cs, s->left, s->rite, scs, sleft, srite);
+        sc_gather3_kernel<<<SC_GRID(N)>>>(N, perm, s->frag, scs, sleft, srite);
         ctx->launches++;
         u32 *prev = nullptr, *khead = nullptr;
         TEC_CUDA(A.get(&prev, (size_t)N));

@@ -121,7 +121,7 @@ def sc_exchange_by_cell(engine, device, group=None):
     tm = time.perf_counter()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     on_gpu = dist.get_backend(group) == "nccl"
-    n, _ = engine.sc_export_dev()
+    n = engine.sc_survivors()
     counts = [None] * world
     dist.all_gather_object(counts, int(n), group=group)
     base = sum(counts[:rank])
