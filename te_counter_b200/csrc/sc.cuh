@@ -465,6 +465,7 @@ __device__ __forceinline__ void sc_for_each_hit(const IndexView& iv, int c, int 
 }
 
 #define SC_MAX_PAIRS 24
+#define SC_REG_PAIRS 8
 
 struct ScOut {
     u64* pairs;            // ensg << 32 | cell, appended
@@ -510,9 +511,12 @@ __device__ void sc_count_fragment(const IndexView& iv, const ScTableView& tv, in
     if (tv.present && left >= 0 && left < rite) {
         // for left < rite every feature that passes a point test is also in the bucket range (:619-621)
         exact = false;
+        u32 pr[SC_REG_PAIRS];                                    // distinct pairs in registers (static indexing only)
+#pragma unroll
+        for (int i = 0; i < SC_REG_PAIRS; ++i) pr[i] = 0xFFFFFFFFu;
         const uint2 cellr = __ldg(tv.sv.cells + c);
         const int x[2] = {left, rite - 1};
-        for (int p = 0; p < 2 && !over; ++p) {
+        for (int p = 0; p < 2; ++p) {
             const int k = x[p] >> tv.sv.shift;
             if ((u32)k >= cellr.y) continue;
             if (p == 1 && x[1] == x[0]) continue;
@@ -526,24 +530,29 @@ __device__ void sc_count_fragment(const IndexView& iv, const ScTableView& tv, in
                 while (hit) {
                     const u32 low = hit & (0u - hit);
                     hit ^= low;
-                    const u32 slot = (low == HB0) ? sector_slot_c<0>(sct) : (low == HB1) ? sector_slot_c<1>(sct) : (low == HB2) ? sector_slot_c<2>(sct)
-                                     : (low == HB3) ? sector_slot_c<3>(sct) : sector_slot_c<4>(sct);
+                    const u32 word = (low & 0x80008000u) ? sct.w[6] : ((low & 0x40004000u) ? sct.w[7] : sct.w[5]);
+                    const u32 slot = (low & 0xFFFF2000u) ? (word >> 16) : (word & 0xFFFFu);
                     const u32 key = __ldg(tv.pair_key + slot);
                     bool found = false;
-                    for (u32 i = 0; i < np; ++i) found |= pairs[i] == key;
+#pragma unroll
+                    for (int i = 0; i < SC_REG_PAIRS; ++i) found |= pr[i] == key;
                     if (!found) {
-                        if (np < SC_MAX_PAIRS) {
-                            pairs[np++] = key;
-                            typemask |= 1u << __ldg(tv.pair_type + slot);
-                            missing |= (key & 7u) == 7u;
-                        } else over = true;
+#pragma unroll
+                        for (int i = 0; i < SC_REG_PAIRS; ++i) if ((u32)i == np) pr[i] = key;
+                        ++np;                                    // np > SC_REG_PAIRS: overflow
+                        typemask |= 1u << __ldg(tv.pair_type + slot);
+                        missing |= (key & 7u) == 7u;
                     }
                 }
                 if (!sector_more(sct) || r < sector_last_s(sct)) break;
                 sec = (sec == prim) ? __ldg(tv.sv.ovf_base + (prim >> 7)) + sector_link(sct) : sec + 1;
             }
         }
-        if (over) { exact = true; typemask = 0; np = 0; over = false; missing = false; }
+        if (np > SC_REG_PAIRS) { exact = true; typemask = 0; np = 0; missing = false; }
+        else {
+#pragma unroll
+            for (int i = 0; i < SC_REG_PAIRS; ++i) if ((u32)i < np) pairs[i] = pr[i];
+        }
     }
     if (exact) {
         sc_for_each_hit(iv, c, left, rite, [&](int64_t fi) {
