@@ -33,7 +33,11 @@ SC_CELL_PAD = 1000               # te_count.py:502  `maxcells+1000`
 
 
 def _open_alignment(filename):
-    import pysam                            # BAM decoding stays with pysam, as in the reference (te_count.py:11)
+    try:
+        import pysam                        # BAM decoding stays with pysam, as in the reference (te_count.py:11)
+    except ImportError:
+        from . import bam as _bam           # stand-in with the same interface for machines without pysam
+        return _bam.AlignmentFile(filename, 'r')
     return pysam.AlignmentFile(filename, 'r')
 
 

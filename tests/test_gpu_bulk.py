@@ -134,3 +134,29 @@ def test_misuse_errors(engine):
     with pytest.raises(_lib.TecError):
         e2.bulk_begin(False, 20)          # no index
     e2.close()
+
+
+@pytest.mark.parametrize("name", ["bulk_pe_rand_b", "bulk_se_rand_b"])
+def test_bulk_from_bam_file(monkeypatch, tmp_path, name):
+    """A real BAM file (independent writer) -> te_counter_b200/bam.py -> packing -> CUDA library ->
+    the reference's TSV bytes."""
+    import sys
+    import te_counter_b200
+    from bam_writer import write_bam
+    from oracle.ref_runner import CaptureLog
+    case = H.load_case(name)
+    recs = [dict(r, name=r.get("name", "r%d" % i)) for i, r in enumerate(case["records"])]
+    if any(r["end"] <= r["start"] and not r.get("flag", 0) & 4 for r in recs):
+        pytest.skip("case has zero-length alignments a file cannot carry")
+    path = str(tmp_path / "x.bam")
+    write_bam(path, recs)
+    monkeypatch.setitem(sys.modules, "pysam", None)
+    mte = te_counter_b200.measureTE("test", case["qual"], device=0)
+    mte.bind_genome(H.GOLD + "/" + case["glb"])
+    mte.load_genome()
+    log = CaptureLog()
+    res = (mte.parse_bampe if case["paired"] else mte.parse_bamse)(path, strand=False, log=log)
+    assert res == case["expected"]["result"]
+    out = tmp_path / "o.tsv"
+    mte.save_result_bulk(res, str(out), log=log)
+    assert out.read_text() == case["expected"]["tsv"]
