@@ -290,6 +290,7 @@ def run_ours(args):
     counts, st = eng.bulk_finish()
 
     # ---- end to end through the host-buffer ABI (pinned host arrays, H2D + D2H in the timed region)
+    parity_full = None
     e2e = None
     if not args.no_e2e:
         host = [eng.pinned(n_rec, dt) for dt in (np.int32, np.int32, np.uint16, np.uint8, np.uint8)]
@@ -320,6 +321,20 @@ def run_ours(args):
                "api": "tec_bulk_begin + tec_bulk_push(host SoA, pinned) + tec_bulk_finish"}
         if world == 1:
             assert (c2 == counts).all(), "e2e counts differ from the device-resident run"
+        # ---- full-size parity: the whole workload against the C restatement of the reference's loop
+        #      (oracle/te_oracle_c.c, the checker), all host cores
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from oracle import te_oracle_c
+            tc0 = time.perf_counter()
+            cidx = te_oracle_c.Index(idx.chrom_id, idx.L, idx.R, idx.ensg_id, idx.type_code, idx.n_chrom, idx.n_ensg,
+                                     idx.bucket_size)
+            fc, fs = te_oracle_c.bulk_count(cidx, paired, 20, *host)
+            tc1 = time.perf_counter()
+            full_ok = bool((fc == counts).all() and fs[:5].tolist() == [int(x) for x in st[:5]])
+            parity_full = {"records": int(n_rec), "bit_exact": full_ok, "seconds": tc1 - tc0, "threads": os.cpu_count(),
+                           "checker": "oracle/te_oracle_c.c (C restatement of te_count.py's bulk loop, pinned through "
+                                      "oracle/te_oracle.py and tests/golden)"}
+            assert full_ok, "full-size counts differ from the C oracle"
         del host
 
     # ---- CPU baseline + parity on a bounded prefix (rank 0, N = 1)
@@ -366,7 +381,7 @@ def run_ours(args):
                          "kernel": "bulk_count_cell_kernel<%s> (+ bulk_slow_kernel on flagged units)" % ("paired" if paired else "single"),
                          "cell_table_bytes": eng.get_info("stab_bytes"), "slow_units_per_launch": eng.get_info("last_slow_units"),
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_record": bpr},
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity, "parity_full": parity_full,
             "stats": {"units": int(st[0]), "assigned": int(st[1]), "lowq": int(st[2]), "badchrom": int(st[3]),
                       "qcfail": int(st[4]), "counts_sum": int(counts.sum())}}
     if rank == 0:

@@ -10,6 +10,10 @@ build container (oracle/ref_runner.py + oracle/make_golden.py -> tests/golden/*.
 the SURVEY.md Appendix-A known-answer vectors.  The reference ships no value-pinning tests of its
 own for this path, so those generated vectors are the pin.
 
+oracle/te_oracle_c.c is a C restatement of the bulk loop only (same literal algorithm, multi-threaded)
+used to check full-size results in seconds; tests/test_oracle_c.py checks it against this module and
+against the golden vectors.
+
 Everything follows the reference literally (10 kb bucket hash, Python sets/dicts, the held-line
 bundle scan), NOT the closed forms the CUDA kernels use, so that the two are independent.
 All citations are relative to /root/reference/.

@@ -30,7 +30,7 @@ struct IndexView {
     const int64_t* chrom_off;   // n_chrom + 1
     const u32* dir;
     const int64_t* dir_off;     // n_chrom + 1
-    const uint8_t* chrom_valid; // n_chrom: the chromosome is a key of genelist.buckets (it has a feature in some bucket)
+    const uint8_t* chrom_valid; // n_chrom: the chromosome is a key of genelist.buckets (it has a feature row)
     int n_chrom;
     int shift;
     int bs;                     // bucket size (10000)

@@ -179,11 +179,10 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
         }
         dir_off[(size_t)c + 1] = dir_off[(size_t)c] + ((int64_t)(maxL >> shift) + 2);
     }
-    // a chromosome is "in the index" iff it is a key of genelist.buckets: some feature of it falls in a bucket
+    // a chromosome is "in the index" iff it is a key of genelist.buckets; the key is created for every feature
+    // row, before its bucket range is looked at (miniglbase/genelist.py:367-368)
     std::vector<uint8_t> chrom_valid((size_t)std::max(n_chrom, 1), 0);
-    for (int c = 0; c < n_chrom; ++c)
-        for (int64_t i = chrom_off[c]; i < chrom_off[c + 1] && !chrom_valid[(size_t)c]; ++i)
-            if (floordiv(R[i] + bucket_size, bucket_size) > L[i] / bucket_size) chrom_valid[(size_t)c] = 1;
+    for (int c = 0; c < n_chrom; ++c) chrom_valid[(size_t)c] = chrom_off[c + 1] > chrom_off[c];
     const int64_t n_dir = dir_off[(size_t)n_chrom];
     ix.n_chrom = n_chrom; ix.n_feat = nf; ix.n_ensg = n_ensg; ix.bs = bucket_size; ix.shift = shift; ix.n_dir = n_dir;
     const size_t nfa = (size_t)std::max<int64_t>(nf, 1);
