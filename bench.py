@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="records of the CPU-baseline sample")
     ap.add_argument("--cpu-cores", type=int, default=0, help="reference arm: worker processes (0 = all)")
     ap.add_argument("--sorted", action="store_true", help="coordinate-sorted arrival order (bulk_se)")
+    ap.add_argument("--sc-parity-records", type=int, default=20_000_000,
+                    help="sc: records of the large parity check against the C++ oracle (0 = skip)")
     ap.add_argument("--opt", action="append", default=[], help="engine tuning knob key=value (tec_set_option)")
     return ap.parse_args()
 
@@ -540,6 +542,39 @@ def run_ours_sc(args, rank, world, local, dev):
                "sample": "first %d records of this workload; pure-Python restatement of sc_parse_bamse "
                          "(oracle/te_oracle.py), single thread as the reference; BAM decode and index load excluded" % ns}
 
+    # ---- large parity check: real 1e7-key bundles, against the C++ restatement (oracle/te_oracle_sc.cpp)
+    parity_full = None
+    if not args.no_cpu and world == 1 and args.sc_parity_records > 0:
+        from oracle import te_oracle_c
+        nb = min(n_rec, args.sc_parity_records)
+        big = [t[:nb].cpu().numpy() for t in cols]
+        big[2] = big[2].view(np.uint16)
+        big[5] = big[5].view(np.uint32)
+        big[6] = big[6].view(np.uint64)
+        big = [np.ascontiguousarray(a) for a in big]
+        eng.sc_begin(20, strand, n_wl)
+        for a0 in range(0, nb, 1 << 24):
+            eng.sc_push(min(nb, a0 + (1 << 24)) - a0, *[a[a0:a0 + (1 << 24)] for a in big])
+        a, b = eng.sc_finalize(bundle_keys, maxcells, pad)
+        g_ensg, g_cell, g_count, g_hc, g_hn, g_st = eng.sc_fetch(a, b)
+        ta = time.perf_counter()
+        out = te_oracle_c.sc_count((idx.chrom_id, idx.L, idx.R, idx.ensg_id, idx.type_code, idx.strand_code), idx.n_chrom,
+                                   idx.bucket_size, 20, strand, bundle_keys, maxcells, pad, *big)
+        tb = time.perf_counter()
+        o_ensg, o_cell, o_count = out["triples_arrays"]
+        ok = (len(o_ensg) == len(g_ensg) and (o_ensg == g_ensg).all() and (o_cell == g_cell).all() and (o_count == g_count).all()
+              and sorted(out["cell_hits"]) == list(zip(g_hc.tolist(), g_hn.tolist()))
+              and all(int(g_st[k]) == out["stats"][f] for k, f in (
+                  (_lib.SS_INVALID_BARCODE, "invalid_barcode"), (_lib.SS_ALREADY_SEEN, "already_seen"), (_lib.SS_LOWQ, "lowq"),
+                  (_lib.SS_QCFAIL, "qcfail"), (_lib.SS_VALID, "valid"), (_lib.SS_ASSIGNED, "assigned"),
+                  (_lib.SS_RAW_BARCODES, "raw_barcodes"), (_lib.SS_BUNDLES, "n_bundles"))))
+        parity_full = {"records": int(nb), "bundles": out["stats"]["n_bundles"], "triples": int(len(o_ensg)), "bit_exact": bool(ok),
+                       "seconds": tb - ta,
+                       "checker": "oracle/te_oracle_sc.cpp (C++ restatement of sc_parse_bamse, checked against "
+                                  "oracle/te_oracle.py and tests/golden)"}
+        assert ok, "single-cell result differs from the C++ oracle"
+        del big
+
     peak, peak_src = load_peaks()
     bpr = BYTES_PER_RECORD["sc"] + INDEX_BYTES_PER_FEATURE * idx.n_features / float(n_rec)
     achieved = n_rec * bpr / (ms_step / 1e3) / 1e9
@@ -556,7 +591,7 @@ def run_ours_sc(args, rank, world, local, dev):
                          "kernel": "whole sc step (radix sort passes dominate; see profiles/)", "kernel_ms": ms_step,
                          "sc_cell_table": bool(eng.get_info("has_sc_stab")), "sc_cell_table_bytes": eng.get_info("sc_stab_bytes"),
                          "algorithmic_bytes_per_record": bpr},
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity, "parity_full": parity_full,
             "stats": {"units": int(st[_lib.SS_UNITS]), "survivors": int(st[_lib.SS_SURVIVORS]),
                       "segments": int(st[_lib.SS_SEGMENTS]), "bundles": int(st[_lib.SS_BUNDLES]),
                       "valid": int(st[_lib.SS_VALID]), "assigned": int(st[_lib.SS_ASSIGNED]),

@@ -25,6 +25,16 @@ def load():
         lib.teo_index_free.argtypes = [vp]
         lib.teo_bulk_count.restype = ctypes.c_int
         lib.teo_bulk_count.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int]
+        lib.teo_sc_count.restype = vp
+        lib.teo_sc_count.argtypes = [ctypes.c_int64, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                     ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp]
+        lib.teo_sc_n_triples.restype = ctypes.c_int64
+        lib.teo_sc_n_triples.argtypes = [vp]
+        lib.teo_sc_n_hit.restype = ctypes.c_int64
+        lib.teo_sc_n_hit.argtypes = [vp]
+        lib.teo_sc_fetch.argtypes = [vp] * 7
+        lib.teo_sc_free.argtypes = [vp]
         _lib = lib
     return _lib
 
@@ -63,3 +73,26 @@ def bulk_count(idx, paired, qual, start, end, chrom, mapq, flag, threads=0):
     lib.teo_bulk_count(idx._h, 1 if paired else 0, int(qual), int(n), *[c.ctypes.data for c in cols],
                        counts.ctypes.data, stats.ctypes.data, int(threads or os.cpu_count() or 1))
     return counts, stats
+
+
+def sc_count(feat, n_chrom, bucket_size, qual, strand, bundle_keys, maxcells, pad, start, end, chrom, mapq, flag, cell, umi):
+    """C++ restatement of te_oracle.sc_count (oracle/te_oracle_sc.cpp).  feat = (chrom_id, L, R, ensg_id,
+    type_code, strand_code) in linearData order.  Returns the same dict as the Python oracle
+    (ReferenceCrash cases are reported in stats['crash_strand'] / stats['zero_division'])."""
+    lib = load()
+    f = [np.ascontiguousarray(a, dt) for a, dt in zip(feat, (np.int32, np.int32, np.int32, np.int32, np.uint8, np.uint8))]
+    cols = [np.ascontiguousarray(a, dt) for a, dt in zip((start, end, chrom, mapq, flag, cell, umi),
+                                                         (np.int32, np.int32, np.uint16, np.uint8, np.uint8, np.uint32, np.uint64))]
+    h = lib.teo_sc_count(len(f[1]), *[a.ctypes.data for a in f], int(n_chrom), int(bucket_size), int(qual), 1 if strand else 0,
+                         int(bundle_keys), int(maxcells), int(pad), len(cols[0]), *[c.ctypes.data for c in cols])
+    nt, nh = lib.teo_sc_n_triples(h), lib.teo_sc_n_hit(h)
+    ensg = np.zeros(nt, np.int32); tcell = np.zeros(nt, np.uint32); cnt = np.zeros(nt, np.int64)
+    hcell = np.zeros(nh, np.uint32); hcnt = np.zeros(nh, np.int64); st = np.zeros(12, np.int64)
+    lib.teo_sc_fetch(h, *[a.ctypes.data for a in (ensg, tcell, cnt, hcell, hcnt, st)])
+    lib.teo_sc_free(h)
+    keys = ("total_reads", "invalid_barcode", "already_seen", "lowq", "qcfail", "valid", "assigned", "raw_barcodes",
+            "n_bundles", "crash_strand", "zero_division")
+    return {"triples": {(int(e), int(c)): int(v) for e, c, v in zip(ensg, tcell, cnt)},
+            "triples_arrays": (ensg, tcell, cnt),
+            "cell_hits": list(zip(hcell.tolist(), hcnt.tolist())),
+            "stats": {k: int(st[i]) for i, k in enumerate(keys)}}
