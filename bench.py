@@ -334,6 +334,7 @@ def run_ours(args):
             tc1 = time.perf_counter()
             full_ok = bool((fc == counts).all() and fs[:5].tolist() == [int(x) for x in st[:5]])
             parity_full = {"records": int(n_rec), "bit_exact": full_ok, "seconds": tc1 - tc0, "threads": os.cpu_count(),
+                           "c_port_records_per_s": n_rec / (tc1 - tc0),
                            "checker": "oracle/te_oracle_c.c (C restatement of te_count.py's bulk loop, pinned through "
                                       "oracle/te_oracle.py and tests/golden)"}
             assert full_ok, "full-size counts differ from the C oracle"
