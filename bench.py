@@ -500,7 +500,7 @@ def run_ours_sc(args, rank, world, local, dev):
             eng.sc_begin(20, strand, n_wl)
             eng.sc_push(n_rec, *host)
             a, b = eng.sc_finalize(bundle_keys, maxcells, pad)
-            out = eng.sc_fetch(a, b)
+            out = eng.sc_fetch(a, b, pinned=True)
             return out, eng.sc_select(maxcells, b)
 
         e2e_step()

@@ -222,12 +222,31 @@ class Engine:
                                               ctypes.byref(nt), ctypes.byref(nh)))
         return nt.value, nh.value
 
-    def sc_fetch(self, n_triples, n_hit_cells):
-        ensg = np.zeros(n_triples, dtype=np.int32)
-        cell = np.zeros(n_triples, dtype=np.uint32)
-        count = np.zeros(n_triples, dtype=np.int64)
-        hcell = np.zeros(n_hit_cells, dtype=np.uint32)
-        hcount = np.zeros(n_hit_cells, dtype=np.int64)
+    def _result_buf(self, name, n, dtype):
+        """grow-only pinned result buffer (view valid until the next fetch that uses it)"""
+        buf = self._res.get(name)
+        if buf is None or len(buf) < n or buf.dtype != np.dtype(dtype):
+            buf = self.pinned(max(n + n // 4, 1024), dtype)
+            self._res[name] = buf
+        return buf[:n]
+
+    def sc_fetch(self, n_triples, n_hit_cells, pinned=False):
+        """(ensg, cell, count, hit_cell, hit_count, stats).  pinned=True: the arrays are views of reusable
+        page-locked buffers (fast device-to-host copies) that the next pinned fetch overwrites."""
+        if pinned:
+            if not hasattr(self, "_res"):
+                self._res = {}
+            ensg = self._result_buf("ensg", n_triples, np.int32)
+            cell = self._result_buf("cell", n_triples, np.uint32)
+            count = self._result_buf("count", n_triples, np.int64)
+            hcell = self._result_buf("hcell", n_hit_cells, np.uint32)
+            hcount = self._result_buf("hcount", n_hit_cells, np.int64)
+        else:
+            ensg = np.zeros(n_triples, dtype=np.int32)
+            cell = np.zeros(n_triples, dtype=np.uint32)
+            count = np.zeros(n_triples, dtype=np.int64)
+            hcell = np.zeros(n_hit_cells, dtype=np.uint32)
+            hcount = np.zeros(n_hit_cells, dtype=np.int64)
         stats = np.zeros(SC_NSTATS, dtype=np.int64)
         self._check(self._lib.tec_sc_fetch(self._h, ctypes.cast(ensg.ctypes.data, _c_i32p),
                                            ctypes.cast(cell.ctypes.data, _c_u32p),

@@ -38,7 +38,10 @@ struct ScState {
     u64* umi = nullptr;
     uint4* frag = nullptr;          // {cs = chrom << 2 | strand code (0 '+', 1 '-', 2 'NA'), left, rite, 0}: one 16-byte
                                     // record, so the gather into sorted order is one random read per survivor
-    int64_t n = 0, cap = 0;
+    int64_t n = 0, cap = 0;         // n is exact only after sc_sync_count()
+    u64* d_n = nullptr;             // survivors held (device): pushes do not wait for the host
+    int64_t n_bound = 0;            // upper bound of n (everything pushed so far), sizes the columns
+    bool n_pending = false;
     void* packed = nullptr;         // multi-GPU: survivors packed for the exchange (tec_sc_partition_dev)
     u64* gidx = nullptr;            // multi-GPU: position of each survivor in the whole job's survivor order
     int64_t gidx_cap = 0;
@@ -71,7 +74,7 @@ static void sc_free_results(tec_ctx* ctx, ScState* s) {
 
 inline void tec_ctx::free_sc() {
     if (!sc) return;
-    cudaFree(sc->cell); cudaFree(sc->umi); cudaFree(sc->frag); cudaFree(sc->gidx);
+    cudaFree(sc->cell); cudaFree(sc->umi); cudaFree(sc->frag); cudaFree(sc->gidx); cudaFree(sc->d_n);
     cudaFree(sc->d_stats); cudaFree(sc->pos); cudaFree(sc->cub_tmp);
     cache.put(sc->packed);
     sc_free_results(this, sc);
@@ -141,11 +144,12 @@ __global__ void sc_filter_kernel(int64_t n, int qual, const uint16_t* __restrict
 }
 
 // stable compaction of the survivors behind the ones already held (pos = exclusive scan of keep)
-__global__ void sc_scatter_kernel(int64_t n, int strand, int64_t base, const u32* __restrict__ keep_pos, const u32* __restrict__ keep_last,
+__global__ void sc_scatter_kernel(int64_t n, int strand, const u64* __restrict__ d_base, const u32* __restrict__ keep_pos, const u32* __restrict__ keep_last,
                                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                                   const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ flag,
                                   const u32* __restrict__ cell, const u64* __restrict__ umi,
                                   u32* __restrict__ o_cell, u64* __restrict__ o_umi, uint4* __restrict__ o_frag) {
+    const int64_t base = (int64_t)*d_base;
     SC_LOOP(r, n) {
         const u32 p = keep_pos[r];
         const u32 nxt = (r + 1 < n) ? keep_pos[r + 1] : *keep_last;
@@ -158,6 +162,9 @@ __global__ void sc_scatter_kernel(int64_t n, int strand, int64_t base, const u32
     }
 }
 
+__global__ void sc_advance_kernel(u64* __restrict__ d_n, const u32* __restrict__ total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *d_n += *total;
+}
 // keep_pos holds the EXCLUSIVE scan; total = scan[n-1] + keep[n-1] is written by this helper
 __global__ void sc_total_kernel(int64_t n, const u32* __restrict__ excl, const u32* __restrict__ keep_last_flag, u32* __restrict__ total) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *total = excl[n - 1] + *keep_last_flag;
@@ -720,7 +727,9 @@ extern "C" int tec_sc_begin(tec_ctx* ctx, int qual, int strand, int64_t n_whitel
     ScState* s = ctx->sc;
     sc_free_results(ctx, s);
     s->qual = qual; s->strand = strand ? 1 : 0; s->n_wl = n_whitelist;
-    s->n = 0; s->units = 0; s->active = true; s->finalized = false; s->has_gidx = false;
+    s->n = 0; s->n_bound = 0; s->n_pending = false; s->units = 0; s->active = true; s->finalized = false; s->has_gidx = false;
+    if (!s->d_n) TEC_CUDA(cudaMalloc(&s->d_n, 8));
+    TEC_CUDA(cudaMemsetAsync(s->d_n, 0, 8, ctx->stream));
     if (!s->d_stats) TEC_CUDA(cudaMalloc(&s->d_stats, TEC_SC_NSTATS * 8));
     TEC_CUDA(cudaMemsetAsync(s->d_stats, 0, TEC_SC_NSTATS * 8, ctx->stream));
     memset(s->stats, 0, sizeof(s->stats));
@@ -739,11 +748,23 @@ static cudaError_t sc_grow(T** p, int64_t old_n, int64_t new_cap, cudaStream_t s
     return e;
 }
 
+// the exact number of survivors (pushes only advance a device counter)
+static int sc_sync_count(tec_ctx* ctx) {
+    ScState* s = ctx->sc;
+    if (!s->n_pending) return TEC_OK;
+    u64 h = 0;
+    TEC_CUDA(cudaMemcpyAsync(&h, s->d_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->n = (int64_t)h;
+    s->n_pending = false;
+    return TEC_OK;
+}
+
 static int sc_ingest_dev(tec_ctx* ctx, int64_t n, const int32_t* start, const int32_t* end, const uint16_t* chrom,
                          const uint8_t* mapq, const uint8_t* flag, const u32* cell, const u64* umi) {
     ScState* s = ctx->sc;
     if (n >= (int64_t)0x7FFFFFFF) TEC_FAIL(TEC_ERR_LIMIT, "tec_sc_push: more than 2^31 records in one push");
-    if (s->n + n >= (int64_t)0xFFFFFFF0) TEC_FAIL(TEC_ERR_LIMIT, "single-cell path holds at most 2^32 surviving records");
+    if (s->n_bound + n >= (int64_t)0xFFFFFFF0) TEC_FAIL(TEC_ERR_LIMIT, "single-cell path holds at most 2^32 records per GPU");
     if (n + 1 > s->pos_cap) {
         TEC_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(s->pos);
@@ -765,23 +786,23 @@ static int sc_ingest_dev(tec_ctx* ctx, int64_t n, const int32_t* start, const in
     ctx->launches += 2;
     sc_total_kernel<<<1, 32, 0, ctx->stream>>>(n, keep, lastflag, total);
     ctx->launches++;
-    u32 h_total = 0;
-    TEC_CUDA(cudaMemcpyAsync(&h_total, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    TEC_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (s->n + h_total > s->cap) {
-        const int64_t cap = std::max<int64_t>(s->n + h_total, s->cap + s->cap / 2 + 1024);
+    // columns sized for everything pushed so far (an upper bound of the survivors): no host round trip per push
+    if (s->n_bound + n > s->cap) {
+        int rc2 = sc_sync_count(ctx);
+        if (rc2) return rc2;
+        const int64_t cap = std::max<int64_t>(s->n_bound + n, s->cap + s->cap / 2 + 1024);
         TEC_CUDA(sc_grow(&s->cell, s->n, cap, ctx->stream));
         TEC_CUDA(sc_grow(&s->umi, s->n, cap, ctx->stream));
         TEC_CUDA(sc_grow(&s->frag, s->n, cap, ctx->stream));
         s->cap = cap;
     }
-    if (h_total) {
-        sc_scatter_kernel<<<SC_GRID(n)>>>(n, s->strand, s->n, keep, total, start, end, chrom, flag, cell, umi,
-                                          s->cell, s->umi, s->frag);
-        ctx->launches++;
-    }
+    sc_scatter_kernel<<<SC_GRID(n)>>>(n, s->strand, s->d_n, keep, total, start, end, chrom, flag, cell, umi,
+                                      s->cell, s->umi, s->frag);
+    sc_advance_kernel<<<1, 32, 0, ctx->stream>>>(s->d_n, total);
+    ctx->launches += 2;
     TEC_CUDA(cudaGetLastError());
-    s->n += h_total;
+    s->n_bound += n;
+    s->n_pending = true;
     s->units += n;
     return TEC_OK;
 }
@@ -951,6 +972,9 @@ extern "C" int tec_sc_survivors(tec_ctx* ctx, int64_t* n) {
     if (!ctx) return TEC_ERR_ARG;
     ScState* s = ctx->sc;
     if (!s || !s->active) TEC_FAIL(TEC_ERR_STATE, "tec_sc_survivors: tec_sc_begin not called");
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    int rc = sc_sync_count(ctx);
+    if (rc) return rc;
     if (n) *n = s->n;
     return TEC_OK;
 }
@@ -965,6 +989,8 @@ extern "C" int tec_sc_partition_dev(tec_ctx* ctx, int world, int64_t gidx_base, 
     if (!s || !s->active) TEC_FAIL(TEC_ERR_STATE, "tec_sc_partition_dev: tec_sc_begin not called");
     if (world < 1 || world > SC_MAX_WORLD || !counts || !records) TEC_FAIL(TEC_ERR_ARG, "tec_sc_partition_dev: 1..8 ranks");
     TEC_CUDA(cudaSetDevice(ctx->device));
+    int rc0 = sc_sync_count(ctx);
+    if (rc0) return rc0;
     const int64_t N = s->n;
     const int n_warps = (int)std::max<int64_t>(1, std::min<int64_t>((N + 1023) / 1024, (int64_t)ctx->n_sm * 64));
     const int64_t per_warp = ((N + n_warps - 1) / n_warps + 31) / 32 * 32;
@@ -1016,6 +1042,9 @@ extern "C" int tec_sc_import_packed_dev(tec_ctx* ctx, int64_t n, const void* rec
     ctx->cache.put(s->packed);
     s->packed = nullptr;
     s->n = n;
+    s->n_bound = n;
+    s->n_pending = false;
+    TEC_CUDA(cudaMemcpy(s->d_n, &n, 8, cudaMemcpyHostToDevice));
     s->has_gidx = true;
     return TEC_OK;
 }
@@ -1064,6 +1093,8 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
     TEC_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     sc_free_results(ctx, s);
     ScArena A(ctx->cache);
+    int rc_n = sc_sync_count(ctx);
+    if (rc_n) return rc_n;
     const int64_t N = s->n, W = std::max<int64_t>(s->n_wl, 1);
     if (N >= (int64_t)0x7FFFFFF0) TEC_FAIL(TEC_ERR_LIMIT, "single-cell path: more than 2^31 surviving records on one GPU");
     int64_t n_b = 0;
