@@ -155,11 +155,6 @@ int tec_bulk_finish(tec_ctx* ctx, int64_t* counts, int64_t* stats);
  * The counters are in the library's internal order (the same on every rank for the same index);
  * tec_bulk_finish returns them in ensg-id order. */
 void* tec_bulk_counts_dev(tec_ctx* ctx);
-/* multi-GPU: peer-mapped addresses of every rank's counter block (this rank's own included).
- * When set, the tally kernel's flush adds its per-CTA partial counts directly into ALL ranks'
- * blocks over NVLink, so the merge is part of the kernel and no collective follows. */
-int tec_bulk_set_peers(tec_ctx* ctx, int n_peers, void* const* peer_counts);
-
 /* ---- single cell (sc_parse_bamse te_count.py:298-707, sc_save_result :709-754) ------------ */
 int tec_sc_begin(tec_ctx* ctx, int qual, int strand, int64_t n_whitelist);
 int tec_sc_push(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,

@@ -47,7 +47,6 @@ SIGNATURES = {
     "tec_bulk_push_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "tec_bulk_finish": (ctypes.c_int, [_vp, _c_i64p, _c_i64p]),
     "tec_bulk_counts_dev": (_vp, [_vp]),
-    "tec_bulk_set_peers": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_vp)]),
     "tec_sc_begin": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64]),
     "tec_sc_push": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tec_sc_push_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -199,10 +198,6 @@ class Engine:
 
     def bulk_counts_dev(self):
         return self._lib.tec_bulk_counts_dev(self._h)
-
-    def bulk_set_peers(self, ptrs):
-        arr = (_vp * len(ptrs))(*ptrs)
-        self._check(self._lib.tec_bulk_set_peers(self._h, len(ptrs), arr))
 
     # -- single cell
     def sc_begin(self, qual, strand, n_whitelist):

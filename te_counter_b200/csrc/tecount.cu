@@ -490,9 +490,3 @@ extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
     if (k == "stab_entries") return ctx->idx.st_entries;
     return -1;
 }
-
-extern "C" int tec_bulk_set_peers(tec_ctx* ctx, int n_peers, void* const* peer_counts) {
-    if (!ctx) return TEC_ERR_ARG;
-    (void)n_peers; (void)peer_counts;
-    TEC_FAIL(TEC_ERR_UNIMPLEMENTED, "tec_bulk_set_peers: not implemented yet");
-}
