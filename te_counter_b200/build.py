@@ -1,4 +1,5 @@
-"""Build recipe for libtecount.so (hand-written CUDA, sm_100a only, in-tree)."""
+"""Build recipes, in-tree: libtecount.so (hand-written CUDA, sm_100a only) and libtecbam.so (host BAM
+decoder, C++ / zlib / threads, no CUDA)."""
 import os
 import subprocess
 import sys
@@ -6,7 +7,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("TEC_LIB") or os.path.join(HERE, "libtecount.so")
+BAM_LIB = os.environ.get("TEC_BAM_LIB") or os.path.join(HERE, "libtecbam.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+CXX = os.environ.get("CXX", "g++")
 
 
 def sources():
@@ -39,5 +42,18 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_bam(force=False):
+    src = [os.path.join(CSRC, "bamdecode.cpp"), os.path.join(os.path.dirname(HERE), "include", "tecbam.h")]
+    if not force and os.path.exists(BAM_LIB) and all(os.path.getmtime(s) <= os.path.getmtime(BAM_LIB) for s in src):
+        return BAM_LIB
+    cmd = [CXX, "-O3", "-std=c++17", "-Wall", "-fPIC", "-shared", "-pthread", "-o", BAM_LIB, src[0], "-lz"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building libtecbam.so")
+    return BAM_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_bam(force="--force" in sys.argv))

@@ -24,6 +24,7 @@ from operator import itemgetter
 import numpy as np
 
 from . import _lib
+from . import fastbam as _fastbam
 from . import index as _index
 from . import reads as _reads
 
@@ -33,12 +34,28 @@ SC_CELL_PAD = 1000               # te_count.py:502  `maxcells+1000`
 
 
 def _open_alignment(filename):
-    try:
-        import pysam                        # BAM decoding stays with pysam, as in the reference (te_count.py:11)
-    except ImportError:
-        from . import bam as _bam           # stand-in with the same interface for machines without pysam
-        return _bam.AlignmentFile(filename, 'r')
-    return pysam.AlignmentFile(filename, 'r')
+    """TEC_BAM_DECODER = auto (default) | native | pysam | python.  `auto`: block-compressed BAM goes
+    through libtecbam (threads inflate and parse into the pinned batch, fastbam.py) when it is
+    built; anything else through pysam as in the reference (te_count.py:11, :65), or through the
+    pure-Python stand-in with pysam's interface (bam.py) where pysam is not installed."""
+    mode = os.environ.get('TEC_BAM_DECODER', 'auto')
+    if mode not in ('auto', 'native', 'pysam', 'python'):
+        raise ValueError('TEC_BAM_DECODER must be auto, native, pysam or python')
+    if mode == 'native' or (mode == 'auto' and _fastbam.available()):
+        try:
+            return _fastbam.NativeBam(filename)
+        except (_fastbam.NotBgzf, OSError):             # SAM text, plain gzip, not a regular file: next reader
+            if mode == 'native':
+                raise
+    if mode != 'python':
+        try:
+            import pysam
+            return pysam.AlignmentFile(filename, 'r')
+        except ImportError:
+            if mode == 'pysam':
+                raise
+    from . import bam as _bam
+    return _bam.AlignmentFile(filename, 'r')
 
 
 class ScResult(Mapping):
@@ -131,12 +148,15 @@ class measureTE:
         eng = self._engine()
         cm = _reads.ChromMap(self.genome.chrom_keys)
         sam = _open_alignment(filename)
+        native = isinstance(sam, _fastbam.NativeBam)
+        if native:
+            sam.bind(cm)
         batch = _reads.Batch(BATCH_RECORDS, alloc=eng.pinned)
         eng.bulk_begin(paired, qual)
         more, done, next_log = True, 0, 1000000
         label = 'reads' if paired else 'SE reads'
         while more:
-            more = _reads.fill_bulk(batch, sam, cm, paired, qual)
+            more = sam.fill_bulk(batch, paired, qual) if native else _reads.fill_bulk(batch, sam, cm, paired, qual)
             eng.bulk_push(batch.n, batch.start, batch.end, batch.chrom, batch.mapq, batch.flag)
             done += batch.n // 2 if paired else batch.n
             while done >= next_log:
@@ -204,12 +224,15 @@ class measureTE:
         eng = self._engine()
         cm = _reads.ChromMap(self.genome.chrom_keys)
         sam = _open_alignment(filename)
+        native = isinstance(sam, _fastbam.NativeBam)
+        if native:
+            sam.bind(cm, whitelist)
         batch = _reads.Batch(BATCH_RECORDS, sc=True, alloc=eng.pinned)
         eng.sc_begin(qual, strand, len(whitelist))
         log.info('Part 1: Collapsing UMI/CB combinations')
         more, done, next_log = True, 0, 10000000
         while more:
-            more = _reads.fill_sc(batch, sam, cm, whitelist, qual)
+            more = sam.fill_sc(batch, qual) if native else _reads.fill_sc(batch, sam, cm, whitelist, qual)
             eng.sc_push(batch.n, batch.start, batch.end, batch.chrom, batch.mapq, batch.flag,
                         batch.cell, batch.umi)
             done += batch.n

@@ -50,6 +50,7 @@ def test_reader_roundtrip(tmp_path, fmt):
 
 def _mte(monkeypatch, case, path):
     monkeypatch.setitem(sys.modules, "pysam", None)          # `import pysam` raises ImportError -> bam.py
+    monkeypatch.setenv("TEC_BAM_DECODER", "python")          # (the native decoder has tests/test_fastbam.py)
     mte = te_counter_b200.measureTE("test", case["qual"])
     mte.bind_genome(H.GOLD + "/" + case["glb"])
     monkeypatch.setattr(mte, "_engine_obj", OracleEngine(0))
