@@ -199,6 +199,21 @@ int tec_sc_import_packed_dev(tec_ctx* ctx, int64_t n, const void* records);
  * ascending id, at most maxcells.  cells_out must hold min(maxcells, n_hit_cells) entries. */
 int tec_sc_select(tec_ctx* ctx, int64_t maxcells, uint32_t* cells_out, int64_t* n_out);
 
+/*
+ * Dense matrix rows of sc_save_result as text (te_count.py:744-754), built on the device: for each of
+ * the n_rows cells, in the order given (normally tec_sc_select's), one line
+ *     <barcode> '\t' <count of ensg 0> '\t' <count of ensg 1> ... '\n'
+ * with every ensg of the index in id (= sorted name) order, zeros included, decimal integers.
+ * cells[r] = whitelist id of row r (each at most once); barcodes = the rows' barcode strings
+ * concatenated, row r is bytes [bc_off[r], bc_off[r+1]).  *n_bytes = length of the text, which stays
+ * in device memory until the next tec_sc_matrix_text / tec_sc_begin; tec_sc_matrix_read copies the
+ * byte range [offset, offset + n) of it into host memory (stream it to the file in chunks).
+ * The header line (te_count.py:745) is the caller's: it is made of the feature names.
+ */
+int tec_sc_matrix_text(tec_ctx *ctx, int64_t n_rows, const uint32_t *cells, const char *barcodes,
+                       const int64_t *bc_off, int64_t *n_bytes);
+int tec_sc_matrix_read(tec_ctx *ctx, int64_t offset, int64_t n, char *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,8 @@ SIGNATURES = {
     "tec_sc_finalize": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_i64p, _c_i64p]),
     "tec_sc_fetch": (ctypes.c_int, [_vp, _c_i32p, _c_u32p, _c_i64p, _c_u32p, _c_i64p, _c_i64p]),
     "tec_sc_select": (ctypes.c_int, [_vp, ctypes.c_int64, _c_u32p, _c_i64p]),
+    "tec_sc_matrix_text": (ctypes.c_int, [_vp, ctypes.c_int64, _c_u32p, ctypes.c_char_p, _c_i64p, _c_i64p]),
+    "tec_sc_matrix_read": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp]),
     "tec_sc_set_collective": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int]),
     "tec_sc_survivors": (ctypes.c_int, [_vp, _c_i64p]),
     "tec_sc_partition_dev": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, _c_i64p, ctypes.POINTER(_vp)]),
@@ -292,3 +294,29 @@ class Engine:
         self._check(self._lib.tec_sc_select(self._h, int(maxcells), ctypes.cast(out.ctypes.data, _c_u32p),
                                             ctypes.byref(n)))
         return out[:n.value]
+
+    def sc_matrix_text(self, cells, barcodes):
+        """Builds sc_save_result's dense rows (te_count.py:744-754) as text on the device for the
+        given whitelist ids / barcode strings; returns the number of bytes."""
+        cells = np.ascontiguousarray(cells, dtype=np.uint32)
+        enc = [b.encode("utf-8") for b in barcodes]
+        assert len(enc) == len(cells)
+        off = np.zeros(len(enc) + 1, dtype=np.int64)
+        if enc:
+            np.cumsum([len(b) for b in enc], out=off[1:])
+        n = ctypes.c_int64(0)
+        self._check(self._lib.tec_sc_matrix_text(self._h, len(cells), ctypes.cast(cells.ctypes.data, _c_u32p), b"".join(enc),
+                                                 ctypes.cast(off.ctypes.data, _c_i64p), ctypes.byref(n)))
+        return n.value
+
+    def sc_matrix_write(self, fh, n_bytes, chunk=1 << 26):
+        """Streams the text built by sc_matrix_text into the binary file object `fh`."""
+        if getattr(self, "_text_buf", None) is None or len(self._text_buf) < min(chunk, max(1, n_bytes)):
+            self._text_buf = self.pinned(min(chunk, max(1, n_bytes)), np.uint8)
+        buf = self._text_buf
+        done = 0
+        while done < n_bytes:
+            k = min(len(buf), n_bytes - done)
+            self._check(self._lib.tec_sc_matrix_read(self._h, done, k, buf.ctypes.data))
+            fh.write(memoryview(buf)[:k])
+            done += k

@@ -63,13 +63,16 @@ struct ScState {
     u32* h_cell = nullptr;          // hit cells ascending
     int64_t* h_count = nullptr;
     int64_t n_hit = 0;
+    char* text = nullptr;           // dense matrix rows as text (sc_text.cuh)
+    int64_t text_bytes = 0;
     int64_t stats[TEC_SC_NSTATS] = {0};
 };
 
 static void sc_free_results(tec_ctx* ctx, ScState* s) {
     ctx->cache.put(s->t_ensg); ctx->cache.put(s->t_cell); ctx->cache.put(s->t_count); ctx->cache.put(s->h_cell); ctx->cache.put(s->h_count);
-    s->t_ensg = nullptr; s->t_cell = nullptr; s->t_count = nullptr; s->h_cell = nullptr; s->h_count = nullptr;
-    s->n_triples = s->n_hit = 0;
+    ctx->cache.put(s->text);
+    s->t_ensg = nullptr; s->t_cell = nullptr; s->t_count = nullptr; s->h_cell = nullptr; s->h_count = nullptr; s->text = nullptr;
+    s->n_triples = s->n_hit = s->text_bytes = 0;
 }
 
 inline void tec_ctx::free_sc() {

@@ -4,6 +4,7 @@
 #include "stab_build.h"
 #include "context.cuh"
 #include "sc.cuh"
+#include "sc_text.cuh"
 
 #include <algorithm>
 #include <cstdio>

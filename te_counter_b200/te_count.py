@@ -272,6 +272,7 @@ class measureTE:
         log.info('Densifying and saving "{0}"'.format(out_filename))
         log.info('Found {0:,} barcodes'.format(len(self.barcodes)))
 
+        sel = None
         if isinstance(result, ScResult) and self._engine_obj is not None and getattr(self, '_sc_hit', None) is not None:
             # top-maxcells on the device: count descending, ties by ascending whitelist id
             sel = self._engine_obj.sc_select(maxcells, len(self._sc_hit[0]))
@@ -294,7 +295,13 @@ class measureTE:
 
         with open(out_filename, 'w') as oh:
             oh.write('{}\t{}\n'.format('name', '\t'.join(result.keys())))
-            if isinstance(result, ScResult):
+            if sel is not None and hasattr(self._engine_obj, 'sc_matrix_text'):
+                # the rows are formatted on the device (libtecount tec_sc_matrix_text) and streamed out
+                oh.flush()
+                n_bytes = self._engine_obj.sc_matrix_text(sel, barcodes_to_do)
+                with open(out_filename, 'ab') as ob:
+                    self._engine_obj.sc_matrix_write(ob, n_bytes)
+            elif isinstance(result, ScResult):
                 _write_dense_rows(oh, result, barcodes_to_do)
             else:
                 for barcode in barcodes_to_do:

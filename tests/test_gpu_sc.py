@@ -167,3 +167,69 @@ def test_sc_umi_key_packing(engine):
     # order check of the packing itself: 3-bit codes and their string order agree with the 2-bit keys
     us = sorted("".join(rng.choice(list("ACGT"), size=8)) for _ in range(200))
     assert [encode_umi(u) for u in us] == sorted(encode_umi(u) for u in us)
+
+
+def _text_from_triples(n_ensg, ensg, cell, count, cells, barcodes):
+    """te_count.py:752-754 restated on the triples: '\\t'.join([barcode] + [str(count or 0) ...])."""
+    m = {(int(e), int(c)): int(v) for e, c, v in zip(ensg, cell, count)}
+    return "".join("\t".join([b] + [str(m.get((e, c), 0)) for e in range(n_ensg)]) + "\n"
+                   for c, b in zip(cells, barcodes)).encode()
+
+
+def _matrix_text(engine, cells, barcodes):
+    import io
+    n = engine.sc_matrix_text(cells, barcodes)
+    out = io.BytesIO()
+    engine.sc_matrix_write(out, n, chunk=4096 + 7)            # several chunks, odd size
+    assert out.tell() == n
+    return out.getvalue()
+
+
+def test_sc_matrix_text_rows(engine):
+    """tec_sc_matrix_text against the reference's row formatting: zeros between entries, counts of
+    1 to 5 digits, rows without any entry, barcodes of different lengths, any row order/subset."""
+    idx = synth.synth_index(3, n_te=3000, n_exon=800, n_gene=60, chrom_len=300_000, n_chrom=2)
+    engine.upload_index(idx)
+    n_wl = 40
+    rng = np.random.default_rng(5)
+    r = synth.synth_sc_reads(6, idx, 30000, n_whitelist=n_wl, n_cells=12, umis_per_cell=300)
+    # one cell with 12,345 UMIs on one feature -> a 5-digit count; another with 150
+    f = int(np.argmax(idx.R - idx.L))
+    extra = {k: [] for k in COLS}
+    for cellid, n_umi in ((3, 12346), (7, 151)):
+        u = np.arange(n_umi, dtype=np.uint64)
+        code = np.zeros(n_umi, dtype=np.uint64)
+        for k in range(8):                                  # 8-character UMIs over A,C,G,T,N in base 5
+            code = (code << np.uint64(3)) | ((u // np.uint64(5 ** (7 - k))) % np.uint64(5) + np.uint64(1))
+        code <<= np.uint64(3 * (21 - 8))
+        extra["start"].append(np.full(n_umi, idx.L[f] + 5, np.int32))
+        extra["end"].append(np.full(n_umi, idx.L[f] + 6, np.int32))
+        extra["chrom"].append(np.full(n_umi, idx.chrom_id[f], np.uint16))
+        extra["mapq"].append(np.full(n_umi, 60, np.uint8))
+        extra["flag"].append(np.zeros(n_umi, np.uint8))
+        extra["cell"].append(np.full(n_umi, cellid, np.uint32))
+        extra["umi"].append(code)
+    r = {k: np.concatenate([np.asarray(r[k])] + extra[k]).astype(np.asarray(r[k]).dtype) for k in COLS}
+    ensg, cell, count, hcell, hcount, st, sel = run_engine(engine, r, 20, False, n_wl, 10 ** 7, 30, 1000)
+    assert count.max() >= 10000 and len(sel) >= 5
+    names = ["BC%d" % i + "-1" * (i % 3) for i in range(n_wl)]
+    names[int(sel[1])] = ""                                  # an empty barcode string is a legal whitelist line
+    for cells in (sel.tolist(), sel.tolist()[::-1][:4], [int(sel[0])],
+                  sel.tolist()[:3] + [c for c in range(n_wl) if c not in set(hcell.tolist())][:2]):   # rows with no entry
+        got = _matrix_text(engine, cells, [names[c] for c in cells])
+        assert got == _text_from_triples(idx.n_ensg, ensg, cell, count, cells, [names[c] for c in cells])
+    assert engine.sc_matrix_text([], []) == 0
+    with pytest.raises(Exception):
+        engine.sc_matrix_text([0, 0], ["a", "b"])            # the same cell twice
+    with pytest.raises(Exception):
+        engine.sc_matrix_text([n_wl], ["a"])                 # outside the whitelist
+
+
+def test_sc_matrix_text_without_triples(engine):
+    idx = synth.synth_index(3, n_te=3000, n_exon=800, n_gene=60, chrom_len=300_000, n_chrom=2)
+    engine.upload_index(idx)
+    engine.sc_begin(20, False, 5)
+    nt, nh = engine.sc_finalize(10 ** 7, 3, 1000)
+    assert nt == 0
+    got = _matrix_text(engine, [4, 1], ["x", "yy"])
+    assert got == ("x" + "\t0" * idx.n_ensg + "\nyy" + "\t0" * idx.n_ensg + "\n").encode()

@@ -122,6 +122,12 @@ def records_bytes(rng, n, contigs, mode, barcodes, first_id):
     return m
 
 
+def _chunk(job):
+    seed, i, n, mode, barcodes = job
+    rng = np.random.default_rng([seed, i])
+    return _deflate_chunk(records_bytes(rng, n, HG38, mode, barcodes, i * 250000).tobytes())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("out")
@@ -141,25 +147,11 @@ def main():
             with open(a.whitelist, "w") as fh:
                 fh.write("".join(bytes(b).decode() + "-1\n" for b in barcodes))
     chunk = 250000
+    jobs = [(a.seed, i, min(chunk, a.records - i * chunk), a.mode, barcodes) for i in range((a.records + chunk - 1) // chunk)]
     with open(a.out, "wb") as fh, ProcessPoolExecutor(a.procs) as ex:
-        carry = header_bytes(HG38)
-        done = 0
-        while done < a.records:
-            parts = []
-            for _ in range(a.procs):
-                if done >= a.records:
-                    break
-                n = min(chunk, a.records - done)
-                n -= n & 1 if a.mode == "pe" and n > 1 else 0
-                raw = carry + records_bytes(rng, n, HG38, a.mode, barcodes, done).tobytes()
-                cut = len(raw) - len(raw) % BLOCK if done + n < a.records else len(raw)
-                parts.append(raw[:cut])
-                carry = raw[cut:]
-                done += n
-            for comp in ex.map(_deflate_chunk, parts):
-                fh.write(comp)
-        if carry:
-            fh.write(_bgzf(carry))
+        fh.write(_bgzf(header_bytes(HG38)))
+        for comp in ex.map(_chunk, jobs):                   # records straddle blocks inside a chunk
+            fh.write(comp)
         fh.write(_bgzf(b""))
     print(a.out, os.path.getsize(a.out), "bytes,", a.records, "records")
 
