@@ -101,6 +101,12 @@ int tbam_next_sc(tbam_reader *r, int qual, int64_t capacity,
  * 2 uncompressed bytes produced, 3 worker threads, 4 nanoseconds spent inside tbam_next_*. */
 int64_t tbam_counter(const tbam_reader *r, int what);
 
+/* One raw-deflate stream (the payload of a BGZF block) into exactly n_out bytes.  engine 0: zlib;
+ * engine 1: the decoder's own table-driven inflate only (bamdecode.cpp uses it first and falls back
+ * to zlib whenever it declines).  Returns 0, or TBAM_E_FORMAT when the engine rejects the stream.
+ * Exposed so that the two can be held against each other (tests/test_fast_inflate.py). */
+int tbam_inflate_raw(const void *in, int64_t n_in, void *out, int64_t n_out, int engine);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@
 // Field semantics follow te_counter_b200/reads.py + bam.py (the Python packing this replaces),
 // which in turn cite the reference's read loops; see the header for file:line.
 #include "../../include/tecbam.h"
+#include "fast_inflate.h"
 
 #include <zlib.h>
 
@@ -175,6 +176,7 @@ struct tbam_reader {
     std::vector<uint8_t> win;                   // uncompressed window; [w_beg, w_end) is unread
     size_t w_beg = 0, w_end = 0;
     size_t window = WINDOW_BYTES;
+    bool use_fast_inflate = true;               // TEC_BAM_INFLATE=zlib turns the table-driven decoder off
     std::vector<Block> blocks;
     std::vector<uint32_t> rec_off;              // starts of the complete records of the window
     size_t rec_cur = 0;                         // first one not handed out yet
@@ -200,6 +202,28 @@ namespace {
 int fail(tbam_reader *r, int status, const std::string &msg) {
     r->err = msg;
     return status;
+}
+
+// One BGZF block: the table-driven decoder of fast_inflate.h first; zlib decides whenever that one
+// declines (it returns false on anything unusual), then the CRC32 of the trailer.
+bool zlib_inflate(const uint8_t *in, uint32_t in_n, uint8_t *out, uint32_t out_n) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<Bytef *>(in);
+    zs.avail_in = in_n;
+    zs.next_out = out;
+    zs.avail_out = out_n;
+    int rc = inflate(&zs, Z_FINISH);
+    bool ok = rc == Z_STREAM_END && zs.avail_out == 0;
+    inflateEnd(&zs);
+    return ok;
+}
+
+bool inflate_block(const Block &b, uint8_t *out, bool fast) {
+    static thread_local fast_inflate::Inflater inf;
+    if (!(fast && inf.run(b.cdata, b.clen, out, b.isize)) && !zlib_inflate(b.cdata, b.clen, out, b.isize)) return false;
+    return uint32_t(crc32(crc32(0L, Z_NULL, 0), out, b.isize)) == b.crc;
 }
 
 // Lists the starts of the complete records in [from, w_end) by hopping over block_size fields.
@@ -274,21 +298,8 @@ int refill(tbam_reader *r, bool list) {
     std::vector<std::vector<uint32_t>> found(list ? size_t(n_tasks) : 0);
     r->pool->run(n_tasks, [&](int t) {
         size_t lo = size_t(t) * per, hi = std::min(bl.size(), lo + per);
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        bool ok = inflateInit2(&zs, -15) == Z_OK;
-        for (size_t i = lo; ok && i < hi; i++) {
-            const Block &b = bl[i];
-            zs.next_in = const_cast<Bytef *>(b.cdata);
-            zs.avail_in = b.clen;
-            zs.next_out = base + b.out;
-            zs.avail_out = b.isize;
-            int rc = inflate(&zs, Z_FINISH);
-            ok = rc == Z_STREAM_END && zs.avail_out == 0 &&
-                 uint32_t(crc32(crc32(0L, Z_NULL, 0), base + b.out, b.isize)) == b.crc;
-            inflateReset(&zs);
-        }
-        inflateEnd(&zs);
+        bool ok = true;
+        for (size_t i = lo; ok && i < hi; i++) ok = inflate_block(bl[i], base + bl[i].out, r->use_fast_inflate);
         if (!ok) bad.store(1);
         if (!list) return;
         int64_t from;
@@ -699,6 +710,7 @@ int tbam_open(const char *path, int n_threads, tbam_reader **out) {
         if (n_threads > 64) n_threads = 64;
     }
     r->pool = new Pool(n_threads);
+    if (const char *z = getenv("TEC_BAM_INFLATE")) r->use_fast_inflate = strcmp(z, "zlib") != 0;
     if (const char *w = getenv("TEC_BAM_WINDOW")) {
         long long v = atoll(w);
         if (v > 0) r->window = size_t(v);
@@ -754,6 +766,21 @@ int tbam_next_sc(tbam_reader *r, int qual, int64_t capacity, int32_t *start, int
                  uint8_t *mapq, uint8_t *flag, uint32_t *cell, uint64_t *umi, int64_t *n_out, int *more) {
     Out o{start, end, chrom, mapq, flag, cell, umi};
     return next_batch(r, MODE_SC, qual, capacity, o, n_out, more);
+}
+
+int tbam_inflate_raw(const void *in, int64_t n_in, void *out, int64_t n_out, int engine) {
+    if (n_in < 0 || n_out < 0 || n_in > (int64_t(1) << 31) || n_out > (int64_t(1) << 31) || (n_in && !in) || (n_out && !out)) return TBAM_E_ARG;
+    uint8_t dummy = 0;
+    const uint8_t *i = in ? (const uint8_t *)in : &dummy;
+    uint8_t *o = out ? (uint8_t *)out : &dummy;
+    bool ok;
+    if (engine == 1) {
+        static thread_local fast_inflate::Inflater inf;
+        ok = inf.run(i, size_t(n_in), o, size_t(n_out));
+    } else {
+        ok = zlib_inflate(i, uint32_t(n_in), o, uint32_t(n_out));
+    }
+    return ok ? TBAM_OK : TBAM_E_FORMAT;
 }
 
 int64_t tbam_counter(const tbam_reader *r, int what) {

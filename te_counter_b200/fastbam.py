@@ -35,6 +35,7 @@ SIGNATURES = {
     "tbam_next_bulk": (_int, [_vp, _int, _int, _i64] + [_vp] * 5 + [ctypes.POINTER(_i64), ctypes.POINTER(_int)]),
     "tbam_next_sc": (_int, [_vp, _int, _i64] + [_vp] * 7 + [ctypes.POINTER(_i64), ctypes.POINTER(_int)]),
     "tbam_counter": (_i64, [_vp, _int]),
+    "tbam_inflate_raw": (_int, [ctypes.c_char_p, _i64, _vp, _i64, _int]),
 }
 
 _lib = None
