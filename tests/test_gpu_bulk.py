@@ -136,10 +136,11 @@ def test_misuse_errors(engine):
     e2.close()
 
 
+@pytest.mark.parametrize("decoder", ["native", "python"])
 @pytest.mark.parametrize("name", ["bulk_pe_rand_b", "bulk_se_rand_b"])
-def test_bulk_from_bam_file(monkeypatch, tmp_path, name):
-    """A real BAM file (independent writer) -> te_counter_b200/bam.py -> packing -> CUDA library ->
-    the reference's TSV bytes."""
+def test_bulk_from_bam_file(monkeypatch, tmp_path, name, decoder):
+    """A real BAM file (independent writer) -> libtecbam (native) or te_counter_b200/bam.py + reads.py
+    (python) -> pinned batches -> CUDA library -> the reference's TSV bytes."""
     import sys
     import te_counter_b200
     from bam_writer import write_bam
@@ -151,6 +152,7 @@ def test_bulk_from_bam_file(monkeypatch, tmp_path, name):
     path = str(tmp_path / "x.bam")
     write_bam(path, recs)
     monkeypatch.setitem(sys.modules, "pysam", None)
+    monkeypatch.setenv("TEC_BAM_DECODER", decoder)
     mte = te_counter_b200.measureTE("test", case["qual"], device=0)
     mte.bind_genome(H.GOLD + "/" + case["glb"])
     mte.load_genome()

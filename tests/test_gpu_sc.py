@@ -233,3 +233,29 @@ def test_sc_matrix_text_without_triples(engine):
     assert nt == 0
     got = _matrix_text(engine, [4, 1], ["x", "yy"])
     assert got == ("x" + "\t0" * idx.n_ensg + "\nyy" + "\t0" * idx.n_ensg + "\n").encode()
+
+
+@pytest.mark.parametrize("name", ["sc_rand_det_strand", "sc_rand_amb_bundles"])
+def test_sc_from_bam_file(monkeypatch, tmp_path, name):
+    """BAM file -> libtecbam -> pinned batches -> CUDA single-cell path -> matrix rows formatted on
+    the device -> the reference's TSV bytes."""
+    import sys
+    import te_counter_b200
+    from bam_writer import write_bam
+    from oracle.ref_runner import CaptureLog
+    case = H.load_case(name)
+    path = str(tmp_path / "x.bam")
+    write_bam(path, [dict(r, name=r.get("name", "r%d" % i)) for i, r in enumerate(case["records"])])
+    wl = tmp_path / "wl.txt"
+    wl.write_text("".join(w + "\n" for w in case["whitelist"]))
+    monkeypatch.setitem(sys.modules, "pysam", None)
+    monkeypatch.setenv("TEC_BAM_DECODER", "native")
+    mte = te_counter_b200.measureTE("test", case["qual"], device=0)
+    mte.bind_genome(H.GOLD + "/" + case["glb"])
+    log = CaptureLog()
+    res = mte.sc_parse_bamse(path, UMIS=True, whitelistfilename=str(wl), strand=case["strand"], log=log, label="l",
+                             maxcells=case["maxcells"], _bundle_keys=case["bundle_keys"], _pad=case["pad"])
+    assert {k: v for k, v in dict(res).items() if v} == case["expected"]["result"]
+    out = tmp_path / "o.tsv"
+    mte.sc_save_result(res, str(out), maxcells=case["maxcells"], log=log)
+    assert out.read_text() == case["expected"]["tsv"]
