@@ -481,6 +481,17 @@ def run_ours_sc(args, rank, world, local, dev):
         ms_step = float(t.item())
     value = n_rec * world / (ms_step / 1e3)
     ensg, cell, count, hcell, hcount, st = eng.sc_fetch(nt, nh)
+    # dense matrix rows of sc_save_result formatted on the device (te_count.py:744-754): size and rate
+    matrix_text = None
+    if world == 1 and len(sel):
+        bcs = ["%016d-1" % int(c) for c in sel.tolist()]
+        eng.sc_matrix_text(sel, bcs)                                    # warm (allocations)
+        ta = time.perf_counter()
+        n_text = eng.sc_matrix_text(sel, bcs)
+        tb = time.perf_counter()
+        matrix_text = {"rows": int(len(sel)), "columns": int(idx.n_ensg), "bytes": int(n_text), "ms": (tb - ta) * 1e3,
+                       "GBps_written": n_text / (tb - ta) / 1e9,
+                       "what": "tec_sc_matrix_text, wall clock around the call (sort of the triples by row + text kernel)"}
     if world > 1:
         args.no_e2e = args.no_cpu = True
 
@@ -593,6 +604,7 @@ def run_ours_sc(args, rank, world, local, dev):
                          "sc_cell_table": bool(eng.get_info("has_sc_stab")), "sc_cell_table_bytes": eng.get_info("sc_stab_bytes"),
                          "algorithmic_bytes_per_record": bpr},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity, "parity_full": parity_full,
+            "matrix_text": matrix_text,
             "stats": {"units": int(st[_lib.SS_UNITS]), "survivors": int(st[_lib.SS_SURVIVORS]),
                       "segments": int(st[_lib.SS_SEGMENTS]), "bundles": int(st[_lib.SS_BUNDLES]),
                       "valid": int(st[_lib.SS_VALID]), "assigned": int(st[_lib.SS_ASSIGNED]),
