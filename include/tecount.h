@@ -48,7 +48,14 @@ typedef enum tec_status {
     TEC_ERR_STATE = -3,         /* call out of order (no index, no begin, ...) */
     TEC_ERR_NOMEM = -4,         /* device or host allocation failed */
     TEC_ERR_LIMIT = -5,         /* input exceeds a documented limit (key width, record count) */
-    TEC_ERR_UNIMPLEMENTED = -6
+    TEC_ERR_UNIMPLEMENTED = -6,
+    TEC_ERR_IO = -7,            /* tec_bam_open: the file cannot be opened or mapped */
+    TEC_ERR_FORMAT = -8,        /* tec_bam_*: corrupt or truncated BAM / BGZF data */
+    TEC_ERR_UNSUPPORTED = -9,   /* tec_bam_*: a file the device decoder refuses (not BGZF, or record boundaries it
+                                   cannot establish block-parallel): decode it with libtecbam instead */
+    /* tec_bam_count: a record on which the reference's read loop raises (same numbers as tecbam.h) */
+    TEC_ERR_BAM_NO_BARCODE_TAG = -10, TEC_ERR_BAM_NO_UMI_TAG = -11, TEC_ERR_BAM_UMI = -12, TEC_ERR_BAM_END_NONE = -13,
+    TEC_ERR_BAM_CHROM_NAME = -14, TEC_ERR_BAM_REF_NONE = -15
 } tec_status;
 
 /* feature type codes: which branch of te_count.py:134-146 / :662-682 a feature can trigger */
@@ -213,6 +220,27 @@ int tec_sc_select(tec_ctx* ctx, int64_t maxcells, uint32_t* cells_out, int64_t* 
 int tec_sc_matrix_text(tec_ctx *ctx, int64_t n_rows, const uint32_t *cells, const char *barcodes,
                        const int64_t *bc_off, int64_t *n_bytes);
 int tec_sc_matrix_read(tec_ctx *ctx, int64_t offset, int64_t n, char *out);
+
+/* ---- BAM file -> counting path, decoded on the device (te_count.py:65-98, :190-214, :351-438)
+ *
+ * The same job as libtecbam (include/tecbam.h: BGZF inflate, record split, fields -> SoA columns, same
+ * field semantics and the same error conditions) done by CUDA kernels with one thread per BGZF block,
+ * with the columns handed to tec_bulk_push_dev / tec_sc_push_dev without leaving the device.  The host
+ * reads the compressed file into pinned memory and walks the per-block results once per window (an
+ * exact check of the record chain).  Usage: tec_bam_open, read the reference names, tec_bam_set_chrom_map
+ * (and tec_bam_set_whitelist) exactly as for tbam_*, tec_bulk_begin / tec_sc_begin, tec_bam_count (decodes
+ * the whole file into the running count), tec_bulk_finish / tec_sc_finalize, tec_bam_close.
+ * mode: 0 single end, 1 paired end, 2 single cell.  On TEC_ERR_UNSUPPORTED start over with libtecbam. */
+typedef struct tec_bam tec_bam;
+int tec_bam_open(tec_ctx *ctx, const char *path, tec_bam **out);
+void tec_bam_close(tec_bam *b);
+int tec_bam_n_references(const tec_bam *b);
+const char *tec_bam_reference_name(const tec_bam *b, int i);
+int tec_bam_set_chrom_map(tec_bam *b, const uint16_t *bulk_ids, const uint16_t *sc_ids, int32_t n, int32_t n_index);
+int tec_bam_set_whitelist(tec_bam *b, const char *barcodes, const int64_t *offsets, int32_t n);
+int tec_bam_count(tec_bam *b, int mode, int qual, int64_t *n_records);
+/* what = 0 blocks inflated by zlib on the host, 1..4 microseconds in load / inflate / chain / parse */
+int64_t tec_bam_info(const tec_bam *b, int what);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@ engine without the built CUDA library, or creating it without a usable GPU, rais
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
@@ -53,6 +54,14 @@ SIGNATURES = {
     "tec_sc_finalize": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_i64p, _c_i64p]),
     "tec_sc_fetch": (ctypes.c_int, [_vp, _c_i32p, _c_u32p, _c_i64p, _c_u32p, _c_i64p, _c_i64p]),
     "tec_sc_select": (ctypes.c_int, [_vp, ctypes.c_int64, _c_u32p, _c_i64p]),
+    "tec_bam_open": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "tec_bam_close": (None, [_vp]),
+    "tec_bam_n_references": (ctypes.c_int, [_vp]),
+    "tec_bam_reference_name": (ctypes.c_char_p, [_vp, ctypes.c_int]),
+    "tec_bam_set_chrom_map": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32]),
+    "tec_bam_set_whitelist": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.c_int32]),
+    "tec_bam_count": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _c_i64p]),
+    "tec_bam_info": (ctypes.c_int64, [_vp, ctypes.c_int]),
     "tec_sc_matrix_text": (ctypes.c_int, [_vp, ctypes.c_int64, _c_u32p, ctypes.c_char_p, _c_i64p, _c_i64p]),
     "tec_sc_matrix_read": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp]),
     "tec_sc_set_collective": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int]),
@@ -88,6 +97,94 @@ class TecError(RuntimeError):
         self.status = status
 
 
+ERR_IO, ERR_FORMAT, ERR_UNSUPPORTED = -7, -8, -9
+ERR_BAM_NO_BARCODE_TAG, ERR_BAM_NO_UMI_TAG, ERR_BAM_UMI, ERR_BAM_END_NONE, ERR_BAM_CHROM_NAME, ERR_BAM_REF_NONE = -10, -11, -12, -13, -14, -15
+
+
+class BamUnsupported(Exception):
+    """The device decoder refuses this file (not BGZF, or a record layout it cannot split
+    block-parallel): decode it on the host (fastbam.NativeBam) instead."""
+
+
+class DeviceBam:
+    """BAM file decoded on the device straight into the running count (include/tecount.h tec_bam_*).
+    Same hand-over of the chromosome map / whitelist and same exceptions as fastbam.NativeBam."""
+
+    def __init__(self, engine, filename):
+        self._eng = engine
+        self._lib = engine._lib
+        self._h = _vp()
+        self.filename = filename
+        rc = self._lib.tec_bam_open(engine._h, os.fsencode(filename), ctypes.byref(self._h))
+        if rc == ERR_UNSUPPORTED:
+            raise BamUnsupported(filename)
+        if rc == ERR_IO:
+            raise OSError("cannot open %s" % filename)
+        engine._check(rc)
+        engine._bams.append(weakref.ref(self))
+        self.references = [self._lib.tec_bam_reference_name(self._h, i).decode("ascii")
+                           for i in range(self._lib.tec_bam_n_references(self._h))]
+
+    def bind(self, chrom_map, whitelist=None):
+        bulk = np.array([chrom_map.bulk_id(n) for n in self.references], dtype=np.uint16)
+        sc = np.empty(len(self.references), dtype=np.uint16)
+        for i, n in enumerate(self.references):
+            try:
+                sc[i] = chrom_map.sc_id(n)
+            except ValueError:
+                sc[i] = 0xFFFD                          # raised when a counted record gets there
+        self._eng._check(self._lib.tec_bam_set_chrom_map(self._h, bulk.ctypes.data, sc.ctypes.data, len(self.references),
+                                                         chrom_map.n_index))
+        if whitelist is not None:
+            enc = [b.encode("utf-8") for b in whitelist.id_to_barcode]
+            off = np.zeros(len(enc) + 1, dtype=np.int64)
+            if enc:
+                np.cumsum([len(b) for b in enc], out=off[1:])
+            self._eng._check(self._lib.tec_bam_set_whitelist(self._h, b"".join(enc), off.ctypes.data, len(enc)))
+
+    def count(self, mode, qual):
+        """mode 0 single end, 1 paired end, 2 single cell; returns the number of records decoded."""
+        n = ctypes.c_int64(0)
+        rc = self._lib.tec_bam_count(self._h, int(mode), int(qual), ctypes.byref(n))
+        if rc == 0:
+            return n.value
+        msg = (self._lib.tec_last_error(self._eng._h) or b"").decode()
+        if rc == ERR_UNSUPPORTED:
+            raise BamUnsupported("%s: %s" % (self.filename, msg))
+        if rc == ERR_BAM_NO_BARCODE_TAG:
+            raise AssertionError('CB or CR tag not found!')                     # te_count.py:409
+        if rc == ERR_BAM_NO_UMI_TAG:
+            raise AssertionError('UB or UR tag not found!')                     # te_count.py:426
+        if rc == ERR_BAM_END_NONE:
+            raise TypeError("unsupported operand type(s) for +: 'NoneType' and 'int'" if mode != 2
+                            else "reference_end is None for a counted read (%s)" % msg)
+        if rc == ERR_BAM_REF_NONE:
+            raise AttributeError("'NoneType' object has no attribute 'replace'")    # te_count.py:431
+        if rc in (ERR_BAM_UMI, ERR_BAM_CHROM_NAME):
+            raise ValueError("%s: %s (%s)" % (self.filename, "UMI the code cannot hold" if rc == ERR_BAM_UMI
+                                              else "chromosome name contains ':' (unsupported in --sc)", msg))
+        if rc == ERR_FORMAT:
+            if "truncated" in msg:
+                raise EOFError("%s: %s" % (self.filename, msg))
+            raise ValueError("%s: %s" % (self.filename, msg))
+        self._eng._check(rc)
+
+    def info(self):
+        names = ("host_inflated_blocks", "us_load", "us_inflate", "us_chain", "us_parse")
+        return {k: int(self._lib.tec_bam_info(self._h, i)) for i, k in enumerate(names)}
+
+    def close(self):
+        if self._h:
+            self._lib.tec_bam_close(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _ptr(a, dtype):
     if a is None:
         return None
@@ -110,9 +207,15 @@ class Engine:
         self.device = device
         self.n_ensg = 0
         self._pinned = []
+        self._bams = []
 
     def close(self):
         if getattr(self, "_h", None):
+            for ref in getattr(self, "_bams", []):          # device decoders hold buffers of this context
+                b = ref()
+                if b is not None:
+                    b.close()
+            self._bams = []
             for p in self._pinned:
                 self._lib.tec_host_free(self._h, p)
             self._pinned = []
@@ -294,6 +397,9 @@ class Engine:
         self._check(self._lib.tec_sc_select(self._h, int(maxcells), ctypes.cast(out.ctypes.data, _c_u32p),
                                             ctypes.byref(n)))
         return out[:n.value]
+
+    def bam_open(self, filename):
+        return DeviceBam(self, filename)
 
     def sc_matrix_text(self, cells, barcodes):
         """Builds sc_save_result's dense rows (te_count.py:744-754) as text on the device for the

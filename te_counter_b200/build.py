@@ -13,7 +13,7 @@ CXX = os.environ.get("CXX", "g++")
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + \
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + \
         [os.path.join(os.path.dirname(HERE), "include", "tecount.h")]
 
 
@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     cmd = [NVCC, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-o", LIB, os.path.join(CSRC, "tecount.cu")]
+           "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-o", LIB, os.path.join(CSRC, "tecount.cu"), "-lz"]
     cmd[1:1] = os.environ.get("TEC_NVCC_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas")

@@ -207,10 +207,10 @@ struct Reader {
 /*
  * Backend concept:
  *   int  reserve(size_t comp_bytes, size_t ubuf_bytes, int n_blocks)   grow the window buffers (ubuf content is kept)
- *   uint8_t* comp_staging()                                            host memory the compressed payloads are gathered into
+ *   int  load(const MappedFile&, size_t lo, size_t n)                  file bytes [lo, lo + n) = the window's compressed blocks
  *   int  put(int64_t at, const uint8_t* data, size_t n)                host bytes into the uncompressed window
  *   int  carry(int64_t from, int64_t n)                                ubuf[0, n) = ubuf[from, from + n)
- *   int  inflate(const BlockDesc*, int n_blocks, size_t comp_bytes, int32_t* status)          bgzfdev::inflate_block + crc32_block per block
+ *   int  inflate(const BlockDesc*, int n_blocks, int32_t* status)      bgzfdev::inflate_block + crc32_block per block (in_off relative to lo)
  *   int  chain(const BlockDesc*, int n_blocks, int64_t w_end, int32_t n_ref, BlockChain* out) find_start (block 0 starts at 0) + hop per block
  *   int  parse(const BlockDesc*, int n_blocks, const BlockChain* used, const int64_t* base, int64_t n_records, int64_t w_end,
  *              int mode, int qual, const Reader&, int* err, int64_t* err_rec)                 parse_record per record into the columns
@@ -236,7 +236,8 @@ int decode_all(Reader& r, Backend& be, int mode, int qual, int window_blocks, in
     for (;;) {
         blocks.clear();
         src.clear();
-        size_t comp = 0, total = 0;
+        size_t total = 0;
+        const size_t file_lo = r.pos;
         while (r.pos < r.file.size && (int)blocks.size() < window_blocks) {
             const uint8_t* cdata;
             uint32_t clen, isize, crc;
@@ -245,10 +246,10 @@ int decode_all(Reader& r, Backend& be, int mode, int qual, int window_blocks, in
             r.pos += (size_t)bs;
             if (!isize) continue;
             BlockDesc d;
-            d.in_off = comp; d.in_len = clen; d.out_off = (uint64_t)carry_n + total; d.out_len = isize; d.crc = crc; d.pad = 0;
+            d.in_off = (uint64_t)(cdata - r.file.map) - file_lo; d.in_len = clen; d.out_off = (uint64_t)carry_n + total; d.out_len = isize;
+            d.crc = crc; d.pad = 0;
             blocks.push_back(d);
             src.push_back(cdata);
-            comp += (clen + 15) & ~size_t(15);
             total += isize;
         }
         const int nb = (int)blocks.size();
@@ -259,12 +260,12 @@ int decode_all(Reader& r, Backend& be, int mode, int qual, int window_blocks, in
         if (!nb && (!first || !carry_n)) break;
         first = false;
         if (nb) {
+            const size_t comp = r.pos - file_lo;
             rc = be.reserve(comp + 16, (size_t)w_end + 64, nb);
             if (rc) return r.fail(E_BACKEND, "backend: cannot allocate the window");
-            uint8_t* st = be.comp_staging();
-            for (int i = 0; i < nb; i++) memcpy(st + blocks[(size_t)i].in_off, src[(size_t)i], blocks[(size_t)i].in_len);
+            if (be.load(r.file, file_lo, comp)) return r.fail(E_BACKEND, "backend: reading the compressed blocks failed");
             status.assign((size_t)nb, 0);
-            if (be.inflate(blocks.data(), nb, comp, status.data())) return r.fail(E_BACKEND, "backend: inflate pass failed");
+            if (be.inflate(blocks.data(), nb, status.data())) return r.fail(E_BACKEND, "backend: inflate pass failed");
             for (int i = 0; i < nb; i++) {
                 if (status[(size_t)i] == bgzfdev::ST_OK) continue;
                 const BlockDesc& d = blocks[(size_t)i];               // the block-parallel inflate declined: zlib decides

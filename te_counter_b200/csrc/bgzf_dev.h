@@ -31,12 +31,12 @@ namespace bgzfdev {
 // Decode tables of 16-bit entries, one lookup for codes up to LB / DB bits.  Longer codes (rare
 // symbols by construction) are decoded bit by bit from the canonical code description
 // (count per length + symbols sorted by code), which needs no second-level tables: the whole
-// scratch area is 4.4 KB per block in flight.
-constexpr int LB = 10, DB = 9, PB = 7;
+// scratch area is 2.9 KB per block in flight (tens of thousands of blocks stay L2-resident).
+constexpr int LB = 9, DB = 8, PB = 7;
 constexpr int LIT_SYMS = 288, DIST_SYMS = 32, PRE_SYMS = 20;
 constexpr int SCRATCH_U16 = (1 << LB) + LIT_SYMS + 16 + (1 << DB) + DIST_SYMS + 16 + (1 << PB) + PRE_SYMS + 16;
 constexpr int SCRATCH_BYTES = SCRATCH_U16 * 2 + 320;                     // tables + code lengths
-constexpr int SCRATCH_STRIDE = 4480;
+constexpr int SCRATCH_STRIDE = 2944;
 static_assert(SCRATCH_BYTES <= SCRATCH_STRIDE, "scratch stride too small");
 
 // table entry: [3:0] code length (0 = no such code), [5:4] kind, [15:6] value
@@ -246,7 +246,34 @@ BGZF_HD int inflate_block(const uint8_t* in, uint32_t in_n, uint8_t* out, uint32
                 rc = build_code(lens, 288, lit, false);
                 if (rc) return rc;
             }
+            // Symbol loop as a flat state machine: one turn either decodes one symbol or copies up to 8
+            // bytes of a pending match.  On the device the 32 lanes of a warp run 32 different
+            // streams; with the copy inside the symbol branch every lane would wait for the longest
+            // match in the warp on every turn.
+            uint32_t copy_left = 0, copy_off = 0, phase = 0;
+            uint64_t pat = 0;                   // the period of a match with distance < 8, one byte per lane of the word
             for (;;) {
+                if (copy_left) {
+                    const uint32_t n = copy_left < 8 ? copy_left : 8;
+                    uint8_t* d8 = out + o;
+                    if (copy_off >= 8) {        // the loads do not depend on this turn's stores: issue them together
+                        const uint8_t* s8 = d8 - copy_off;
+                        uint8_t c[8];
+                        for (uint32_t j = 0; j < 8; j++) c[j] = j < n ? s8[j] : 0;
+                        for (uint32_t j = 0; j < 8; j++)
+                            if (j < n) d8[j] = c[j];
+                    } else {
+                        uint32_t ph = phase;
+                        for (uint32_t j = 0; j < 8; j++) {
+                            if (j < n) d8[j] = (uint8_t)(pat >> (8 * ph));
+                            ph = ph + 1 == copy_off ? 0 : ph + 1;
+                        }
+                        phase = ph;             // (advanced 8 times; only read again if copy_left stays > 0, i.e. n == 8)
+                    }
+                    o += n;
+                    copy_left -= n;
+                    continue;
+                }
                 const uint32_t e = decode_sym(b, lit);
                 if (!e) return ST_FORMAT;
                 const uint32_t kind = (e >> 4) & 3;
@@ -269,8 +296,14 @@ BGZF_HD int inflate_block(const uint8_t* in, uint32_t in_n, uint8_t* out, uint32
                 if (!need(b, x)) return ST_FORMAT;
                 off += take(b, x);
                 if (off > o || len > out_n - o) return ST_FORMAT;
-                for (uint32_t k = 0; k < len; k++) out[o + k] = out[o + k - off];
-                o += len;
+                copy_left = len;
+                copy_off = off;
+                if (off < 8) {
+                    pat = 0;
+                    for (uint32_t j = 0; j < 7; j++)
+                        if (j < off) pat |= (uint64_t)out[o - off + j] << (8 * j);
+                    phase = 0;
+                }
             }
         } else {
             return ST_FORMAT;

@@ -139,6 +139,9 @@ struct tec_ctx {
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
     int opt_sc_pack_umi = 1;              // single cell: 2-bit UMI sort keys when every UMI is fixed-length ACGT
     int opt_sc_algo = -1;                 // -1 auto, 0 exact search only, 1 cell table
+    int opt_bam_lanes = 1;                // BGZF blocks decoded per warp by the inflate kernel (1..32): the streams of a warp
+                                          // diverge on every symbol; measured 201 ms (1) / 206 (2) / 241 (8) / 398 (32) per 3.7 GB
+    int opt_bam_window_blocks = 65536;    // BGZF blocks decoded per pass by tec_bam_count (one thread each)
     int opt_ctas_per_sm = 2;              // resident CTAs per SM of the fast bulk kernel (512 threads each)
 
     // host staging
@@ -148,13 +151,23 @@ struct tec_ctx {
     int stage_next = 0;
 
     ScState* sc = nullptr;
+    uint8_t* bam_pinned[2] = {nullptr, nullptr};    // staging chunks of the device BAM decoder (bamgpu.cuh)
+    cudaEvent_t bam_ev[2] = {nullptr, nullptr};
     DevCache cache;
 
     int ensure_stage(int64_t n, bool sc_layout);
     void free_stage();
     void free_index();
     void free_sc();
-    void free_all() { free_stage(); free_index(); free_sc(); cache.trim(); }
+    void free_bam() {
+        for (int i = 0; i < 2; i++) {
+            if (bam_pinned[i]) cudaFreeHost(bam_pinned[i]);
+            if (bam_ev[i]) cudaEventDestroy(bam_ev[i]);
+            bam_pinned[i] = nullptr;
+            bam_ev[i] = nullptr;
+        }
+    }
+    void free_all() { free_stage(); free_index(); free_sc(); free_bam(); cache.trim(); }
 };
 
 inline void tec_ctx::free_stage() {

@@ -5,6 +5,7 @@
 #include "context.cuh"
 #include "sc.cuh"
 #include "sc_text.cuh"
+#include "bamgpu.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -466,6 +467,8 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
     else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
+    else if (k == "bam_lanes") { if (value < 1 || value > 32) TEC_FAIL(TEC_ERR_ARG, "bam_lanes: 1..32"); ctx->opt_bam_lanes = (int)value; }
+    else if (k == "bam_window_blocks") { if (value < 1 || value > (1 << 20)) TEC_FAIL(TEC_ERR_ARG, "bam_window_blocks: 1..1048576"); ctx->opt_bam_window_blocks = (int)value; }
     else TEC_FAIL(TEC_ERR_ARG, "tec_set_option: unknown key " + k);
     return TEC_OK;
 }
@@ -491,3 +494,91 @@ extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
     if (k == "stab_entries") return ctx->idx.st_entries;
     return -1;
 }
+
+// ------------------------------------------------------------------------------------------------
+// BAM file -> counting path on the device (bamgpu.cuh)
+int BamGpuBackend::deliver(int64_t n, int mode) {
+    const int rc = mode == bgzfdev::MODE_SC
+                       ? tec_sc_push_dev(ctx, n, col.start, col.end, col.chrom, col.mapq, col.flag, col.cell, col.umi)
+                       : tec_bulk_push_dev(ctx, n, col.start, col.end, col.chrom, col.mapq, col.flag);
+    return rc ? 1 : 0;
+}
+
+static int bam_status(tec_ctx* ctx, const bamorch::Reader& r, int rc) {
+    if (rc == bamorch::OK) return TEC_OK;
+    if (rc != bamorch::E_BACKEND) ctx->err = r.err;         // the backend left the CUDA text in ctx->err
+    switch (rc) {
+    case bamorch::E_IO: return TEC_ERR_IO;
+    case bamorch::E_FORMAT: return TEC_ERR_FORMAT;
+    case bamorch::E_NOT_BGZF: return TEC_ERR_UNSUPPORTED;
+    case bamorch::E_UNSUPPORTED: return TEC_ERR_UNSUPPORTED;
+    case bamorch::E_ARG: return TEC_ERR_ARG;
+    case bamorch::E_BACKEND: return TEC_ERR_CUDA;
+    }
+    if (rc <= bamorch::E_RECORD) return -(bamorch::E_RECORD - rc);      // TEC_ERR_BAM_*: -10 ... -15 (and -2 for a malformed record)
+    return TEC_ERR_FORMAT;
+}
+
+extern "C" int tec_bam_open(tec_ctx* ctx, const char* path, tec_bam** out) {
+    if (!ctx || !path || !out) return TEC_ERR_ARG;
+    *out = nullptr;
+    tec_bam* b = new tec_bam(ctx);
+    const int rc = b->reader.open_path(path);
+    if (rc) {
+        const int st = bam_status(ctx, b->reader, rc);
+        delete b;
+        return st;
+    }
+    *out = b;
+    return TEC_OK;
+}
+
+extern "C" void tec_bam_close(tec_bam* b) { delete b; }
+
+extern "C" int tec_bam_n_references(const tec_bam* b) { return b ? (int)b->reader.refs.size() : 0; }
+
+extern "C" const char* tec_bam_reference_name(const tec_bam* b, int i) {
+    return b && i >= 0 && (size_t)i < b->reader.refs.size() ? b->reader.refs[(size_t)i].c_str() : nullptr;
+}
+
+extern "C" int tec_bam_set_chrom_map(tec_bam* b, const uint16_t* bulk_ids, const uint16_t* sc_ids, int32_t n, int32_t n_index) {
+    if (!b) return TEC_ERR_ARG;
+    b->be.ctx_uploaded = false;
+    return bam_status(b->ctx, b->reader, b->reader.set_chrom_map(bulk_ids, sc_ids, n, n_index));
+}
+
+extern "C" int tec_bam_set_whitelist(tec_bam* b, const char* barcodes, const int64_t* offsets, int32_t n) {
+    if (!b) return TEC_ERR_ARG;
+    b->be.ctx_uploaded = false;
+    return bam_status(b->ctx, b->reader, b->reader.set_whitelist(barcodes, offsets, n));
+}
+
+extern "C" int tec_bam_count(tec_bam* b, int mode, int qual, int64_t* n_records) {
+    if (!b) return TEC_ERR_ARG;
+    tec_ctx* ctx = b->ctx;
+    if (n_records) *n_records = 0;
+    if (mode < 0 || mode > 2) TEC_FAIL(TEC_ERR_ARG, "tec_bam_count: mode must be 0 (single end), 1 (paired end) or 2 (single cell)");
+    if (mode == bgzfdev::MODE_SC) {
+        if (!ctx->sc || !ctx->sc->active) TEC_FAIL(TEC_ERR_STATE, "tec_bam_count: tec_sc_begin not called");
+    } else if (!ctx->bulk_active || (ctx->paired ? 1 : 0) != mode) {
+        TEC_FAIL(TEC_ERR_STATE, "tec_bam_count: tec_bulk_begin not called for this mode");
+    }
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    int64_t n = 0;
+    const int rc = bamorch::decode_all(b->reader, b->be, mode, qual, ctx->opt_bam_window_blocks, &n);
+    if (n_records) *n_records = n;
+    return bam_status(ctx, b->reader, rc);
+}
+
+extern "C" int64_t tec_bam_info(const tec_bam* b, int what) {
+    if (!b) return 0;
+    switch (what) {
+    case 0: return b->be.n_declined;
+    case 1: return (int64_t)(b->be.ms_load * 1e3);
+    case 2: return (int64_t)(b->be.ms_inflate * 1e3);
+    case 3: return (int64_t)(b->be.ms_chain * 1e3);
+    case 4: return (int64_t)(b->be.ms_parse * 1e3);
+    }
+    return 0;
+}
+

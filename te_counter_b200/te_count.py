@@ -34,13 +34,17 @@ SC_CELL_PAD = 1000               # te_count.py:502  `maxcells+1000`
 
 
 def _open_alignment(filename):
-    """TEC_BAM_DECODER = auto (default) | native | pysam | python.  `auto`: block-compressed BAM goes
-    through libtecbam (threads inflate and parse into the pinned batch, fastbam.py) when it is
-    built; anything else through pysam as in the reference (te_count.py:11, :65), or through the
-    pure-Python stand-in with pysam's interface (bam.py) where pysam is not installed."""
+    """Host readers.  TEC_BAM_DECODER = auto (default) | gpu | native | pysam | python.  `auto` / `gpu`:
+    the callers first try the device decoder (tec_bam_*) and come here only for files it refuses;
+    then block-compressed BAM goes through libtecbam (threads inflate and parse into the pinned
+    batch, fastbam.py) when it is built; anything else through pysam as in the reference
+    (te_count.py:11, :65), or through the pure-Python stand-in with pysam's interface (bam.py) where
+    pysam is not installed."""
     mode = os.environ.get('TEC_BAM_DECODER', 'auto')
-    if mode not in ('auto', 'native', 'pysam', 'python'):
-        raise ValueError('TEC_BAM_DECODER must be auto, native, pysam or python')
+    if mode not in ('auto', 'gpu', 'native', 'pysam', 'python'):
+        raise ValueError('TEC_BAM_DECODER must be auto, gpu, native, pysam or python')
+    if mode == 'gpu':
+        mode = 'auto'
     if mode == 'native' or (mode == 'auto' and _fastbam.available()):
         try:
             return _fastbam.NativeBam(filename)
@@ -56,6 +60,12 @@ def _open_alignment(filename):
                 raise
     from . import bam as _bam
     return _bam.AlignmentFile(filename, 'r')
+
+
+def _device_decoder_wanted(eng):
+    """`auto` and `gpu`: decode the BAM on the device (tec_bam_*: 2.7x the 16 host cores of the B200 box);
+    files it refuses (SAM text, record layouts it cannot split block-parallel) go to the host readers."""
+    return os.environ.get('TEC_BAM_DECODER', 'auto') in ('auto', 'gpu') and hasattr(eng, 'bam_open')
 
 
 class ScResult(Mapping):
@@ -147,14 +157,34 @@ class measureTE:
         qual = self._qual()
         eng = self._engine()
         cm = _reads.ChromMap(self.genome.chrom_keys)
-        sam = _open_alignment(filename)
-        native = isinstance(sam, _fastbam.NativeBam)
-        if native:
-            sam.bind(cm)
-        batch = _reads.Batch(BATCH_RECORDS, alloc=eng.pinned)
-        eng.bulk_begin(paired, qual)
-        more, done, next_log = True, 0, 1000000
         label = 'reads' if paired else 'SE reads'
+        more, done, next_log = True, 0, 1000000
+        if _device_decoder_wanted(eng):
+            try:                                              # BGZF inflate, record split and packing on the device
+                dev = eng.bam_open(filename)
+                try:
+                    dev.bind(cm)
+                    eng.bulk_begin(paired, qual)
+                    done = dev.count(1 if paired else 0, qual)
+                    done = done // 2 if paired else done
+                    more = False
+                    self._bam_info = dev.info()
+                finally:
+                    dev.close()
+            except _lib.BamUnsupported:
+                more = True                                   # start over with a host decoder
+            while done >= next_log:
+                log.info('Processed {:,} {}'.format(next_log, label))
+                next_log += 1000000
+        sam = batch = None
+        if more:
+            done, next_log = 0, 1000000
+            sam = _open_alignment(filename)
+            native = isinstance(sam, _fastbam.NativeBam)
+            if native:
+                sam.bind(cm)
+            batch = _reads.Batch(BATCH_RECORDS, alloc=eng.pinned)
+            eng.bulk_begin(paired, qual)
         while more:
             more = sam.fill_bulk(batch, paired, qual) if native else _reads.fill_bulk(batch, sam, cm, paired, qual)
             eng.bulk_push(batch.n, batch.start, batch.end, batch.chrom, batch.mapq, batch.flag)
@@ -162,7 +192,8 @@ class measureTE:
             while done >= next_log:
                 log.info('Processed {:,} {}'.format(next_log, label))
                 next_log += 1000000
-        sam.close()
+        if sam is not None:
+            sam.close()
         counts, st = eng.bulk_finish()
         if st[_lib.BS_CRASH_NAME]:
             log.error('Unmatched pair!')
@@ -223,14 +254,33 @@ class measureTE:
         self.load_genome()                                    # te_count.py:581 (done up front here)
         eng = self._engine()
         cm = _reads.ChromMap(self.genome.chrom_keys)
-        sam = _open_alignment(filename)
-        native = isinstance(sam, _fastbam.NativeBam)
-        if native:
-            sam.bind(cm, whitelist)
-        batch = _reads.Batch(BATCH_RECORDS, sc=True, alloc=eng.pinned)
-        eng.sc_begin(qual, strand, len(whitelist))
         log.info('Part 1: Collapsing UMI/CB combinations')
         more, done, next_log = True, 0, 10000000
+        if _device_decoder_wanted(eng):
+            try:
+                dev = eng.bam_open(filename)
+                try:
+                    dev.bind(cm, whitelist)
+                    eng.sc_begin(qual, strand, len(whitelist))
+                    done = dev.count(2, qual)
+                    more = False
+                    self._bam_info = dev.info()
+                finally:
+                    dev.close()
+            except _lib.BamUnsupported:
+                more = True
+            while done >= next_log:
+                log.info('  Processed {:,} SE valid reads'.format(next_log))
+                next_log += 10000000
+        sam = batch = None
+        if more:
+            done, next_log = 0, 10000000
+            sam = _open_alignment(filename)
+            native = isinstance(sam, _fastbam.NativeBam)
+            if native:
+                sam.bind(cm, whitelist)
+            batch = _reads.Batch(BATCH_RECORDS, sc=True, alloc=eng.pinned)
+            eng.sc_begin(qual, strand, len(whitelist))
         while more:
             more = sam.fill_sc(batch, qual) if native else _reads.fill_sc(batch, sam, cm, whitelist, qual)
             eng.sc_push(batch.n, batch.start, batch.end, batch.chrom, batch.mapq, batch.flag,
@@ -239,7 +289,8 @@ class measureTE:
             while done >= next_log:
                 log.info('  Processed {:,} SE valid reads'.format(next_log))
                 next_log += 10000000
-        sam.close()
+        if sam is not None:
+            sam.close()
         log.info(f'Part 2: Get the best {maxcells} barcodes and remove dupes')
         n_triples, n_hit = eng.sc_finalize(_bundle_keys, maxcells, _pad)
         ensg, cell, count, hcell, hcount, st = eng.sc_fetch(n_triples, n_hit)

@@ -236,7 +236,8 @@ def test_sc_matrix_text_without_triples(engine):
 
 
 @pytest.mark.parametrize("name", ["sc_rand_det_strand", "sc_rand_amb_bundles"])
-def test_sc_from_bam_file(monkeypatch, tmp_path, name):
+@pytest.mark.parametrize("decoder", ["native", "auto"])
+def test_sc_from_bam_file(monkeypatch, tmp_path, name, decoder):
     """BAM file -> libtecbam -> pinned batches -> CUDA single-cell path -> matrix rows formatted on
     the device -> the reference's TSV bytes."""
     import sys
@@ -249,7 +250,7 @@ def test_sc_from_bam_file(monkeypatch, tmp_path, name):
     wl = tmp_path / "wl.txt"
     wl.write_text("".join(w + "\n" for w in case["whitelist"]))
     monkeypatch.setitem(sys.modules, "pysam", None)
-    monkeypatch.setenv("TEC_BAM_DECODER", "native")
+    monkeypatch.setenv("TEC_BAM_DECODER", decoder)
     mte = te_counter_b200.measureTE("test", case["qual"], device=0)
     mte.bind_genome(H.GOLD + "/" + case["glb"])
     log = CaptureLog()

@@ -39,7 +39,10 @@ struct HostBackend {
         if (ubuf.size() < ubuf_bytes) ubuf.resize(ubuf_bytes);
         return 0;
     }
-    uint8_t* comp_staging() { return comp.data(); }
+    int load(const bamorch::MappedFile& f, size_t lo, size_t n) {
+        memcpy(comp.data(), f.map + lo, n);
+        return 0;
+    }
     int put(int64_t at, const uint8_t* data, size_t n) {
         memcpy(ubuf.data() + at, data, n);
         return 0;
@@ -48,7 +51,7 @@ struct HostBackend {
         memmove(ubuf.data(), ubuf.data() + from, (size_t)n);
         return 0;
     }
-    int inflate(const bamorch::BlockDesc* bl, int nb, size_t, int32_t* status) {
+    int inflate(const bamorch::BlockDesc* bl, int nb, int32_t* status) {
         for (int b = 0; b < nb; b++) {          // one CUDA thread per b
             const bamorch::BlockDesc& d = bl[b];
             int st = bgzfdev::inflate_block(comp.data() + d.in_off, d.in_len, ubuf.data() + d.out_off, d.out_len, scratch.data());

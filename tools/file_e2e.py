@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--dir", default="/tmp")
     ap.add_argument("--maxcells", type=int, default=10000)
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value")
+    ap.add_argument("--decoder", choices=["native", "gpu"], default="native", help="TEC_BAM_DECODER for the timed call")
     a = ap.parse_args()
     path = os.path.join(a.dir, "tec_synth_%s.bam" % a.mode)
     wlf = os.path.join(a.dir, "tec_synth_wl.txt")
@@ -61,8 +63,12 @@ def main():
     mte.genome = idx
     mte.all_feature_names = idx.names
     mte.load_genome = lambda: None                      # the synthetic index has no .glb file
+    for kv in a.opt:
+        k, v = kv.split("=")
+        mte._engine().set_option(k, int(v))
     mte._engine()                                       # index upload + table build: outside the timed call, as load_genome is
-    out = {"mode": a.mode, "file_bytes": os.path.getsize(path), "host_cores": os.cpu_count(), "make_bam_s": t_make}
+    os.environ["TEC_BAM_DECODER"] = a.decoder
+    out = {"mode": a.mode, "decoder": a.decoder, "file_bytes": os.path.getsize(path), "host_cores": os.cpu_count(), "make_bam_s": t_make}
     runs = []
     for _ in range(3):
         t0 = time.perf_counter()
@@ -74,6 +80,8 @@ def main():
     n = mte.total_reads - 1
     n_rec = n * 2 if a.mode == "pe" else n
     out.update({"records": n_rec, "file_to_result_s": runs, "file_to_result_records_per_s": n_rec / min(runs)})
+    if getattr(mte, "_bam_info", None):
+        out["device_decoder_last_run"] = mte._bam_info
     wl = reads.Whitelist(wlf) if a.mode == "sc" else None
     cols, dt, threads = decode_all(path, a.mode, idx.chrom_keys, wl)
     out.update({"decode_only_records_per_s": len(cols["start"]) / dt, "decode_threads": threads})
