@@ -140,8 +140,8 @@ struct BamGpuBackend {
         for (int i = 0; i < 2; i++)
             if (!ctx->bam_pinned[i]) BAM_CK(cudaHostAlloc(&ctx->bam_pinned[i], TEC_BAM_CHUNK, cudaHostAllocDefault));
         if (!ctx->bam_ev[0]) {
-            BAM_CK(cudaEventCreateWithFlags(&ctx->bam_ev[0], cudaEventDisableTiming));
-            BAM_CK(cudaEventCreateWithFlags(&ctx->bam_ev[1], cudaEventDisableTiming));
+            for (int i = 0; i < 3; i++) BAM_CK(cudaEventCreateWithFlags(&ctx->bam_ev[i], cudaEventDisableTiming));
+            BAM_CK(cudaStreamCreateWithFlags(&ctx->bam_stream2, cudaStreamNonBlocking));
         }
         return 0;
     }
@@ -181,34 +181,32 @@ struct BamGpuBackend {
         }
         return 0;
     }
-    int load(const bamorch::MappedFile& f, size_t lo, size_t n) {
-        const double t0 = now_ms();
-        // page cache -> two pinned chunks (a few pread streams each: one tops out near 5 GB/s) -> HBM; the
-        // reads of a chunk overlap the H2D copy of the one before
-        int i = 0;
-        for (size_t off = 0; off < n; off += TEC_BAM_CHUNK, i ^= 1) {
-            const size_t len = std::min<size_t>(TEC_BAM_CHUNK, n - off);
-            uint8_t* buf = ctx->bam_pinned[i];
-            BAM_CK(cudaEventSynchronize(ctx->bam_ev[i]));
-            const int nt = (int)std::max<size_t>(1, std::min<size_t>(8, len >> 22));
-            std::vector<std::thread> th;
-            std::vector<int> bad((size_t)nt, 0);
-            for (int t = 0; t < nt; t++)
-                th.emplace_back([&, t] {
-                    size_t a = len * (size_t)t / (size_t)nt, b = len * (size_t)(t + 1) / (size_t)nt;
-                    while (a < b) {
-                        const ssize_t k = pread(f.fd, buf + a, b - a, (off_t)(lo + off + a));
-                        if (k <= 0) { bad[(size_t)t] = 1; return; }
-                        a += (size_t)k;
-                    }
-                });
-            for (auto& x : th) x.join();
-            for (int x : bad)
-                if (x) { ctx->err = "pread failed"; return 1; }
-            BAM_CK(cudaMemcpyAsync(d_comp + off, buf, len, cudaMemcpyHostToDevice, ctx->stream));
-            BAM_CK(cudaEventRecord(ctx->bam_ev[i], ctx->stream));
-        }
-        ms_load += now_ms() - t0;
+    const bamorch::MappedFile* cur_file = nullptr;
+    size_t cur_lo = 0, cur_n = 0;
+    int load(const bamorch::MappedFile& f, size_t lo, size_t n) {       // the bytes move inside inflate(), chunk by chunk
+        cur_file = &f;
+        cur_lo = lo;
+        cur_n = n;
+        return 0;
+    }
+    int read_chunk(uint8_t* buf, size_t off, size_t len) {
+        const int nt = (int)std::max<size_t>(1, std::min<size_t>(8, len >> 22));
+        std::vector<std::thread> th;
+        std::vector<int> bad((size_t)nt, 0);
+        const int fd = cur_file->fd;
+        const size_t lo = cur_lo;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t] {
+                size_t a = len * (size_t)t / (size_t)nt, b = len * (size_t)(t + 1) / (size_t)nt;
+                while (a < b) {
+                    const ssize_t k = pread(fd, buf + a, b - a, (off_t)(lo + off + a));
+                    if (k <= 0) { bad[(size_t)t] = 1; return; }
+                    a += (size_t)k;
+                }
+            });
+        for (auto& x : th) x.join();
+        for (int x : bad)
+            if (x) { ctx->err = "pread failed"; return 1; }
         return 0;
     }
     int put(int64_t at, const uint8_t* data, size_t n) {
@@ -232,18 +230,43 @@ struct BamGpuBackend {
         BAM_CK(cudaMemcpyAsync(d_ubuf, d_tmp, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
         return 0;
     }
+    // page cache -> two pinned chunks (a few pread streams each: one tops out near 5 GB/s) -> HBM -> inflate
+    // kernel over the blocks of the chunk.  Chunks alternate between two streams, so the host reads
+    // chunk i+1 while chunk i is copied and chunk i-1 is being inflated.
     int inflate(const bamorch::BlockDesc* bl, int nb, int32_t* status) {
         const double t0 = now_ms();
+        cudaStream_t st[2] = {ctx->stream, ctx->bam_stream2};
         BAM_CK(cudaMemcpyAsync(d_blocks, bl, sizeof(bamorch::BlockDesc) * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+        BAM_CK(cudaEventRecord(ctx->bam_ev[2], ctx->stream));
+        BAM_CK(cudaStreamWaitEvent(ctx->bam_stream2, ctx->bam_ev[2], 0));       // descriptors (and the window so far) are in place
         const int lanes = ctx->opt_bam_lanes;
-        const int64_t warps = (nb + lanes - 1) / lanes;
-        bam_inflate_kernel<<<(unsigned)((warps * 32 + BAM_TPB - 1) / BAM_TPB), BAM_TPB, 0, ctx->stream>>>(nb, d_blocks, d_comp, d_ubuf, d_scratch, d_crc,
-                                                                                                         d_status, lanes);
-        BAM_CK(cudaGetLastError());
+        int b0 = 0, i = 0;
+        while (b0 < nb) {
+            // blocks [b0, b1): compressed bytes [c_lo, c_hi) of the window, at most one chunk
+            const size_t c_lo = b0 ? (size_t)bl[b0].in_off : 0;
+            int b1 = b0;
+            while (b1 < nb && (size_t)bl[b1].in_off + bl[b1].in_len + 8 - c_lo <= TEC_BAM_CHUNK) b1++;
+            if (b1 == b0) { ctx->err = "BGZF block larger than the staging chunk"; return 1; }
+            const size_t c_hi = std::min<size_t>(cur_n, (size_t)bl[b1 - 1].in_off + bl[b1 - 1].in_len + 8);   // through the last trailer
+            uint8_t* buf = ctx->bam_pinned[i];
+            BAM_CK(cudaEventSynchronize(ctx->bam_ev[i]));                       // the copy that last used this chunk is done
+            if (read_chunk(buf, c_lo, c_hi - c_lo)) return 1;
+            BAM_CK(cudaMemcpyAsync(d_comp + c_lo, buf, c_hi - c_lo, cudaMemcpyHostToDevice, st[i]));
+            BAM_CK(cudaEventRecord(ctx->bam_ev[i], st[i]));
+            const int n = b1 - b0;
+            const int64_t warps = (n + lanes - 1) / lanes;
+            bam_inflate_kernel<<<(unsigned)((warps * 32 + BAM_TPB - 1) / BAM_TPB), BAM_TPB, 0, st[i]>>>(
+                n, d_blocks + b0, d_comp, d_ubuf, d_scratch + (size_t)b0 * bgzfdev::SCRATCH_STRIDE, d_crc, d_status + b0, lanes);
+            BAM_CK(cudaGetLastError());
+            ctx->launches++;
+            b0 = b1;
+            i ^= 1;
+        }
+        BAM_CK(cudaEventRecord(ctx->bam_ev[2], ctx->bam_stream2));
+        BAM_CK(cudaStreamWaitEvent(ctx->stream, ctx->bam_ev[2], 0));
         BAM_CK(cudaMemcpyAsync(status, d_status, 4 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
         BAM_CK(cudaStreamSynchronize(ctx->stream));
-        for (int i = 0; i < nb; i++) n_declined += status[i] != 0;
-        ctx->launches++;
+        for (int k = 0; k < nb; k++) n_declined += status[k] != 0;
         ms_inflate += now_ms() - t0;
         return 0;
     }

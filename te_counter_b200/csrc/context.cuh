@@ -152,7 +152,8 @@ struct tec_ctx {
 
     ScState* sc = nullptr;
     uint8_t* bam_pinned[2] = {nullptr, nullptr};    // staging chunks of the device BAM decoder (bamgpu.cuh)
-    cudaEvent_t bam_ev[2] = {nullptr, nullptr};
+    cudaEvent_t bam_ev[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t bam_stream2 = nullptr;
     DevCache cache;
 
     int ensure_stage(int64_t n, bool sc_layout);
@@ -162,10 +163,14 @@ struct tec_ctx {
     void free_bam() {
         for (int i = 0; i < 2; i++) {
             if (bam_pinned[i]) cudaFreeHost(bam_pinned[i]);
-            if (bam_ev[i]) cudaEventDestroy(bam_ev[i]);
             bam_pinned[i] = nullptr;
+        }
+        for (int i = 0; i < 3; i++) {
+            if (bam_ev[i]) cudaEventDestroy(bam_ev[i]);
             bam_ev[i] = nullptr;
         }
+        if (bam_stream2) cudaStreamDestroy(bam_stream2);
+        bam_stream2 = nullptr;
     }
     void free_all() { free_stage(); free_index(); free_sc(); free_bam(); cache.trim(); }
 };

@@ -171,8 +171,8 @@ class measureTE:
                     self._bam_info = dev.info()
                 finally:
                     dev.close()
-            except _lib.BamUnsupported:
-                more = True                                   # start over with a host decoder
+            except (_lib.BamUnsupported, OSError):
+                more = True                                   # start over with a host reader
             while done >= next_log:
                 log.info('Processed {:,} {}'.format(next_log, label))
                 next_log += 1000000
@@ -267,7 +267,7 @@ class measureTE:
                     self._bam_info = dev.info()
                 finally:
                     dev.close()
-            except _lib.BamUnsupported:
+            except (_lib.BamUnsupported, OSError):
                 more = True
             while done >= next_log:
                 log.info('  Processed {:,} SE valid reads'.format(next_log))
