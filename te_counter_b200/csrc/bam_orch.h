@@ -106,6 +106,36 @@ inline bool zlib_block(const uint8_t* in, uint32_t in_n, uint8_t* out, uint32_t 
     return ok && (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, out_n) == crc;
 }
 
+// CRC32 lookup table and the "append 2^k zero bytes" operators of bgzfdev::crc32_shift (zlib's crc32_combine
+// construction: the operator for one zero BIT, squared 3 times -> one byte, then squared once per k).
+inline void crc32_tables(uint32_t table[256], uint32_t mats[bgzfdev::CRC_SHIFT_MATS * 32]) {
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        table[i] = c;
+    }
+    uint32_t a[32], b[32];
+    a[0] = 0xEDB88320u;                         // one zero bit: reflected CRC shifts right
+    for (int n = 1; n < 32; n++) a[n] = 1u << (n - 1);
+    auto times = [](const uint32_t* m, uint32_t v) {
+        uint32_t r = 0;
+        for (int i = 0; v; v >>= 1, i++)
+            if (v & 1) r ^= m[i];
+        return r;
+    };
+    auto square = [&](uint32_t* dst, const uint32_t* src) {
+        for (int n = 0; n < 32; n++) dst[n] = times(src, src[n]);
+    };
+    square(b, a);                               // 2 bits
+    square(a, b);                               // 4 bits
+    square(b, a);                               // 8 bits = one byte
+    for (int k = 0; k < bgzfdev::CRC_SHIFT_MATS; k++) {
+        memcpy(mats + 32 * k, b, sizeof(b));
+        square(a, b);
+        memcpy(b, a, sizeof(b));
+    }
+}
+
 struct Reader {
     MappedFile file;
     size_t pos = 0;                         // next BGZF block

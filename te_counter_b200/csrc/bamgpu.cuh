@@ -23,12 +23,31 @@
 #define TEC_BAM_CHUNK (size_t(128) << 20)
 
 __global__ void bam_inflate_kernel(int nb, const bamorch::BlockDesc* __restrict__ bl, const uint8_t* __restrict__ comp, uint8_t* __restrict__ ubuf,
-                                   uint8_t* __restrict__ scratch, const uint32_t* __restrict__ crc_table, int32_t* __restrict__ status, int lanes) {
+                                   uint8_t* __restrict__ scratch, const uint32_t* __restrict__ crc_table, const uint32_t* __restrict__ crc_mats,
+                                   int32_t* __restrict__ status, int lanes) {
     // `lanes` streams per warp: 32 independent Huffman streams in one warp diverge on every symbol, fewer
     // streams per warp trade idle lanes for less serialisation (option bam_lanes)
     const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (lanes == 1) {
+        // one block per warp: lane 0 decodes, then all 32 lanes share the CRC32 of the inflated bytes
+        if (warp >= nb) return;
+        const bamorch::BlockDesc d = bl[warp];
+        uint8_t* out = ubuf + d.out_off;
+        int st = 0;
+        if (lane == 0) st = bgzfdev::inflate_block(comp + d.in_off, d.in_len, out, d.out_len, scratch + (size_t)warp * bgzfdev::SCRATCH_STRIDE);
+        __syncwarp();                                   // lane 0's stores are visible to the warp
+        st = __shfl_sync(0xFFFFFFFFu, st, 0);
+        if (st == bgzfdev::ST_OK) {
+            uint32_t c = bgzfdev::crc32_lane_share(out, d.out_len, lane, crc_table, crc_mats);
+            for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xFFFFFFFFu, c, o);
+            if ((c ^ 0xFFFFFFFFu) != d.crc) st = bgzfdev::ST_CRC;
+        }
+        if (lane == 0) status[warp] = st;
+        return;
+    }
     if (lane >= lanes) return;
-    const int b = (int)((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lanes + lane);
+    const int b = (int)(warp * lanes + lane);
     if (b >= nb) return;
     const bamorch::BlockDesc d = bl[b];
     uint8_t* out = ubuf + d.out_off;
@@ -87,7 +106,7 @@ struct BamGpuBackend {
     int64_t* d_base = nullptr;
     int64_t* d_rec_off = nullptr;
     int32_t* d_status = nullptr;
-    uint32_t* d_crc = nullptr;
+    uint32_t* d_crc = nullptr;             // 256-entry table, then the shift operators of bgzfdev::crc32_shift
     unsigned long long* d_err = nullptr;
     uint16_t *d_bulk_ids = nullptr, *d_sc_ids = nullptr;
     uint32_t* d_wl_slot = nullptr;
@@ -127,12 +146,8 @@ struct BamGpuBackend {
 
     int init() {
         if (d_crc) return 0;
-        uint32_t t[256];
-        for (uint32_t i = 0; i < 256; i++) {
-            uint32_t c = i;
-            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-            t[i] = c;
-        }
+        uint32_t t[256 + bgzfdev::CRC_SHIFT_MATS * 32];
+        bamorch::crc32_tables(t, t + 256);
         BAM_CK(cudaSetDevice(ctx->device));
         BAM_CK(dev_alloc(&d_crc, sizeof(t)));
         BAM_CK(cudaMemcpy(d_crc, t, sizeof(t), cudaMemcpyHostToDevice));
@@ -256,7 +271,7 @@ struct BamGpuBackend {
             const int n = b1 - b0;
             const int64_t warps = (n + lanes - 1) / lanes;
             bam_inflate_kernel<<<(unsigned)((warps * 32 + BAM_TPB - 1) / BAM_TPB), BAM_TPB, 0, st[i]>>>(
-                n, d_blocks + b0, d_comp, d_ubuf, d_scratch + (size_t)b0 * bgzfdev::SCRATCH_STRIDE, d_crc, d_status + b0, lanes);
+                n, d_blocks + b0, d_comp, d_ubuf, d_scratch + (size_t)b0 * bgzfdev::SCRATCH_STRIDE, d_crc, d_crc + 256, d_status + b0, lanes);
             BAM_CK(cudaGetLastError());
             ctx->launches++;
             b0 = b1;

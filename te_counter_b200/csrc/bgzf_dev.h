@@ -333,6 +333,34 @@ BGZF_HD uint32_t crc32_block(const uint8_t* p, uint32_t n, const uint32_t* table
     return c ^ 0xFFFFFFFFu;
 }
 
+// CRC32 of a block by the 32 lanes of a warp: lane i runs the byte loop over its slice
+// [i * S, (i + 1) * S) (lane 0 starts from the standard initial state, the others from 0), moves its
+// result over the bytes behind its slice with the shift operators, and the XOR of the 32 results,
+// complemented, is the CRC32 of the block (CRC is linear over GF(2): crc(A || B) = shift(crc(A), |B|) ^ crc(B)).
+// shift_mats[k] = the 32x32 GF(2) matrix "append 2^k zero bytes", k = 0..16 (crc32_shift_matrices, host).
+constexpr int CRC_SHIFT_MATS = 17;
+
+BGZF_HD uint32_t crc32_shift(uint32_t crc, uint32_t n_bytes, const uint32_t* shift_mats) {
+    for (int k = 0; k < CRC_SHIFT_MATS; k++) {
+        if (!((n_bytes >> k) & 1)) continue;
+        const uint32_t* m = shift_mats + 32 * k;
+        uint32_t r = 0;
+        for (int bit = 0; bit < 32; bit++)
+            if ((crc >> bit) & 1) r ^= m[bit];
+        crc = r;
+    }
+    return crc;
+}
+
+// the share of lane `lane` (0..31); XOR the 32 shares and complement
+BGZF_HD uint32_t crc32_lane_share(const uint8_t* p, uint32_t n, int lane, const uint32_t* table, const uint32_t* shift_mats) {
+    const uint32_t S = (n + 31) / 32;
+    const uint32_t lo = (uint32_t)lane * S < n ? (uint32_t)lane * S : n, hi = lo + S < n ? lo + S : n;
+    uint32_t c = lane == 0 ? 0xFFFFFFFFu : 0u;
+    for (uint32_t i = lo; i < hi; i++) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    return crc32_shift(c, n - hi, shift_mats);
+}
+
 // ------------------------------------------------------------------------------------- records
 BGZF_HD uint32_t ld32(const uint8_t* p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 BGZF_HD uint32_t ld16(const uint8_t* p) { return p[0] | ((uint32_t)p[1] << 8); }

@@ -172,3 +172,11 @@ def test_block_inflate_equals_zlib(lib):
             if st == 0:
                 assert zlib.decompress(bytes(c), -15) == out[:n].tobytes()
     assert n_declined < 30
+
+
+def test_warp_crc32_equals_zlib(lib):
+    lib.bgzfdev_crc32_lanes.restype = ctypes.c_uint32
+    rng = np.random.default_rng(4)
+    for n in [0, 1, 2, 31, 32, 33, 63, 64, 65, 1000, 2047, 2048, 65279, 65280, 65535, 65536] + [int(x) for x in rng.integers(0, 65537, 40)]:
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert lib.bgzfdev_crc32_lanes(data, n) == (zlib.crc32(data) & 0xFFFFFFFF), n

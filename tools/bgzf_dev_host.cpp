@@ -22,16 +22,12 @@ struct HostBackend {
     std::vector<uint8_t> o_mapq, o_flag;
     std::vector<uint32_t> o_cell;
     std::vector<uint64_t> o_umi;
-    uint32_t crc_table[256];
+    uint32_t crc_table[256], crc_mats[bgzfdev::CRC_SHIFT_MATS * 32];
     int n_inflate_declined = 0;
     int force_decline_every = 0;                // test hook: pretend the block-parallel inflate declined every k-th block
 
     HostBackend() {
-        for (uint32_t i = 0; i < 256; i++) {
-            uint32_t c = i;
-            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-            crc_table[i] = c;
-        }
+        bamorch::crc32_tables(crc_table, crc_mats);
         scratch.resize(bgzfdev::SCRATCH_STRIDE);
     }
     int reserve(size_t comp_bytes, size_t ubuf_bytes, int) {
@@ -55,7 +51,11 @@ struct HostBackend {
         for (int b = 0; b < nb; b++) {          // one CUDA thread per b
             const bamorch::BlockDesc& d = bl[b];
             int st = bgzfdev::inflate_block(comp.data() + d.in_off, d.in_len, ubuf.data() + d.out_off, d.out_len, scratch.data());
-            if (st == bgzfdev::ST_OK && bgzfdev::crc32_block(ubuf.data() + d.out_off, d.out_len, crc_table) != d.crc) st = bgzfdev::ST_CRC;
+            if (st == bgzfdev::ST_OK) {         // the device computes it with the 32 lanes of the warp: same shares here, one after the other
+                uint32_t c = 0;
+                for (int lane = 0; lane < 32; lane++) c ^= bgzfdev::crc32_lane_share(ubuf.data() + d.out_off, d.out_len, lane, crc_table, crc_mats);
+                if ((c ^ 0xFFFFFFFFu) != d.crc || bgzfdev::crc32_block(ubuf.data() + d.out_off, d.out_len, crc_table) != d.crc) st = bgzfdev::ST_CRC;
+            }
             if (force_decline_every && b % force_decline_every == 0) {
                 memset(ubuf.data() + d.out_off, 0xAB, d.out_len);
                 st = bgzfdev::ST_DECLINED;
@@ -169,6 +169,20 @@ void bgzfdev_fetch(void* h, int32_t* start, int32_t* end, uint16_t* chrom, uint8
     memcpy(flag, b.o_flag.data(), n);
     if (cell && !b.o_cell.empty()) memcpy(cell, b.o_cell.data(), n * 4);
     if (umi && !b.o_umi.empty()) memcpy(umi, b.o_umi.data(), n * 8);
+}
+
+// CRC32 the way the warp computes it (32 lane shares), for holding it against zlib.crc32
+uint32_t bgzfdev_crc32_lanes(const void* p, int64_t n) {
+    static uint32_t table[256], mats[bgzfdev::CRC_SHIFT_MATS * 32];
+    static bool init = false;
+    if (!init) {
+        bamorch::crc32_tables(table, mats);
+        init = true;
+    }
+    uint8_t dummy = 0;
+    uint32_t c = 0;
+    for (int lane = 0; lane < 32; lane++) c ^= bgzfdev::crc32_lane_share(p ? (const uint8_t*)p : &dummy, (uint32_t)n, lane, table, mats);
+    return c ^ 0xFFFFFFFFu;
 }
 
 // the block inflate alone, for holding it against zlib
