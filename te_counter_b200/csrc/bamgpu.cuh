@@ -252,6 +252,7 @@ struct BamGpuBackend {
         const double t0 = now_ms();
         cudaStream_t st[2] = {ctx->stream, ctx->bam_stream2};
         BAM_CK(cudaMemcpyAsync(d_blocks, bl, sizeof(bamorch::BlockDesc) * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+        BAM_CK(cudaMemsetAsync(d_status, 0xFF, 4 * (size_t)nb, ctx->stream));      // a block no kernel reports on counts as declined
         BAM_CK(cudaEventRecord(ctx->bam_ev[2], ctx->stream));
         BAM_CK(cudaStreamWaitEvent(ctx->bam_stream2, ctx->bam_ev[2], 0));       // descriptors (and the window so far) are in place
         const int lanes = ctx->opt_bam_lanes;
