@@ -35,7 +35,9 @@ __global__ void bam_inflate_kernel(int nb, const bamorch::BlockDesc* __restrict_
         const bamorch::BlockDesc d = bl[warp];
         uint8_t* out = ubuf + d.out_off;
         int st = 0;
-        if (lane == 0) st = bgzfdev::inflate_block(comp + d.in_off, d.in_len, out, d.out_len, scratch + (size_t)warp * bgzfdev::SCRATCH_STRIDE);
+        // the decode tables of the warp's block live in shared memory (2.9 KB per warp): a lookup per symbol
+        extern __shared__ __align__(16) uint8_t bam_smem[];
+        if (lane == 0) st = bgzfdev::inflate_block(comp + d.in_off, d.in_len, out, d.out_len, bam_smem + (threadIdx.x >> 5) * bgzfdev::SCRATCH_STRIDE);
         __syncwarp();                                   // lane 0's stores are visible to the warp
         st = __shfl_sync(0xFFFFFFFFu, st, 0);
         if (st == bgzfdev::ST_OK) {
@@ -271,7 +273,8 @@ struct BamGpuBackend {
             BAM_CK(cudaEventRecord(ctx->bam_ev[i], st[i]));
             const int n = b1 - b0;
             const int64_t warps = (n + lanes - 1) / lanes;
-            bam_inflate_kernel<<<(unsigned)((warps * 32 + BAM_TPB - 1) / BAM_TPB), BAM_TPB, 0, st[i]>>>(
+            const size_t smem = lanes == 1 ? (size_t)(BAM_TPB / 32) * bgzfdev::SCRATCH_STRIDE : 0;
+            bam_inflate_kernel<<<(unsigned)((warps * 32 + BAM_TPB - 1) / BAM_TPB), BAM_TPB, smem, st[i]>>>(
                 n, d_blocks + b0, d_comp, d_ubuf, d_scratch + (size_t)b0 * bgzfdev::SCRATCH_STRIDE, d_crc, d_crc + 256, d_status + b0, lanes);
             BAM_CK(cudaGetLastError());
             ctx->launches++;
