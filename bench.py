@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--sorted", action="store_true", help="coordinate-sorted arrival order (bulk_se)")
     ap.add_argument("--sc-parity-records", type=int, default=20_000_000,
                     help="sc: records of the large parity check against the C++ oracle (0 = skip)")
+    ap.add_argument("--file-records", type=int, default=8_000_000,
+                    help="bulk: records of the synthetic BAM file of the from_file leg (0 = skip)")
     ap.add_argument("--opt", action="append", default=[], help="engine tuning knob key=value (tec_set_option)")
     return ap.parse_args()
 
@@ -387,6 +389,17 @@ def run_ours(args):
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity, "parity_full": parity_full,
             "stats": {"units": int(st[0]), "assigned": int(st[1]), "lowq": int(st[2]), "badchrom": int(st[3]),
                       "qcfail": int(st[4]), "counts_sum": int(counts.sum())}}
+    # ---- the same count from a BAM FILE on disk through the public call (measureTE.parse_bampe / parse_bamse): the
+    #      file decoded on the device (tec_bam_*), then by the host decoder (libtecbam), with the Python packing
+    #      both replace timed on a sample; results of the two decoders must be equal
+    from_file = None
+    if rank == 0 and world == 1 and not args.no_e2e and args.file_records > 0:
+        try:
+            from_file = file_leg(eng, idx, paired, args.file_records)
+        except Exception as e:                          # noqa: BLE001 -- an extra leg: report, do not lose the bench line
+            from_file = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    line["from_file"] = from_file
     if rank == 0:
         print(json.dumps(line))
     eng.close()
@@ -617,6 +630,59 @@ def run_ours_sc(args, rank, world, local, dev):
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def file_leg(eng, idx, paired, n_records):
+    """BAM file on disk -> counts through measureTE (wall clock around the public call, best of 3), per decoder."""
+    import logging
+    import tempfile
+    import te_counter_b200
+    from te_counter_b200 import bam as pybam, reads as treads, synth_bam
+    log = logging.getLogger("bench.file_leg")
+    log.addHandler(logging.NullHandler())
+    log.propagate = False
+    tmp = tempfile.mkdtemp(prefix="tec_bench_")
+    path = os.path.join(tmp, "synth.bam")
+    try:
+        size = synth_bam.write(path, n_records & ~1, "pe" if paired else "se")
+        mte = te_counter_b200.measureTE("bench", 20)
+        mte.genome = idx
+        mte.all_feature_names = idx.names
+        mte._engine_obj = eng
+        mte._index_on_device = True
+        out = {"records": n_records & ~1, "file_bytes": size, "host_cores": os.cpu_count(),
+               "api": "measureTE.parse_bampe(file)" if paired else "measureTE.parse_bamse(file)"}
+        results = {}
+        old = os.environ.get("TEC_BAM_DECODER")
+        try:
+            for dec, key in (("gpu", "device_decoder"), ("native", "host_decoder")):
+                os.environ["TEC_BAM_DECODER"] = dec
+                best = None
+                for _ in range(3):
+                    ta = time.perf_counter()
+                    res = (mte.parse_bampe if paired else mte.parse_bamse)(path, log=log)
+                    dt = time.perf_counter() - ta
+                    best = dt if best is None else min(best, dt)
+                results[dec] = res
+                out[key] = {"records_per_s": (n_records & ~1) / best, "seconds": best}
+        finally:
+            if old is None:
+                os.environ.pop("TEC_BAM_DECODER", None)
+            else:
+                os.environ["TEC_BAM_DECODER"] = old
+        out["decoders_agree"] = results["gpu"] == results["native"]
+        assert out["decoders_agree"], "device and host BAM decoders disagree"
+        f = pybam.AlignmentFile(path, "r")
+        b = treads.Batch(200000)
+        ta = time.perf_counter()
+        treads.fill_bulk(b, f, treads.ChromMap(idx.chrom_keys), paired, 20)
+        out["python_packing"] = {"records_per_s": b.n / (time.perf_counter() - ta), "sample_records": b.n, "cores": 1,
+                                 "what": "bam.py + reads.fill_bulk, the stand-in for the reference's pysam loop"}
+        f.close()
+        return out
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def main():

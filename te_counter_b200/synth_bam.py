@@ -1,9 +1,10 @@
-"""Writes a synthetic BGZF-compressed BAM of fixed-layout records, fast (numpy builds the record
-bytes, a process pool deflates the blocks), for measuring the host decoder (tools/bam_bench.py)
-and file-to-TSV runs of measureTE.  Records look like 10x / bulk RNA-seq alignments: 100 bp reads,
-CIGAR 100M or 40M<gap>N60M, 4-bit packed random sequence, skewed qualities, NH/AS/CB/UB tags.
+"""Synthetic workload, file form: writes a BGZF-compressed BAM of fixed-layout records, fast (numpy
+builds the record bytes, a process pool deflates the blocks), for measuring the BAM decoders
+(tools/bam_bench.py), file-to-result runs of measureTE (tools/file_e2e.py) and the `from_file` leg
+of bench.py.  Records look like 10x / bulk RNA-seq alignments: 100 bp reads, CIGAR 40M<gap>N60M,
+4-bit packed random sequence, skewed qualities, NH/AS/CB/UB tags.
 
-    python tools/make_synth_bam.py out.bam --records 4000000 --mode sc --whitelist wl.txt
+    python -m te_counter_b200.synth_bam out.bam --records 4000000 --mode sc --whitelist wl.txt
 """
 import argparse
 import os
@@ -13,8 +14,6 @@ import zlib
 from concurrent.futures import ProcessPoolExecutor
 
 import numpy as np
-
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 HG38 = [("chr%s" % c, n) for c, n in zip(
     list(range(1, 23)) + ["X", "Y", "M"],
@@ -128,6 +127,26 @@ def _chunk(job):
     return _deflate_chunk(records_bytes(rng, n, HG38, mode, barcodes, i * 250000).tobytes())
 
 
+def write(out, records=4000000, mode="pe", whitelist=None, n_barcodes=100000, seed=20261018, procs=None):
+    """Writes the file; returns its size in bytes."""
+    rng = np.random.default_rng(seed)
+    barcodes = None
+    if mode == "sc":
+        barcodes = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (n_barcodes, 16))]
+        barcodes = np.unique(barcodes, axis=0)
+        if whitelist:
+            with open(whitelist, "w") as fh:
+                fh.write("".join(bytes(b).decode() + "-1\n" for b in barcodes))
+    chunk = 250000
+    jobs = [(seed, i, min(chunk, records - i * chunk), mode, barcodes) for i in range((records + chunk - 1) // chunk)]
+    with open(out, "wb") as fh, ProcessPoolExecutor(procs or os.cpu_count() or 1) as ex:
+        fh.write(_bgzf(header_bytes(HG38)))
+        for comp in ex.map(_chunk, jobs):                   # records straddle blocks inside a chunk
+            fh.write(comp)
+        fh.write(_bgzf(b""))
+    return os.path.getsize(out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("out")
@@ -138,22 +157,8 @@ def main():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--procs", type=int, default=os.cpu_count() or 1)
     a = ap.parse_args()
-    rng = np.random.default_rng(a.seed)
-    barcodes = None
-    if a.mode == "sc":
-        barcodes = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (a.barcodes, 16))]
-        barcodes = np.unique(barcodes, axis=0)
-        if a.whitelist:
-            with open(a.whitelist, "w") as fh:
-                fh.write("".join(bytes(b).decode() + "-1\n" for b in barcodes))
-    chunk = 250000
-    jobs = [(a.seed, i, min(chunk, a.records - i * chunk), a.mode, barcodes) for i in range((a.records + chunk - 1) // chunk)]
-    with open(a.out, "wb") as fh, ProcessPoolExecutor(a.procs) as ex:
-        fh.write(_bgzf(header_bytes(HG38)))
-        for comp in ex.map(_chunk, jobs):                   # records straddle blocks inside a chunk
-            fh.write(comp)
-        fh.write(_bgzf(b""))
-    print(a.out, os.path.getsize(a.out), "bytes,", a.records, "records")
+    size = write(a.out, a.records, a.mode, a.whitelist, a.barcodes, a.seed, a.procs)
+    print(a.out, size, "bytes,", a.records, "records")
 
 
 if __name__ == "__main__":

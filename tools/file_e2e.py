@@ -52,8 +52,8 @@ def main():
     path = os.path.join(a.dir, "tec_synth_%s.bam" % a.mode)
     wlf = os.path.join(a.dir, "tec_synth_wl.txt")
     t0 = time.perf_counter()
-    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synth_bam.py"), path, "--records", str(a.records),
-                    "--mode", a.mode, "--whitelist", wlf], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([sys.executable, "-m", "te_counter_b200.synth_bam", path, "--records", str(a.records),
+                    "--mode", a.mode, "--whitelist", wlf], check=True, stdout=subprocess.DEVNULL, cwd=ROOT)
     t_make = time.perf_counter() - t0
     idx = synth.synth_index()
     log = logging.getLogger("file_e2e")
