@@ -121,7 +121,8 @@ int64_t tec_launch_count(const tec_ctx* ctx);
 int tec_trim(tec_ctx* ctx);
 
 /* tuning knobs: "bulk_algo" (-1 auto, 0 exact search kernel, 1 cell-table kernel), "stab_shift"
- * (log2 of the cell size, 8..11, used by the next tec_index_upload), "ctas_per_sm", "all_hot" (counters
+ * (log2 of the cell size, 8..11, or 0 = default: 10 for bulk, 11 for the single-cell pair table; used by the
+ * next tec_index_upload), "ctas_per_sm", "all_hot" (counters
  * of every ensg in shared memory when they fit), "sc_algo" (-1 auto, 0 exact search in Part 3, 1 cell
  * table), "sc_pack_umi" (2-bit UMI sort keys when possible).
  * tec_get_info: "has_stab", "stab_bytes", "has_sc_stab", "sc_stab_bytes", "n_sm", "n_features",

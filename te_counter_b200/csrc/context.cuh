@@ -109,6 +109,11 @@ struct DevCache {
     }
 };
 
+// log2 of the cell size of the two cell tables.  Bulk: 1 kbp cells (104 MB for the hg38-like index) measured
+// 125.9e9 records/s against 121.1e9 with 2 kbp cells (65 MB): fewer overflow sectors outweigh the extra L2 misses.
+#define TEC_BULK_STAB_SHIFT 10
+#define TEC_SC_STAB_SHIFT 11
+
 struct tec_ctx {
     int device = 0;
     int n_sm = 148;
@@ -135,7 +140,7 @@ struct tec_ctx {
     std::vector<int32_t> ensg_of_slot;    // slot = rank of an ensg by number of feature rows
     // options (tec_set_option)
     int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 stab-table kernel
-    int opt_stab_shift = 11;
+    int opt_stab_shift = 0;               // log2 of the cell size; 0 = TEC_BULK_STAB_SHIFT / TEC_SC_STAB_SHIFT
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
     int opt_sc_pack_umi = 1;              // single cell: 2-bit UMI sort keys when every UMI is fixed-length ACGT
     int opt_sc_algo = -1;                 // -1 auto, 0 exact search only, 1 cell table

@@ -214,7 +214,7 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
     // cell table for the bulk fast path
     {
         StabTable st;
-        stab_build(st, n_chrom, chrom_off, L, R, fslot.data(), type_code, n_ensg, ctx->opt_stab_shift);
+        stab_build(st, n_chrom, chrom_off, L, R, fslot.data(), type_code, n_ensg, ctx->opt_stab_shift ? ctx->opt_stab_shift : TEC_BULK_STAB_SHIFT);
         if (st.why_not.empty()) {
             TEC_CUDA(cudaMalloc(&ix.st_sectors, std::max<size_t>(st.sectors.size(), 8) * 4));
             std::vector<uint2> cells((size_t)n_chrom + 1, make_uint2(0u, 0u));      // + sentinel for ids outside the index
@@ -256,7 +256,7 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
                 R1[(size_t)i] = (floordiv(R[i], bucket_size) < L[i] / bucket_size) ? L1[(size_t)i] : R[i] + 1;
             }
             StabTable st;
-            stab_build(st, n_chrom, chrom_off, L1.data(), R1.data(), pslot.data(), type_code, (int)uniq.size(), ctx->opt_stab_shift);
+            stab_build(st, n_chrom, chrom_off, L1.data(), R1.data(), pslot.data(), type_code, (int)uniq.size(), ctx->opt_stab_shift ? ctx->opt_stab_shift : TEC_SC_STAB_SHIFT);
             if (st.why_not.empty()) {
                 std::vector<uint2> cells((size_t)std::max(n_chrom, 1));
                 for (int c = 0; c < n_chrom; ++c)
@@ -462,7 +462,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return TEC_ERR_ARG;
     const std::string k(key);
     if (k == "bulk_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "bulk_algo: -1, 0 or 1"); ctx->opt_bulk_algo = (int)value; }
-    else if (k == "stab_shift") { if (value < 8 || value > STAB_MAX_SHIFT) TEC_FAIL(TEC_ERR_ARG, "stab_shift: 8..11"); ctx->opt_stab_shift = (int)value; }
+    else if (k == "stab_shift") { if (value && (value < 8 || value > STAB_MAX_SHIFT)) TEC_FAIL(TEC_ERR_ARG, "stab_shift: 0 (default) or 8..11"); ctx->opt_stab_shift = (int)value; }
     else if (k == "sc_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "sc_algo: -1, 0 or 1"); ctx->opt_sc_algo = (int)value; }
     else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
     else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }

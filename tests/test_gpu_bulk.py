@@ -46,7 +46,7 @@ def test_bulk_matches_oracle_seeded(engine, paired, seed, algo, shift):
         (os_["assigned"], os_["lowq"], os_["badchrom"], os_["qcfail"])
     assert counts.sum() > 1000
     engine.set_option("bulk_algo", -1)
-    engine.set_option("stab_shift", 11)
+    engine.set_option("stab_shift", 0)
 
 
 @pytest.mark.parametrize("algo", [0, 1])
