@@ -180,3 +180,26 @@ def test_warp_crc32_equals_zlib(lib):
     for n in [0, 1, 2, 31, 32, 33, 63, 64, 65, 1000, 2047, 2048, 65279, 65280, 65535, 65536] + [int(x) for x in rng.integers(0, 65537, 40)]:
         data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
         assert lib.bgzfdev_crc32_lanes(data, n) == (zlib.crc32(data) & 0xFFFFFFFF), n
+
+
+@pytest.mark.parametrize("mode", ["se", "pe", "sc"])
+@pytest.mark.parametrize("window_blocks", [3, 1 << 16])
+def test_committed_bam_fixtures(lib, mode, window_blocks):
+    """The block-parallel decoder against the committed fixtures of tests/make_bam_golden.py (arrays of the
+    Python packing); ids of chromosomes outside the index are compared up to renaming, as in test_fastbam."""
+    from test_fastbam import _canon_chrom
+    want = np.load(os.path.join(H.GOLD, "bam_mixed_expected.npz"))
+    idx = H.load_index("idx_rand_a.glb")
+    wl = reads.Whitelist(os.path.join(H.GOLD, "bam_mixed_whitelist.txt")) if mode == "sc" else None
+    rc, _, got = _decode(lib, os.path.join(H.GOLD, "bam_mixed_%s.bam" % mode), mode, reads.ChromMap(idx.chrom_keys), wl, 20, window_blocks)
+    assert rc == 0 and len(got["start"]) == 600
+
+    class _B:
+        pass
+    a, b = _B(), _B()
+    a.n = b.n = 600
+    a.chrom, b.chrom = want["%s_chrom" % mode], got["chrom"]
+    n_index = len(idx.chrom_keys)
+    assert np.array_equal(_canon_chrom([(a, False)], n_index)[0], _canon_chrom([(b, False)], n_index)[0])
+    for k in ("start", "end", "mapq", "flag") + (("cell", "umi") if mode == "sc" else ()):
+        assert np.array_equal(want["%s_%s" % (mode, k)], got[k]), k

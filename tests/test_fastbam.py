@@ -348,3 +348,24 @@ def test_decoder_selection(monkeypatch, tmp_path):
     monkeypatch.setenv("TEC_BAM_DECODER", "native")
     with pytest.raises(fastbam.NotBgzf):
         tc._open_alignment(s)
+
+
+@pytest.mark.parametrize("mode", ["se", "pe", "sc"])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_committed_bam_fixtures(mode, threads):
+    """tests/golden/bam_mixed_*.bam against the committed arrays of the Python packing
+    (tests/make_bam_golden.py)."""
+    want = np.load(os.path.join(H.GOLD, "bam_mixed_expected.npz"))
+    idx = H.load_index("idx_rand_a.glb")
+    wl = reads.Whitelist(os.path.join(H.GOLD, "bam_mixed_whitelist.txt")) if mode == "sc" else None
+    nat = _native_batches(os.path.join(H.GOLD, "bam_mixed_%s.bam" % mode), mode, reads.ChromMap(idx.chrom_keys), wl, 20, 1024, threads)
+    b = nat[0][0]
+    assert b.n == 600 and nat[0][1] is False
+
+    class _B:
+        pass
+    w = _B()
+    w.n = 600
+    for k in COLS + (("cell", "umi") if mode == "sc" else ()):
+        setattr(w, k, want["%s_%s" % (mode, k)])
+    _same([(w, False)], nat, mode == "sc", len(idx.chrom_keys))
