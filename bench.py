@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--sc-parity-records", type=int, default=20_000_000,
                     help="sc: records of the large parity check against the C++ oracle (0 = skip)")
     ap.add_argument("--file-records", type=int, default=8_000_000,
-                    help="bulk: records of the synthetic BAM file of the from_file leg (0 = skip)")
+                    help="records of the synthetic BAM file of the from_file leg (0 = skip)")
     ap.add_argument("--opt", action="append", default=[], help="engine tuning knob key=value (tec_set_option)")
     return ap.parse_args()
 
@@ -622,6 +622,13 @@ def run_ours_sc(args, rank, world, local, dev):
                       "segments": int(st[_lib.SS_SEGMENTS]), "bundles": int(st[_lib.SS_BUNDLES]),
                       "valid": int(st[_lib.SS_VALID]), "assigned": int(st[_lib.SS_ASSIGNED]),
                       "triples": int(nt), "hit_cells": int(nh), "selected": int(len(sel))}}
+    from_file = None
+    if rank == 0 and world == 1 and not args.no_e2e and args.file_records > 0:
+        try:
+            from_file = file_leg(eng, idx, False, args.file_records, sc={"strand": strand, "maxcells": maxcells})
+        except Exception as e:                          # noqa: BLE001 -- an extra leg: report, do not lose the bench line
+            from_file = {"error": "%s: %s" % (type(e).__name__, e)}
+    line["from_file"] = from_file
     if os.environ.get("TEC_DIST_TIMING"):
         line["phase_s_last_step"] = phase
         line["exchange_s_total"] = dict(tdist.TIMING)
@@ -632,8 +639,9 @@ def run_ours_sc(args, rank, world, local, dev):
         dist.destroy_process_group()
 
 
-def file_leg(eng, idx, paired, n_records):
-    """BAM file on disk -> counts through measureTE (wall clock around the public call, best of 3), per decoder."""
+def file_leg(eng, idx, paired, n_records, sc=None):
+    """BAM file on disk -> counts through measureTE (wall clock around the public call, best of 3), per decoder.
+    sc = dict(strand, maxcells) for the single-cell call."""
     import logging
     import tempfile
     import te_counter_b200
@@ -644,14 +652,16 @@ def file_leg(eng, idx, paired, n_records):
     tmp = tempfile.mkdtemp(prefix="tec_bench_")
     path = os.path.join(tmp, "synth.bam")
     try:
-        size = synth_bam.write(path, n_records & ~1, "pe" if paired else "se")
+        wlf = os.path.join(tmp, "whitelist.txt")
+        size = synth_bam.write(path, n_records & ~1, "sc" if sc else "pe" if paired else "se", whitelist=wlf)
         mte = te_counter_b200.measureTE("bench", 20)
         mte.genome = idx
         mte.all_feature_names = idx.names
         mte._engine_obj = eng
         mte._index_on_device = True
+        mte.load_genome = lambda: None                  # (sc_parse_bamse reloads the .glb; the synthetic index has none)
         out = {"records": n_records & ~1, "file_bytes": size, "host_cores": os.cpu_count(),
-               "api": "measureTE.parse_bampe(file)" if paired else "measureTE.parse_bamse(file)"}
+               "api": "measureTE.sc_parse_bamse(file)" if sc else "measureTE.parse_bampe(file)" if paired else "measureTE.parse_bamse(file)"}
         results = {}
         old = os.environ.get("TEC_BAM_DECODER")
         try:
@@ -660,7 +670,12 @@ def file_leg(eng, idx, paired, n_records):
                 best = None
                 for _ in range(3):
                     ta = time.perf_counter()
-                    res = (mte.parse_bampe if paired else mte.parse_bamse)(path, log=log)
+                    if sc:
+                        r = mte.sc_parse_bamse(path, whitelistfilename=wlf, strand=sc["strand"], log=log, label="bench",
+                                               maxcells=sc["maxcells"])
+                        res = (r.ensg.tolist(), r.cell.tolist(), r.count.tolist(), dict(mte.barcodes))
+                    else:
+                        res = (mte.parse_bampe if paired else mte.parse_bamse)(path, log=log)
                     dt = time.perf_counter() - ta
                     best = dt if best is None else min(best, dt)
                 results[dec] = res
@@ -673,11 +688,14 @@ def file_leg(eng, idx, paired, n_records):
         out["decoders_agree"] = results["gpu"] == results["native"]
         assert out["decoders_agree"], "device and host BAM decoders disagree"
         f = pybam.AlignmentFile(path, "r")
-        b = treads.Batch(200000)
+        b = treads.Batch(200000, sc=bool(sc))
         ta = time.perf_counter()
-        treads.fill_bulk(b, f, treads.ChromMap(idx.chrom_keys), paired, 20)
+        if sc:
+            treads.fill_sc(b, f, treads.ChromMap(idx.chrom_keys), treads.Whitelist(wlf), 20)
+        else:
+            treads.fill_bulk(b, f, treads.ChromMap(idx.chrom_keys), paired, 20)
         out["python_packing"] = {"records_per_s": b.n / (time.perf_counter() - ta), "sample_records": b.n, "cores": 1,
-                                 "what": "bam.py + reads.fill_bulk, the stand-in for the reference's pysam loop"}
+                                 "what": "bam.py + reads.fill_*, the stand-in for the reference's pysam loop"}
         f.close()
         return out
     finally:
