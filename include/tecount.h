@@ -231,7 +231,11 @@ int tec_sc_matrix_read(tec_ctx *ctx, int64_t offset, int64_t n, char *out);
  * exact check of the record chain).  Usage: tec_bam_open, read the reference names, tec_bam_set_chrom_map
  * (and tec_bam_set_whitelist) exactly as for tbam_*, tec_bulk_begin / tec_sc_begin, tec_bam_count (decodes
  * the whole file into the running count), tec_bulk_finish / tec_sc_finalize, tec_bam_close.
- * mode: 0 single end, 1 paired end, 2 single cell.  On TEC_ERR_UNSUPPORTED start over with libtecbam. */
+ * mode: 0 single end, 1 paired end, 2 single cell.  On TEC_ERR_UNSUPPORTED start over with libtecbam.
+ * Options (tec_set_option): "bam_window_blocks" (BGZF blocks per pass, default 65536: 4.3 GB of inflated bytes
+ * in HBM), "bam_lanes" (blocks decoded per warp, default 1).  Limits shared with libtecbam: reference_end comes
+ * from the CIGAR field of the record (alignments of more than 65535 operations, which BAM moves to a CG tag, are
+ * not expanded); tag values are compared as bytes. */
 typedef struct tec_bam tec_bam;
 int tec_bam_open(tec_ctx *ctx, const char *path, tec_bam **out);
 void tec_bam_close(tec_bam *b);
