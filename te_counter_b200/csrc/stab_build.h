@@ -46,7 +46,9 @@
 #include <vector>
 
 #define STAB_ENTRIES 5
+#ifndef STAB_EXT
 #define STAB_EXT 256                     // a cell's entries also cover the first STAB_EXT bp of the next cell
+#endif                                   // (A/B on the 500 M-record config, 1 kbp cells: 128 -> 121.8e9, 256 -> 125.5e9, 384 -> 124.7e9 records/s)
 #define STAB_MAX_SHIFT 11
 #define STAB_MAX_SLOTS 65535
 #define STAB_BLOCK_SHIFT 7               // ovf_base granularity: 128 primary sectors
