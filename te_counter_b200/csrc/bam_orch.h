@@ -332,7 +332,12 @@ int decode_all(Reader& r, Backend& be, int mode, int qual, int window_blocks, in
                 c.start = bgzfdev::NO_START;
                 continue;
             }
-            if (c.start != expect) return r.fail(E_UNSUPPORTED, "record boundaries could not be established block-parallel");
+            if (c.start != expect) {
+                char buf[160];
+                snprintf(buf, sizeof buf, "record boundaries could not be established block-parallel (block %d of the window: guess %lld, chain %lld)",
+                         b, (long long)c.start, (long long)expect);
+                return r.fail(E_UNSUPPORTED, buf);
+            }
             if (c.bad) return r.fail(E_FORMAT, "alignment record with impossible block_size");
             n_rec += c.count;
             if (c.count) last_used = b;

@@ -368,7 +368,11 @@ BGZF_HD uint32_t ld16(const uint8_t* p) { return p[0] | ((uint32_t)p[1] << 8); }
 constexpr int64_t NO_START = -1;
 constexpr uint32_t MAX_BLOCK_SIZE = 1u << 28;
 
-// Does a complete, well-formed looking alignment record start at w[p]?  (w_end = bytes in the window)
+// Does a well-formed looking alignment record start at w[p]?  (w_end = bytes in the window.)  Checks the
+// fixed fields, the read name ([!-~]+ and its NUL) and walks the optional fields: they must be
+// well-formed and end exactly where block_size says -- as far as the window reaches.  This is only
+// the GUESS of the block-parallel split (bam_orch.h verifies the chain exactly); the stricter it
+// is, the fewer files are refused.
 BGZF_HD bool plausible(const uint8_t* w, int64_t p, int64_t w_end, int32_t n_ref) {
     if (p + 36 > w_end) return false;
     const uint32_t bs = ld32(w + p);
@@ -381,7 +385,45 @@ BGZF_HD bool plausible(const uint8_t* w, int64_t p, int64_t w_end, int32_t n_ref
     if (l_name < 1 || l_seq < 0) return false;
     const uint64_t fixed = 32ull + l_name + 4ull * n_cig + (uint64_t)((l_seq + 1) / 2) + (uint64_t)l_seq;
     if (fixed > bs) return false;
-    if (p + 4 + 32 + (int64_t)l_name <= w_end && r[32 + l_name - 1] != 0) return false;     // name is NUL-terminated
+    const int64_t limit = w_end - (p + 4);              // bytes of this record the window holds
+    for (uint32_t i = 0; i < l_name && 32 + (int64_t)i < limit; i++) {
+        const uint8_t ch = r[32 + i];
+        if (i + 1 == l_name ? ch != 0 : (ch < 0x21 || ch > 0x7E)) return false;
+    }
+    for (uint32_t i = 0; i < n_cig && 32 + (int64_t)l_name + 4 * (int64_t)i + 4 <= limit; i++)
+        if ((ld32(r + 32 + l_name + 4 * i) & 15) > 8) return false;         // CIGAR operations are 0..8
+    // optional fields: tag, type, value ... up to block_size
+    int64_t a = (int64_t)fixed;
+    const int64_t end = (int64_t)bs;
+    while (a < end) {
+        if (a + 3 > limit) return true;                 // the window ends here: consistent so far
+        if (a + 3 > end) return false;
+        const uint8_t ty = r[a + 2];
+        a += 3;
+        int64_t adv;
+        if (ty == 'A' || ty == 'c' || ty == 'C') adv = 1;
+        else if (ty == 's' || ty == 'S') adv = 2;
+        else if (ty == 'i' || ty == 'I' || ty == 'f') adv = 4;
+        else if (ty == 'Z' || ty == 'H') {
+            int64_t z = a;
+            while (z < end && z < limit && r[z]) z++;
+            if (z >= end) return false;
+            if (z >= limit) return true;
+            adv = z - a + 1;
+        } else if (ty == 'B') {
+            if (a + 5 > end) return false;
+            if (a + 5 > limit) return true;
+            const uint8_t st = r[a];
+            int64_t sz;
+            if (st == 'c' || st == 'C') sz = 1;
+            else if (st == 's' || st == 'S') sz = 2;
+            else if (st == 'i' || st == 'I' || st == 'f') sz = 4;
+            else return false;
+            adv = 5 + sz * (int64_t)ld32(r + a + 1);
+        } else return false;
+        if (adv > end - a) return false;
+        a += adv;
+    }
     return true;
 }
 

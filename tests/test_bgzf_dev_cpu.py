@@ -203,3 +203,57 @@ def test_committed_bam_fixtures(lib, mode, window_blocks):
     assert np.array_equal(_canon_chrom([(a, False)], n_index)[0], _canon_chrom([(b, False)], n_index)[0])
     for k in ("start", "end", "mapq", "flag") + (("cell", "umi") if mode == "sc" else ()):
         assert np.array_equal(want["%s_%s" % (mode, k)], got[k]), k
+
+
+def _split_blocks(raw):
+    out, o = [], 0
+    while o < len(raw):
+        n = int.from_bytes(raw[o + 16:o + 18], "little") + 1
+        out.append(raw[o:o + n])
+        o += n
+    return out
+
+
+def test_header_over_many_blocks_empty_blocks_and_no_references(lib, tmp_path):
+    """Layouts around the records: a header much longer than a block (3000 reference sequences), empty
+    BGZF blocks in the middle of the file, a file without reference sequences (all reads unmapped)."""
+    from bam_writer import _bgzf_block
+    rng = np.random.default_rng(12)
+    recs = [{"chrom": "contig_%04d" % int(rng.integers(3000)), "start": int(rng.integers(1, 50000)), "end": 0,
+             "flag": int(rng.choice([0, 16, 1024]))} for _ in range(4000)]
+    for r in recs:
+        r["end"] = r["start"] + 76
+    recs += [{"chrom": "contig_%04d" % i, "start": 5, "end": 90} for i in range(3000)]      # every contig in the header
+    path = str(tmp_path / "many.bam")
+    write_bam(path, recs, block=500)
+    blocks = _split_blocks(open(path, "rb").read())
+    with_empty = []
+    for i, b in enumerate(blocks):
+        with_empty.append(b)
+        if i % 7 == 3:
+            with_empty.append(_bgzf_block(b""))
+    open(path, "wb").write(b"".join(with_empty))
+    keys = ["contig_%04d" % i for i in range(0, 3000, 3)]
+    want = _native(path, "se", reads.ChromMap(keys), None, 0)
+    assert len(want["start"]) == 7000
+    for wb in (1, 64, 1 << 16):
+        rc, msg, got = _decode(lib, path, "se", reads.ChromMap(keys), None, 0, wb)
+        assert rc == 0, (wb, msg)
+        from test_fastbam import _canon_chrom
+
+        class _B:
+            pass
+        a, b = _B(), _B()
+        a.n = b.n = 7000
+        a.chrom, b.chrom = want["chrom"], got["chrom"]
+        assert np.array_equal(_canon_chrom([(a, False)], len(keys))[0], _canon_chrom([(b, False)], len(keys))[0])
+        for k in ("start", "end", "mapq", "flag"):
+            assert np.array_equal(want[k], got[k]), (k, wb)
+    # no reference sequences at all
+    path2 = str(tmp_path / "unaligned.bam")
+    write_bam(path2, [{"chrom": None, "start": -1, "end": -1, "flag": 4 | (77 if i % 2 == 0 else 141)} for i in range(501)], block=333)
+    want = _native(path2, "pe", reads.ChromMap(["1"]), None, 20)
+    rc, _, got = _decode(lib, path2, "pe", reads.ChromMap(["1"]), None, 20, 2)
+    assert rc == 0 and len(got["start"]) == 500
+    for k in want:
+        assert np.array_equal(want[k], got[k]), k
