@@ -34,15 +34,9 @@ MAX_ENSG = 1 << 24                       # ensg id field width in the packed dev
 
 
 class _Bag:
-    """Attribute bag standing in for genelist / location instances while unpickling."""
-
-    def __setstate__(self, state):
-        if isinstance(state, dict):
-            self.__dict__.update(state)
-        elif isinstance(state, tuple) and len(state) == 2:       # (dict, slots)
-            for part in state:
-                if part:
-                    self.__dict__.update(part)
+    """Attribute bag standing in for genelist / location instances while unpickling.  No
+    __setstate__: the C unpickler then restores the instance dict (and a (dict, slots) pair) itself,
+    which is ~6 us per feature cheaper than a Python-level call."""
 
 
 class _Genelist(_Bag):
@@ -147,26 +141,60 @@ def _read_pickle(path):
 
 def verify_buckets(gl_buckets, chrom_str, L, R, bs=BUCKET_SIZE):
     """Check the pickled bucket hash == {b*bs: [n : L[n]//bs <= b <= R[n]//bs]} per chromosome
-    (miniglbase/genelist.py:367-380).  Raises ValueError when it is anything else."""
+    (miniglbase/genelist.py:367-380).  Raises ValueError when it is anything else.
+
+    One flat pass: every (chromosome, bucket, feature id) entry of the hash goes into three arrays
+    (C-level iteration over the dict values), then the membership rule, the chromosome key, the
+    absence of duplicates and the total are checked with array operations -- a genome-scale index
+    has ~300 k buckets, a Python loop over them cost more than the unpickling."""
+    from itertools import chain
     n = len(L)
     L = np.asarray(L, dtype=np.int64)
     R = np.asarray(R, dtype=np.int64)
     expected_total = int(np.sum(R // bs - L // bs + 1)) if n else 0
-    total = 0
+    chrom_code = {}
+    feat_chrom = np.fromiter((chrom_code.setdefault(c, len(chrom_code)) for c in chrom_str), dtype=np.int64, count=n)
+    b_key, b_chrom, b_len = [], [], []
+    flat = []
     for chrom, bdict in gl_buckets.items():
-        for b, ids in bdict.items():
-            ids = np.asarray(ids, dtype=np.int64)
-            total += len(ids)
-            if len(ids) == 0:
-                continue
-            if len(np.unique(ids)) != len(ids) or ids.min() < 0 or ids.max() >= n:
-                raise ValueError("bucket %s:%s holds duplicate or out-of-range feature ids" % (chrom, b))
-            ok = ((L[ids] // bs) * bs <= b) & (b <= (R[ids] // bs) * bs)
-            if not ok.all() or (b % bs) != 0:
-                raise ValueError("bucket %s:%s is not the 10 kb bucket hash of its features" % (chrom, b))
-            for i in ids[:1]:
-                if chrom_str[int(i)] != chrom:
-                    raise ValueError("bucket chromosome key %r does not match its features" % (chrom,))
+        code = chrom_code.get(chrom, -1)
+        m = len(bdict)
+        if not m:
+            continue
+        try:
+            keys = np.fromiter(bdict.keys(), dtype=np.int64, count=m)
+        except (TypeError, ValueError):
+            raise ValueError("bucket keys of chromosome %r are not integers" % (chrom,))
+        b_key.append(keys)
+        b_chrom.append(np.full(m, code, dtype=np.int64))
+        b_len.append(np.fromiter(map(len, bdict.values()), dtype=np.int64, count=m))
+        flat.append(bdict.values())
+    if not b_key:
+        if expected_total:
+            raise ValueError("bucket hash has 0 entries, closed form expects %d (bucket_size mismatch?)" % expected_total)
+        return
+    b_key, b_chrom, b_len = np.concatenate(b_key), np.concatenate(b_chrom), np.concatenate(b_len)
+    total = int(b_len.sum())
+    try:
+        ids = np.fromiter(chain.from_iterable(chain.from_iterable(flat)), dtype=np.int64, count=total)
+    except (TypeError, ValueError):
+        raise ValueError("bucket hash holds something that is not a feature id")
+    which = np.repeat(np.arange(len(b_key)), b_len)            # bucket of every entry
+    if total and (ids.min() < 0 or ids.max() >= n):
+        bad = which[np.flatnonzero((ids < 0) | (ids >= n))[0]]
+        raise ValueError("bucket %s holds duplicate or out-of-range feature ids" % (int(b_key[bad]),))
+    if (b_key % bs).any():
+        raise ValueError("bucket %s is not the 10 kb bucket hash of its features" % (int(b_key[np.flatnonzero(b_key % bs)[0]]),))
+    eb = b_key[which]
+    ok = ((L[ids] // bs) * bs <= eb) & (eb <= (R[ids] // bs) * bs)
+    if not ok.all():
+        raise ValueError("bucket %s is not the 10 kb bucket hash of its features" % (int(eb[np.flatnonzero(~ok)[0]]),))
+    wrong = feat_chrom[ids] != b_chrom[which]
+    if wrong.any():
+        raise ValueError("bucket chromosome key does not match its features (bucket %s)" % (int(eb[np.flatnonzero(wrong)[0]]),))
+    pair = which * np.int64(max(n, 1)) + ids
+    if len(np.unique(pair)) != total:
+        raise ValueError("a bucket holds duplicate or out-of-range feature ids")
     if total != expected_total:
         raise ValueError("bucket hash has %d entries, closed form expects %d (bucket_size mismatch?)"
                          % (total, expected_total))
