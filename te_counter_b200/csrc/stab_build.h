@@ -43,6 +43,8 @@
 #include <stdint.h>
 #include <algorithm>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #define STAB_ENTRIES 5
@@ -116,24 +118,28 @@ inline void stab_build(StabTable& t, int n_chrom, const int64_t* chrom_off, cons
     }
     t.n_primary = t.cell_base[(size_t)n_chrom];
     if ((uint64_t)t.n_primary >= 0xFFFFFFF0ull) { t.why_not = "too many cells"; return; }
-    // entries: per chromosome, per slot union of [L, R), clipped to cells
+    // entries: per chromosome, per slot union of [L, R), clipped to cells.  Chromosomes own disjoint,
+    // ascending cell ranges, so each one is built and sorted on its own (a thread per chromosome at a
+    // time) and the concatenation in chromosome order is the globally sorted list.
     struct Iv { uint32_t slot; int32_t L, R; };
-    std::vector<Iv> iv;
-    std::vector<StabEntry> ent;
-    ent.reserve((size_t)chrom_off[n_chrom] + (size_t)chrom_off[n_chrom] / 4);
-    for (int c = 0; c < n_chrom; ++c) {
-        iv.clear();
+    std::vector<std::vector<StabEntry>> per((size_t)n_chrom);
+    std::vector<int64_t> merged((size_t)n_chrom, 0);
+    auto build_chrom = [&](int c) {
+        std::vector<Iv> iv;
+        std::vector<StabEntry>& ent = per[(size_t)c];
+        iv.reserve((size_t)(chrom_off[c + 1] - chrom_off[c]));
         for (int64_t i = chrom_off[c]; i < chrom_off[c + 1]; ++i)
             if (R[i] > L[i]) iv.push_back({slot[i], L[i], R[i]});    // [L, R) empty: never stabbed
         std::sort(iv.begin(), iv.end(), [](const Iv& a, const Iv& b) { return a.slot != b.slot ? a.slot < b.slot : a.L < b.L; });
+        ent.reserve(iv.size() + iv.size() / 2);
+        const int64_t n_cells_c = t.cell_base[(size_t)c + 1] - t.cell_base[(size_t)c];
         size_t i = 0;
         while (i < iv.size()) {
             const uint32_t s = iv[i].slot;
             int64_t a = iv[i].L, b = iv[i].R;
             size_t j = i + 1;
             while (j < iv.size() && iv[j].slot == s && iv[j].L <= b) { b = std::max<int64_t>(b, iv[j].R); ++j; }
-            t.n_merged++;
-            const int64_t n_cells_c = t.cell_base[(size_t)c + 1] - t.cell_base[(size_t)c];
+            merged[(size_t)c]++;
             for (int64_t k = std::max<int64_t>(0, (a - STAB_EXT) >> shift); k <= (b - 1) >> shift && k < n_cells_c; ++k) {
                 const int64_t c0 = k << shift;
                 const int64_t lo = std::max(a, c0), hi = std::min(b, c0 + csize + STAB_EXT);
@@ -142,12 +148,34 @@ inline void stab_build(StabTable& t, int n_chrom, const int64_t* chrom_off, cons
             }
             i = j;
         }
+        std::sort(ent.begin(), ent.end(), [](const StabEntry& a, const StabEntry& b) {
+            if (a.cell != b.cell) return a.cell < b.cell;
+            if (a.s != b.s) return a.s < b.s;
+            return a.slot < b.slot;
+        });
+    };
+    {
+        const int n_threads = (int)std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 16u, (unsigned)std::max(n_chrom, 1)}));
+        std::atomic<int> next{0};
+        std::vector<std::thread> pool;
+        auto work = [&] {
+            for (int c; (c = next.fetch_add(1)) < n_chrom;) build_chrom(c);
+        };
+        for (int k = 1; k < n_threads; ++k) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
     }
-    std::sort(ent.begin(), ent.end(), [](const StabEntry& a, const StabEntry& b) {
-        if (a.cell != b.cell) return a.cell < b.cell;
-        if (a.s != b.s) return a.s < b.s;
-        return a.slot < b.slot;
-    });
+    std::vector<StabEntry> ent;
+    {
+        size_t total = 0;
+        for (const auto& v : per) total += v.size();
+        ent.reserve(total);
+        for (int c = 0; c < n_chrom; ++c) {
+            t.n_merged += merged[(size_t)c];
+            ent.insert(ent.end(), per[(size_t)c].begin(), per[(size_t)c].end());
+            std::vector<StabEntry>().swap(per[(size_t)c]);
+        }
+    }
     t.n_entries = (int64_t)ent.size();
     // overflow sectors: consecutive per cell, cells in order; links are relative to the block base
     int64_t n_over = 0;
