@@ -135,8 +135,15 @@ class GlbIndex:
 
 
 def _read_pickle(path):
-    with open(os.path.realpath(path), "rb") as fh:
-        return _GlbUnpickler(io.BufferedReader(fh)).load()
+    import gc
+    was = gc.isenabled()
+    gc.disable()                    # millions of small objects, none of them garbage: the collector only costs time here
+    try:
+        with open(os.path.realpath(path), "rb") as fh:
+            return _GlbUnpickler(io.BufferedReader(fh)).load()
+    finally:
+        if was:
+            gc.enable()
 
 
 def verify_buckets(gl_buckets, chrom_str, L, R, bs=BUCKET_SIZE):
@@ -201,55 +208,59 @@ def verify_buckets(gl_buckets, chrom_str, L, R, bs=BUCKET_SIZE):
 
 
 def from_rows(rows, buckets=None, verify=True):
-    """rows: iterable of dicts with keys loc (chr/left/right mapping), type, ensg [, strand].
+    """rows: sequence of dicts with keys loc (chr/left/right mapping), type, ensg [, strand].
     Mirrors what load_genome() exposes: all_feature_names = sorted(set(ensg)) (te_count.py:35) and
-    chromosome keys = the keys of genelist.buckets (first-appearance order of loc['chr'])."""
-    chrom_keys, chrom_lookup = [], {}
-    strand_strings, strand_lookup = ["+", "-"], {"+": 0, "-": 1}
+    chromosome keys = the keys of genelist.buckets (first-appearance order of loc['chr']).
+
+    Column-wise: every field is pulled out of the row dicts with C-level iteration (map +
+    itemgetter) -- a genome-scale index has ~6 M rows and a Python statement per field per row
+    costs more than unpickling them."""
+    from itertools import repeat
+    from operator import attrgetter, itemgetter
+    rows = rows if isinstance(rows, list) else list(rows)
     n = len(rows)
-    chrom_id = np.empty(n, np.int32)
-    L = np.empty(n, np.int32)
-    R = np.empty(n, np.int32)
-    type_code = np.empty(n, np.uint8)
-    strand_code = np.empty(n, np.uint8)
-    ensg = [None] * n
-    chrom_str = [None] * n
-    for i, row in enumerate(rows):
-        if "tss_loc" in row:
-            raise ValueError("index rows carry 'tss_loc'; the reference would bucket on it "
-                             "(miniglbase/genelist.py:345) -- unsupported")
-        loc = row["loc"]
-        loc = loc.loc if hasattr(loc, "loc") else loc
-        c = loc["chr"]
-        cid = chrom_lookup.get(c)
-        if cid is None:
-            cid = chrom_lookup[c] = len(chrom_keys)
-            chrom_keys.append(c)
-        chrom_id[i] = cid
-        chrom_str[i] = c
-        L[i] = loc["left"]
-        R[i] = loc["right"]
-        type_code[i] = _TYPE_CODES.get(row["type"], T_OTHER)
-        if "strand" in row:
-            s = row["strand"]
-            sc = strand_lookup.get(s)
-            if sc is None:
-                if len(strand_strings) >= 4:
-                    raise ValueError("more than 4 distinct strand strings in the index")
-                sc = strand_lookup[s] = len(strand_strings)
-                strand_strings.append(s)
-            strand_code[i] = sc
-        else:
-            strand_code[i] = STRAND_MISSING
-        ensg[i] = row["ensg"]
+    if any(map(contains_tss, rows)):
+        raise ValueError("index rows carry 'tss_loc'; the reference would bucket on it "
+                         "(miniglbase/genelist.py:345) -- unsupported")
+    locs = list(map(itemgetter("loc"), rows))
+    if n and not isinstance(locs[0], dict):
+        try:
+            locs = list(map(attrgetter("loc"), locs))           # location objects hold the dict in .loc
+        except AttributeError:
+            locs = [l.loc if hasattr(l, "loc") else l for l in locs]
+    elif any(not isinstance(l, dict) for l in locs):
+        locs = [l.loc if hasattr(l, "loc") else l for l in locs]
+    chrom_str = list(map(itemgetter("chr"), locs))
+    chrom_keys = list(dict.fromkeys(chrom_str))                  # first-appearance order
+    chrom_lookup = {k: i for i, k in enumerate(chrom_keys)}
+    chrom_id = np.fromiter(map(chrom_lookup.__getitem__, chrom_str), dtype=np.int32, count=n)
+    L = np.fromiter(map(itemgetter("left"), locs), dtype=np.int64, count=n).astype(np.int32)
+    R = np.fromiter(map(itemgetter("right"), locs), dtype=np.int64, count=n).astype(np.int32)
+    type_code = np.fromiter(map(_TYPE_CODES.get, map(itemgetter("type"), rows), repeat(T_OTHER)), dtype=np.uint8, count=n)
+    missing = object()
+    strands = [r.get("strand", missing) for r in rows]
+    strand_strings = ["+", "-"]
+    for st in dict.fromkeys(strands):                            # distinct values in first-appearance order
+        if st is not missing and st not in strand_strings:
+            if len(strand_strings) >= 4:
+                raise ValueError("more than 4 distinct strand strings in the index")
+            strand_strings.append(st)
+    strand_lookup = {st: i for i, st in enumerate(strand_strings)}
+    strand_lookup[missing] = STRAND_MISSING
+    strand_code = np.fromiter(map(strand_lookup.__getitem__, strands), dtype=np.uint8, count=n)
+    ensg = list(map(itemgetter("ensg"), rows))
     names = sorted(set(ensg))
     name_id = {k: i for i, k in enumerate(names)}
-    ensg_id = np.fromiter((name_id[e] for e in ensg), dtype=np.int32, count=n)
+    ensg_id = np.fromiter(map(name_id.__getitem__, ensg), dtype=np.int32, count=n)
     if buckets is not None and verify:
         verify_buckets(buckets, chrom_str, L, R)
         if list(buckets.keys()) != chrom_keys:
             raise ValueError("bucket chromosome keys differ from the feature rows")
     return GlbIndex(chrom_keys, chrom_id, L, R, ensg_id, type_code, strand_code, names, strand_strings)
+
+
+def contains_tss(row):
+    return "tss_loc" in row
 
 
 CACHE_SUFFIX = ".tecidx.npz"
