@@ -12,8 +12,6 @@ import os
 
 import numpy as np
 
-from . import reads as _reads
-
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TEC_BAM_LIB") or os.path.join(HERE, "libtecbam.so")
 
@@ -84,7 +82,6 @@ class NativeBam:
         self.filename = filename
         self.references = [lib.tbam_reference_name(self._h, i).decode("ascii")
                            for i in range(lib.tbam_n_references(self._h))]
-        self._bulk_msg = True
 
     def bind(self, chrom_map, whitelist=None):
         """Hands over what the reference's loop looks up per record: the chromosome key of every

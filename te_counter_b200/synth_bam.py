@@ -9,7 +9,6 @@ of bench.py.  Records look like 10x / bulk RNA-seq alignments: 100 bp reads, CIG
 import argparse
 import os
 import struct
-import sys
 import zlib
 from concurrent.futures import ProcessPoolExecutor
 

@@ -14,7 +14,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from te_counter_b200 import bam, fastbam, reads, synth      # noqa: E402
+from te_counter_b200 import bam, fastbam, reads             # noqa: E402
 
 
 def main():
