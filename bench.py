@@ -383,6 +383,8 @@ def run_ours(args):
             "config": workload_config(args, n_rec, world), "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "traffic_source": "profiles/r01_bulk_ncu_traffic.json: ncu --set full capture of the kernel on the 2 kbp "
+                                           "cell table (65 MB), scaled to this launch size; the 1 kbp default (104 MB) misses L2 more often",
                          "kernel": "bulk_count_cell_kernel<%s> (+ bulk_slow_kernel on flagged units)" % ("paired" if paired else "single"),
                          "cell_table_bytes": eng.get_info("stab_bytes"), "slow_units_per_launch": eng.get_info("last_slow_units"),
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_record": bpr},
