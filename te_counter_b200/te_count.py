@@ -173,6 +173,10 @@ class measureTE:
                     dev.close()
             except (_lib.BamUnsupported, OSError):
                 more = True                                   # start over with a host reader
+            except _lib.TecError as e:
+                if 'memory' not in str(e):                    # no room for the decode window next to the other
+                    raise                                     # buffers of this GPU: decode on the host instead
+                more = True
             while done >= next_log:
                 log.info('Processed {:,} {}'.format(next_log, label))
                 next_log += 1000000
@@ -268,6 +272,10 @@ class measureTE:
                 finally:
                     dev.close()
             except (_lib.BamUnsupported, OSError):
+                more = True
+            except _lib.TecError as e:
+                if 'memory' not in str(e):
+                    raise
                 more = True
             while done >= next_log:
                 log.info('  Processed {:,} SE valid reads'.format(next_log))
