@@ -96,3 +96,19 @@ def test_random_record_shapes(lib, tmp_path, seed, n_ref):        # noqa: F811
         assert np.array_equal(_canon_chrom([(a, False)], len(keys))[0], _canon_chrom([(b, False)], len(keys))[0])
         for k in ("start", "end", "mapq", "flag"):
             assert np.array_equal(want[k], got[k]), (k, wb)
+
+
+@pytest.mark.parametrize("seed,n_ref,n_rec", [(11, 3, 1501), (12, 300, 1500), (13, 3000, 777)])
+def test_random_record_shapes_paired(lib, tmp_path, seed, n_ref, n_rec):      # noqa: F811
+    """Pairs in file order (mate-name rule, odd trailing record) across block and window borders."""
+    rng = np.random.default_rng(seed)
+    path = str(tmp_path / "f.bam")
+    _random_bam(path, rng, n_rec, n_ref)
+    keys = ["ref%d" % i for i in range(0, n_ref, 2)]
+    want = _native(path, "pe", reads.ChromMap(keys), None, 0)
+    assert len(want["start"]) == n_rec - (n_rec & 1)
+    for wb in (1, 2, 9, 1 << 16):
+        rc, msg, got = _decode(lib, path, "pe", reads.ChromMap(keys), None, 0, wb)
+        assert rc == 0, (wb, msg)
+        for k in ("start", "end", "mapq", "flag"):
+            assert np.array_equal(want[k], got[k]), (k, wb)
