@@ -174,7 +174,7 @@ class measureTE:
             except (_lib.BamUnsupported, OSError):
                 more = True                                   # start over with a host reader
             except _lib.TecError as e:
-                if 'memory' not in str(e):                    # no room for the decode window next to the other
+                if 'out of memory' not in str(e):             # no room for the decode window next to the other
                     raise                                     # buffers of this GPU: decode on the host instead
                 more = True
             while done >= next_log:
@@ -274,7 +274,7 @@ class measureTE:
             except (_lib.BamUnsupported, OSError):
                 more = True
             except _lib.TecError as e:
-                if 'memory' not in str(e):
+                if 'out of memory' not in str(e):
                     raise
                 more = True
             while done >= next_log:
