@@ -7,6 +7,7 @@ of bench.py.  Records look like 10x / bulk RNA-seq alignments: 100 bp reads, CIG
     python -m te_counter_b200.synth_bam out.bam --records 4000000 --mode sc --whitelist wl.txt
 """
 import argparse
+import multiprocessing
 import os
 import struct
 import zlib
@@ -138,7 +139,10 @@ def write(out, records=4000000, mode="pe", whitelist=None, n_barcodes=100000, se
                 fh.write("".join(bytes(b).decode() + "-1\n" for b in barcodes))
     chunk = 250000
     jobs = [(seed, i, min(chunk, records - i * chunk), mode, barcodes) for i in range((records + chunk - 1) // chunk)]
-    with open(out, "wb") as fh, ProcessPoolExecutor(procs or os.cpu_count() or 1) as ex:
+    # worker processes come from a fork server: the caller may be a multi-threaded process with a CUDA context
+    # (bench.py), which must not be forked
+    ctx = multiprocessing.get_context("forkserver")
+    with open(out, "wb") as fh, ProcessPoolExecutor(procs or os.cpu_count() or 1, mp_context=ctx) as ex:
         fh.write(_bgzf(header_bytes(HG38)))
         for comp in ex.map(_chunk, jobs):                   # records straddle blocks inside a chunk
             fh.write(comp)
