@@ -387,6 +387,7 @@ def run_ours(args):
                                            "cell table (65 MB), scaled to this launch size; the 1 kbp default (104 MB) misses L2 more often",
                          "kernel": "bulk_count_cell_kernel<%s> (+ bulk_slow_kernel on flagged units)" % ("paired" if paired else "single"),
                          "cell_table_bytes": eng.get_info("stab_bytes"), "slow_units_per_launch": eng.get_info("last_slow_units"),
+                         "deferred_units_per_launch": eng.get_info("last_deferred_units"),
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_record": bpr},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity, "parity_full": parity_full,
             "stats": {"units": int(st[0]), "assigned": int(st[1]), "lowq": int(st[2]), "badchrom": int(st[3]),

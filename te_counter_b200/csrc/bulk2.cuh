@@ -1,0 +1,432 @@
+// Bulk counting, two passes over the cell table of stab2_build.h (the default bulk path).
+//
+// Reference semantics (te_counter, te_count/te_count.py): filter SE :203-218, filter + mate merge PE
+// :76-102, candidate buckets :106-116 / :222-231, point tests :118-126 / :233-241, type rule + tally
+// :128-149 / :243-261; closed forms in the header of bulk.cuh.
+//
+//   bulk2_fast_kernel    one pass over the records, straight-line code, two units per thread.  A unit whose
+//                        two points are covered by ONE primary sector (the cell of the smaller point also
+//                        covers `ext` bp of the next cell) and lie below the sector's threshold is filtered,
+//                        tested against the five entries (16-bit lanes, both points at once), de-duplicated
+//                        (twin flags) and tallied into shared-memory counters right there.  Every other unit
+//                        that passed the filter is appended to the warp's own segment of the deferred list
+//                        (no atomics: the list is partitioned by warp).
+//   bulk2_second_kernel  the deferred units (about 6 % of a paired-end workload): one or two sector chains,
+//                        a register set of distinct ensg, hot counters in shared memory.  Units in EDGE cells
+//                        (the reference's two-bucket candidate rule can bite there) or with more distinct ensg
+//                        than the register set go on to bulk_slow_kernel's exact search.
+//
+// Streamed per unit: 16 B (PE; `end` is never read) / 12 B (SE) of records; one random 32-byte sector of the
+// L2-resident table; one shared-memory reduction per entry.
+#pragma once
+#include "common.cuh"
+#include "bulk.cuh"
+#include "stab2_build.h"
+
+struct Stab2View {
+    const u32* sectors;          // 8 words per sector, 32-byte aligned
+    const uint2* cells;          // per chromosome {first sector, number of cells}; [n_chrom] = {0, 0} sentinel
+    const u32* ovf_first;        // per primary sector: first overflow sector
+    const uint8_t* slot_type;    // n_slots
+    int shift, ext;
+    int all_counted;
+};
+
+#define B2_UPT 2                 // units per thread in the fast kernel
+#define B2_MAXD 8                // register set of the second pass
+
+__device__ __forceinline__ u32 ld_stream_v2u32(const void* p, u64 pol, u32& y) {
+    u32 x;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(x), "=r"(y) : "l"(p), "l"(pol));
+    return x;
+}
+__device__ __forceinline__ int4 ld_stream_int4(const int32_t* p, u64 pol) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+
+// the records of a thread's two consecutive units, as loaded (unpacked at use)
+template <bool PAIRED> struct B2Raw;
+template <> struct B2Raw<true> { u32 fl, mq, c0, c1; int4 st; };            // 2 pairs = 4 records
+template <> struct B2Raw<false> { u32 fl, mq, ch; int2 st, en; };          // 2 records
+
+template <bool PAIRED, bool FULL>
+__device__ __forceinline__ void b2_load(B2Raw<PAIRED>& r, u32 u0, u32 n_units, const int32_t* __restrict__ start,
+                                        const int32_t* __restrict__ end, const uint16_t* __restrict__ chrom,
+                                        const uint8_t* __restrict__ mapq, const uint8_t* __restrict__ flag, u64 pol) {
+    if (FULL || u0 + 2 <= n_units) {
+        if constexpr (PAIRED) {
+            r.fl = ld_stream_u32(flag + 2 * (size_t)u0, pol);
+            r.mq = ld_stream_u32(mapq + 2 * (size_t)u0, pol);
+            r.c0 = ld_stream_v2u32(chrom + 2 * (size_t)u0, pol, r.c1);
+            r.st = ld_stream_int4(start + 2 * (size_t)u0, pol);
+        } else {
+            r.fl = ld_stream_u16(flag + u0, pol);
+            r.mq = ld_stream_u16(mapq + u0, pol);
+            r.ch = ld_stream_u32(chrom + u0, pol);
+            r.st = ld_stream_int2(start + u0, pol);
+            r.en = ld_stream_int2(end + u0, pol);
+        }
+    } else if (u0 < n_units) {                       // the last, odd unit of the launch
+        if constexpr (PAIRED) {
+            r.fl = ld_stream_u16(flag + 2 * (size_t)u0, pol);
+            r.mq = ld_stream_u16(mapq + 2 * (size_t)u0, pol);
+            r.c0 = ld_stream_u32(chrom + 2 * (size_t)u0, pol);
+            r.c1 = 0;
+            const int2 s = ld_stream_int2(start + 2 * (size_t)u0, pol);
+            r.st = make_int4(s.x, s.y, 0, 0);
+        } else {
+            r.fl = ld_stream_u8(flag + u0, pol);
+            r.mq = ld_stream_u8(mapq + u0, pol);
+            r.ch = ld_stream_u16(chrom + u0, pol);
+            r.st = make_int2(ld_stream_int(start + u0, pol), 0);
+            r.en = make_int2(ld_stream_int(end + u0, pol), 0);
+        }
+    }
+}
+
+template <bool PAIRED>
+__device__ __forceinline__ void b2_unpack(const B2Raw<PAIRED>& r, int j, u32& fl, u32& q, u32& c, int& loc1, int& loc2) {
+    if constexpr (PAIRED) {
+        fl = j ? (r.fl >> 16) : (r.fl & 0xFFFFu);             // both mates' flag bytes
+        q = j ? ((r.mq >> 16) & 0xFFu) : (r.mq & 0xFFu);      // read1 only (:88)
+        c = (j ? r.c1 : r.c0) & 0xFFFFu;                      // read1 only (:96)
+        loc1 = j ? r.st.z : r.st.x;                           // :97
+        loc2 = j ? r.st.w : r.st.y;                           // :98 mate START
+    } else {
+        fl = j ? (r.fl >> 8) : (r.fl & 0xFFu);
+        q = j ? (r.mq >> 8) : (r.mq & 0xFFu);
+        c = j ? (r.ch >> 16) : (r.ch & 0xFFFFu);
+        loc1 = j ? r.st.y : r.st.x;                           // :213
+        loc2 = j ? r.en.y : r.en.x;                           // :214
+    }
+}
+
+// +1 for an entry when its hit bit is set (ALLHOT: every counter in shared memory; the lanes that did not
+// hit add to a scratch word of their own behind the counters, so there is no branch)
+template <bool ALLHOT>
+__device__ __forceinline__ void b2_bump(bool hit, u32 slot, u32 hot_addr, u32 scratch_addr, u32 n_hot, u64* __restrict__ counts, u32 one) {
+    if (ALLHOT) {
+        const u32 addr = hit ? (hot_addr + slot * 4u) : scratch_addr;
+        asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(one) : "memory");
+    } else {
+        const bool hot = slot < n_hot;
+        const u32 addr = (hit && hot) ? (hot_addr + slot * 4u) : scratch_addr;
+        asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(one) : "memory");
+        if (hit && !hot) atomicAdd(counts + slot, 1ULL);
+    }
+}
+__device__ __forceinline__ u32 b2_lo16(u32 w) { return __byte_perm(w, 0u, 0x4410u); }
+__device__ __forceinline__ u32 b2_hi16(u32 w) { return __byte_perm(w, 0u, 0x4432u); }
+
+// what a thread of the fast kernel carries across tiles
+struct B2Thread {
+    u32 n_assigned, n_lowq, n_badchrom, n_qcfail;
+    u32* wp;                      // next free entry of the warp's segment of the deferred list (warp-uniform)
+};
+struct B2Const {
+    u32 reject2, lim, lt_mask, hot_addr, scratch_addr, one, n_hot, n_units;
+    int shift, cmask, qual, n_chrom;
+};
+
+// One turn of a warp: 64 consecutive units, two per lane.  FULL: every unit of the tile exists.
+template <bool PAIRED, bool ALLHOT, bool FULL>
+__device__ __forceinline__ void b2_tile(const B2Raw<PAIRED>& cur, const u32 u0, const Stab2View& sv, const B2Const& k,
+                                        B2Thread& t, u64* __restrict__ counts, u64* __restrict__ stats) {
+    bool look[B2_UPT], ok[B2_UPT];
+    int ra[B2_UPT], rb[B2_UPT];
+    u32 rmax[B2_UPT], sec[B2_UPT];
+    // ---- filter (te_count.py:78-102 / :203-218) and the sector each unit needs
+#pragma unroll
+    for (int j = 0; j < B2_UPT; ++j) {
+        u32 fl, q, c;
+        int loc1, loc2;
+        b2_unpack<PAIRED>(cur, j, fl, q, c, loc1, loc2);
+        // first failing test wins, as in the reference's if / continue chain; branch-free counters
+        const bool live = FULL || (u0 + j < k.n_units);
+        const bool f_qc = (fl & k.reject2) != 0;                                           // :81-86 / :204
+        const bool f_lq = (int)q < k.qual;                                                 // :88 / :208
+        const bool f_nm = PAIRED && (fl & TEC_F_NAME_MISMATCH);                            // :92-94
+        // chromosomes that are not keys of the bucket hash (no feature row) have zero cells
+        const uint2 cell = __ldg(sv.cells + min(c, (u32)k.n_chrom));
+        const bool f_bc = cell.y == 0;                                                     // :100 / :216
+        t.n_qcfail += live & f_qc;
+        t.n_lowq += live & !f_qc & f_lq;
+        t.n_badchrom += live & !(f_qc | f_lq | f_nm) & f_bc;
+        // a name mismatch (the reference dies there, :92-94) is left to the second pass, like every rare case
+        look[j] = live & !(f_qc | f_lq) & (f_nm | !f_bc);
+        // point A x = loc1, point B x = loc2 - 1 (bulk.cuh header); the cell of the smaller one
+        const int xa = loc1, xb = loc2 - 1;
+        const int mn = min(xa, xb);
+        const int kc = mn >> k.shift;                         // arithmetic shift: negative stays negative
+        const int base = mn & ~k.cmask;
+        ra[j] = xa - base;
+        rb[j] = xb - base;
+        rmax[j] = (u32)(max(xa, xb) - base);
+        ok[j] = look[j] & !f_nm & ((u32)kc < cell.y) & (rmax[j] < k.lim);
+        sec[j] = ok[j] ? cell.x + (u32)kc : 0u;
+        asm volatile("" : "+r"(sec[j]));                      // select the index, not the 64-bit address
+    }
+    Sector s[B2_UPT];
+#pragma unroll
+    for (int j = 0; j < B2_UPT; ++j) s[j] = ld_sector(sv.sectors, sec[j]);
+#pragma unroll
+    for (int j = 0; j < B2_UPT; ++j) {
+        const u32 w2 = s[j].w[2];
+        const u32 thr = (w2 >> 16) & 0x7FFu;
+        const bool inplace = ok[j] & (rmax[j] < thr);
+        const bool defer = look[j] & !inplace;
+        // ---- five interval tests, both points at once (16-bit lanes, stab_build.h)
+        const PointK pa = make_point((u32)ra[j]), pb = make_point((u32)rb[j]);
+        const u32 m = inplace ? 0x80008000u : 0u;
+        u32 a0 = (((pa.xg - s[j].w[0]) & (s[j].w[3] + pa.kg)) | ((pb.xg - s[j].w[0]) & (s[j].w[3] + pb.kg))) & m;
+        u32 a1 = (((pa.xg - s[j].w[1]) & (s[j].w[4] + pa.kg)) | ((pb.xg - s[j].w[1]) & (s[j].w[4] + pb.kg))) & m;
+        u32 a2 = (((pa.xg - w2) & (s[j].w[5] + pa.kg)) | ((pb.xg - w2) & (s[j].w[5] + pb.kg))) & m & 0x8000u;
+        // twins: entries (0, 1) / (2, 3) carry the same ensg -> the pair counts once
+        a0 &= ~((a0 << 16) & w2 & 0x80000000u);
+        a1 &= ~((a1 << 16) & (w2 << 1) & 0x80000000u);
+        if (!sv.all_counted) {
+            // type rule of te_count.py:134-147 over the hit entries
+            u32 typemask = 0;
+            if (a0 & 0x8000u) typemask |= 1u << __ldg(sv.slot_type + (s[j].w[6] & 0xFFFFu));
+            if (a0 & 0x80000000u) typemask |= 1u << __ldg(sv.slot_type + (s[j].w[6] >> 16));
+            if (a1 & 0x8000u) typemask |= 1u << __ldg(sv.slot_type + (s[j].w[7] & 0xFFFFu));
+            if (a1 & 0x80000000u) typemask |= 1u << __ldg(sv.slot_type + (s[j].w[7] >> 16));
+            if (a2) typemask |= 1u << __ldg(sv.slot_type + (s[j].w[5] >> 16));
+            if (typemask) {
+                t.n_assigned++;                                                            // :149
+                const u32 counted = (1u << TEC_T_GENE) | (1u << TEC_T_TE) | (1u << TEC_T_SNRNA);
+                if (!(typemask & counted)) {
+                    if (typemask & (1u << TEC_T_ENHANCER)) atomicAdd(stats + TEC_BS_CRASH_ENHANCER, 1ULL);   // :145-147
+                    a0 = a1 = a2 = 0;
+                }
+            }
+        } else {
+            t.n_assigned += (a0 | a1 | a2) != 0;                                           // :128, :149
+        }
+        b2_bump<ALLHOT>(a0 & 0x8000u, b2_lo16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        b2_bump<ALLHOT>(a0 & 0x80000000u, b2_hi16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        b2_bump<ALLHOT>(a1 & 0x8000u, b2_lo16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        b2_bump<ALLHOT>(a1 & 0x80000000u, b2_hi16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        b2_bump<ALLHOT>(a2 != 0, b2_hi16(s[j].w[5]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        // ---- everything else goes to the second pass: the warp's own segment of the list, no atomics
+        const u32 dm = __ballot_sync(0xFFFFFFFFu, defer);
+        if (defer) t.wp[__popc(dm & k.lt_mask)] = u0 + j;
+        t.wp += __popc(dm);
+    }
+}
+
+template <bool PAIRED, int NT, bool ALLHOT>
+__global__ void __launch_bounds__(NT, 2048 / NT / 2)
+bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
+                  const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                  const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ mapq,
+                  const uint8_t* __restrict__ flag, u64* __restrict__ counts, u64* __restrict__ stats,
+                  u32* __restrict__ defer_list, u32* __restrict__ defer_count, u32 seg_cap, u32 n_hot) {
+    constexpr int WARPS = NT / 32;
+    __shared__ u64 s_stats[TEC_BULK_NSTATS];
+    extern __shared__ __align__(16) u32 s_hot_dyn[];
+    for (u32 i = threadIdx.x; i < n_hot + 32; i += blockDim.x) s_hot_dyn[i] = 0;
+    if (threadIdx.x < TEC_BULK_NSTATS) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 reject = TEC_F_UNMAPPED | TEC_F_DUP | TEC_F_QCFAIL;
+    const u64 pol = make_evict_first_policy();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    B2Const k;
+    k.reject2 = PAIRED ? (reject | (reject << 8)) : reject;
+    k.shift = sv.shift;
+    k.cmask = (1 << sv.shift) - 1;
+    k.lim = (u32)(k.cmask + 1 + sv.ext);                      // relative positions a sector covers
+    k.lt_mask = (1u << lane) - 1u;
+    k.hot_addr = (u32)__cvta_generic_to_shared(&s_hot_dyn[0]);
+    asm volatile("" : "+r"(k.hot_addr));                      // keep it in a register (not recomputed per use)
+    k.scratch_addr = k.hot_addr + (n_hot + (u32)lane) * 4u;
+    // the increment as a run-time value: a literal 1 makes ptxas pick ATOMS.POPC.INC, which needs a
+    // converged warp and therefore a branch around every reduction
+    k.one = (u32)(n_units > 0);
+    asm volatile("" : "+r"(k.one));
+    k.n_hot = n_hot;
+    k.n_units = n_units;
+    k.qual = qual;
+    k.n_chrom = n_chrom;
+    const u32 gw = blockIdx.x * WARPS + wib;
+    u32* const my_list = defer_list + (size_t)gw * seg_cap;
+    B2Thread t;
+    t.n_assigned = t.n_lowq = t.n_badchrom = t.n_qcfail = 0;
+    t.wp = my_list;
+    // full tiles of 64 units, warp-strided; the records of the next tile are requested before the current
+    // one is looked up (two register buffers, swapped by unrolling)
+    const u32 n_full = n_units >> 6;
+    const u32 stride = gridDim.x * WARPS;
+    u32 tile = gw;
+    B2Raw<PAIRED> ra, rb;
+    if (tile < n_full) b2_load<PAIRED, true>(ra, tile * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+    while (tile < n_full) {
+        u32 nx = tile + stride;
+        if (nx < n_full) b2_load<PAIRED, true>(rb, nx * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+        b2_tile<PAIRED, ALLHOT, true>(ra, tile * 64 + 2 * lane, sv, k, t, counts, stats);
+        tile = nx;
+        if (tile >= n_full) break;
+        nx = tile + stride;
+        if (nx < n_full) b2_load<PAIRED, true>(ra, nx * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+        b2_tile<PAIRED, ALLHOT, true>(rb, tile * 64 + 2 * lane, sv, k, t, counts, stats);
+        tile = nx;
+    }
+    // the last, partial tile belongs to the warp whose turn it would be
+    if ((n_units & 63u) && (n_full % stride) == gw) {
+        const u32 u0 = n_full * 64 + 2 * lane;
+        ra = B2Raw<PAIRED>();
+        b2_load<PAIRED, false>(ra, u0, n_units, start, end, chrom, mapq, flag, pol);
+        b2_tile<PAIRED, ALLHOT, false>(ra, u0, sv, k, t, counts, stats);
+    }
+    if (lane == 0) defer_count[gw] = (u32)(t.wp - my_list);
+    u64 v[4] = {t.n_assigned, t.n_lowq, t.n_badchrom, t.n_qcfail};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const u64 sum = warp_sum(v[i]);
+        if (lane == 0 && sum) atomicAdd(&s_stats[TEC_BS_ASSIGNED + i], sum);
+    }
+    __syncthreads();
+    if (threadIdx.x >= TEC_BS_ASSIGNED && threadIdx.x < TEC_BS_ASSIGNED + 4 && s_stats[threadIdx.x])
+        atomicAdd(stats + threadIdx.x, s_stats[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + TEC_BS_UNITS, (u64)n_units);
+    for (u32 i = threadIdx.x; i < n_hot; i += blockDim.x) {
+        const u32 x = s_hot_dyn[i];
+        if (x) atomicAdd(counts + i, (u64)x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Second pass: the units the fast kernel deferred (they passed the filter).  One thread per unit; warp gw
+// reads the segment warp gw of the fast kernel wrote.
+__device__ __forceinline__ u32 b2_sector_hits(const Sector& s, const PointK a, const PointK b) {
+    const u32 a0 = ((a.xg - s.w[0]) & (s.w[3] + a.kg)) | ((b.xg - s.w[0]) & (s.w[3] + b.kg));
+    const u32 a1 = ((a.xg - s.w[1]) & (s.w[4] + a.kg)) | ((b.xg - s.w[1]) & (s.w[4] + b.kg));
+    const u32 a2 = ((a.xg - s.w[2]) & (s.w[5] + a.kg)) | ((b.xg - s.w[2]) & (s.w[5] + b.kg));
+    return (a0 & 0x80008000u) | ((a1 & 0x80008000u) >> 1) | ((a2 & 0x8000u) >> 2);     // HB0..HB4 of bulk.cuh
+}
+
+template <bool PAIRED>
+__global__ void __launch_bounds__(256)
+bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                    const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ flag, u64* __restrict__ counts, u64* __restrict__ stats,
+                    const u32* __restrict__ defer_list, const u32* __restrict__ defer_count, u32 seg_cap, u32 n_warps,
+                    u32* __restrict__ slow_list, u32 sv_n_chrom) {
+    // hot ensg counters privatised per CTA (a Zipf-hot TE name would otherwise serialise in one L2 slice)
+    __shared__ u32 s_hot[TEC_HOT_SLOTS];
+    for (int i = threadIdx.x; i < TEC_HOT_SLOTS; i += blockDim.x) s_hot[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const u32 lt_mask = (1u << lane) - 1u;
+    const int shift = sv.shift;
+    const int cmask = (1 << shift) - 1;
+    const u32 lim = (u32)(cmask + 1 + sv.ext);
+    u32 n_assigned = 0;
+    for (u32 gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gw < n_warps; gw += gridDim.x * (blockDim.x >> 5)) {
+        const u32 cnt = __ldg(defer_count + gw);
+        const u32* const list = defer_list + (size_t)gw * seg_cap;
+        for (u32 i0 = 0; i0 < cnt; i0 += 32) {
+            const bool live = i0 + lane < cnt;
+            bool exact = false;
+            u32 u = 0;
+            if (live) {
+                u = __ldg(list + i0 + lane);
+                int c, loc1, loc2;
+                bool name_crash = false;
+                if (PAIRED) {
+                    c = chrom[2 * (size_t)u];
+                    const int2 s2 = *reinterpret_cast<const int2*>(start + 2 * (size_t)u);
+                    loc1 = s2.x; loc2 = s2.y;
+                    name_crash = (flag[2 * (size_t)u] & TEC_F_NAME_MISMATCH) != 0;
+                } else { c = chrom[u]; loc1 = start[u]; loc2 = end[u]; }
+                if (name_crash) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);                // :92-94
+                // (a unit with a name mismatch may sit on a chromosome without cells: zero cells, no probe)
+                const uint2 cell = name_crash ? make_uint2(0u, 0u) : __ldg(sv.cells + min((u32)c, sv_n_chrom));
+                const int xa = loc1, xb = loc2 - 1;
+                // probes: one sector chain holding both points, or one chain per point
+                u32 prim[2], pts[2];                                       // pts = ra | rb << 16 (S2_R_NONE = none)
+                int np = 0;
+                {
+                    const int mn = min(xa, xb), k = mn >> shift, base = mn & ~cmask;
+                    const u32 rm = (u32)(max(xa, xb) - base);
+                    if ((u32)k < cell.y && rm < lim) {
+                        prim[0] = cell.x + (u32)k;
+                        pts[0] = (u32)(xa - base) | ((u32)(xb - base) << 16);
+                        np = 1;
+                    } else {
+                        if (xa >= 0 && (u32)(xa >> shift) < cell.y) { prim[np] = cell.x + (u32)(xa >> shift); pts[np] = (u32)(xa & cmask) | (S2_R_NONE << 16); ++np; }
+                        if (xb >= 0 && (u32)(xb >> shift) < cell.y) { prim[np] = cell.x + (u32)(xb >> shift); pts[np] = S2_R_NONE | ((u32)(xb & cmask) << 16); ++np; }
+                    }
+                }
+                u32 dist[B2_MAXD];
+#pragma unroll
+                for (int i = 0; i < B2_MAXD; ++i) dist[i] = 0xFFFFFFFFu;
+                u32 nd = 0;
+                for (int p = 0; p < np; ++p) {
+                    const u32 ra = pts[p] & 0xFFFFu, rb = pts[p] >> 16;
+                    const PointK pa = make_point(ra), pb = make_point(rb);
+                    const int rm = max(ra == S2_R_NONE ? -1 : (int)ra, rb == S2_R_NONE ? -1 : (int)rb);
+                    u32 sec = prim[p];
+                    for (;;) {
+                        const Sector s = ld_sector(sv.sectors, sec);
+                        const u32 header = s.w[2] >> 16;
+                        const bool first = sec == prim[p];
+                        if (first && (header & S2_H_EDGE)) exact = true;
+                        u32 hit = b2_sector_hits(s, pa, pb);
+                        while (hit) {
+                            const u32 low = hit & (0u - hit);
+                            hit ^= low;
+                            const u32 w = (low == HB0) ? sector_slot_c<0>(s) : (low == HB1) ? sector_slot_c<1>(s) : (low == HB2) ? sector_slot_c<2>(s)
+                                          : (low == HB3) ? sector_slot_c<3>(s) : sector_slot_c<4>(s);
+                            bool found = false;
+#pragma unroll
+                            for (int j = 0; j < B2_MAXD; ++j) found |= (dist[j] == w);
+                            if (!found) {
+#pragma unroll
+                                for (int j = 0; j < B2_MAXD; ++j) if ((u32)j == nd) dist[j] = w;
+                                ++nd;                                                  // nd > B2_MAXD: overflow
+                            }
+                        }
+                        if (!(header & S2_H_MORE)) break;
+                        if (!(first && (header & S2_H_EDGE)) && rm < (int)(header & 0x7FFu)) break;
+                        sec = first ? __ldg(sv.ovf_first + sec) : sec + 1;
+                    }
+                }
+                if (nd > B2_MAXD) exact = true;
+                if (!exact && nd) {                                                    // :128 result not empty
+                    n_assigned++;                                                      // :149
+                    bool count_it = true;
+                    if (!sv.all_counted) {
+                        u32 typemask = 0;
+#pragma unroll
+                        for (int j = 0; j < B2_MAXD; ++j) if ((u32)j < nd) typemask |= 1u << __ldg(sv.slot_type + dist[j]);
+                        const u32 counted = (1u << TEC_T_GENE) | (1u << TEC_T_TE) | (1u << TEC_T_SNRNA);
+                        if (!(typemask & counted)) {
+                            if (typemask & (1u << TEC_T_ENHANCER)) atomicAdd(stats + TEC_BS_CRASH_ENHANCER, 1ULL);   // :145-147
+                            count_it = false;
+                        }
+                    }
+                    if (count_it) {
+#pragma unroll
+                        for (int j = 0; j < B2_MAXD; ++j) {
+                            if ((u32)j < nd) {
+                                if (dist[j] < TEC_HOT_SLOTS) atomicAdd(&s_hot[dist[j]], 1u);
+                                else atomicAdd(counts + dist[j], 1ULL);
+                            }
+                        }
+                    }
+                }
+            }
+            flag_slow_warp(slow_list, exact, u, lt_mask);
+        }
+    }
+    const u64 a_sum = warp_sum((u64)n_assigned);
+    if (lane == 0 && a_sum) atomicAdd(stats + TEC_BS_ASSIGNED, a_sum);
+    __syncthreads();
+    for (int i = threadIdx.x; i < TEC_HOT_SLOTS; i += blockDim.x) {
+        const u32 x = s_hot[i];
+        if (x) atomicAdd(counts + i, (u64)x);
+    }
+}

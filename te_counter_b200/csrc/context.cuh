@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "bulk.cuh"
+#include "bulk2.cuh"
 #include <map>
 
 #define TEC_STAGE_RECORDS (int64_t(16) << 20)     // records per host->device staging chunk
@@ -30,6 +31,22 @@ struct DevIndex {
         StabView v;
         v.sectors = st_sectors; v.cells = st_cells; v.slot_type = st_slot_type; v.ovf_base = st_ovf_base;
         v.shift = st_shift; v.all_counted = st_all_counted;
+        return v;
+    }
+    // cell table, layout 2 (stab2_build.h): the default bulk path (bulk2.cuh)
+    u32* s2_sectors = nullptr;
+    uint2* s2_cells = nullptr;
+    u32* s2_ovf_first = nullptr;
+    uint8_t* s2_slot_type = nullptr;
+    int s2_shift = 10, s2_ext = STAB_EXT, s2_all_counted = 1;
+    bool has_stab2 = false;
+    size_t stab2_bytes = 0;
+    int64_t s2_primary = 0, s2_overflow = 0, s2_entries = 0, s2_edge_cells = 0, s2_twin_sectors = 0;
+    std::string stab_why_not;             // why no cell table could be built (the exact search kernel is used then)
+    Stab2View stab2_view() const {
+        Stab2View v;
+        v.sectors = s2_sectors; v.cells = s2_cells; v.ovf_first = s2_ovf_first; v.slot_type = s2_slot_type;
+        v.shift = s2_shift; v.ext = s2_ext; v.all_counted = s2_all_counted;
         return v;
     }
     // single-cell cell table (sc.cuh ScTableView)
@@ -112,6 +129,7 @@ struct DevCache {
 // log2 of the cell size of the two cell tables.  Bulk: 1 kbp cells (104 MB for the hg38-like index) measured
 // 125.9e9 records/s against 121.1e9 with 2 kbp cells (65 MB): fewer overflow sectors outweigh the extra L2 misses.
 #define TEC_BULK_STAB_SHIFT 10
+#define TEC_BULK_STAB2_SHIFT 10
 #define TEC_SC_STAB_SHIFT 11
 
 struct tec_ctx {
@@ -137,9 +155,12 @@ struct tec_ctx {
     void* d_ring = nullptr;               // per-warp second deferral ring of the fast bulk kernel (QEnt)
     u32* d_ring_u = nullptr;
     int64_t ring_cap = 0;                 // entries
+    u32* d_defer_list = nullptr;          // bulk2: per-warp segments of deferred unit indices
+    u32* d_defer_count = nullptr;         // bulk2: entries per segment
+    int64_t defer_cap = 0, defer_warps = 0;
     std::vector<int32_t> ensg_of_slot;    // slot = rank of an ensg by number of feature rows
     // options (tec_set_option)
-    int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 stab-table kernel
+    int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 cell-table kernel with in-kernel rings (round 1), 2 two-pass kernels (bulk2.cuh)
     int opt_stab_shift = 0;               // log2 of the cell size; 0 = TEC_BULK_STAB_SHIFT / TEC_SC_STAB_SHIFT
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
     int opt_sc_pack_umi = 1;              // single cell: 2-bit UMI sort keys when every UMI is fixed-length ACGT
@@ -193,6 +214,7 @@ inline void tec_ctx::free_index() {
     cudaFree(ix.L); cudaFree(ix.R); cudaFree(ix.pmaxR); cudaFree(ix.info);
     cudaFree(ix.chrom_off); cudaFree(ix.dir); cudaFree(ix.dir_off); cudaFree(ix.chrom_valid);
     cudaFree(ix.st_sectors); cudaFree(ix.st_cells); cudaFree(ix.st_slot_type); cudaFree(ix.st_ovf_base);
+    cudaFree(ix.s2_sectors); cudaFree(ix.s2_cells); cudaFree(ix.s2_ovf_first); cudaFree(ix.s2_slot_type);
     cudaFree(ix.sc_sectors); cudaFree(ix.sc_cells); cudaFree(ix.sc_ovf_base); cudaFree(ix.sc_pair_key); cudaFree(ix.sc_pair_type);
     ix = DevIndex();
     cudaFree(d_counts);
@@ -201,6 +223,8 @@ inline void tec_ctx::free_index() {
     d_slow_list = nullptr;
     cudaFree(d_ring); cudaFree(d_ring_u);
     d_ring = nullptr; d_ring_u = nullptr; ring_cap = 0;
+    cudaFree(d_defer_list); cudaFree(d_defer_count);
+    d_defer_list = nullptr; d_defer_count = nullptr; defer_cap = 0; defer_warps = 0;
     slow_cap = 0;
     has_index = false;
     bulk_active = false;

@@ -74,6 +74,77 @@ struct StabEntry {
     uint32_t s, len, slot;
 };
 
+// Entries of the cell table: per chromosome, per slot the union of [L, R) (so one ensg never has two
+// overlapping or touching entries), clipped to cells of 2^shift bp that also cover the first `ext` bp of
+// the next cell.  Sorted by (cell, start, slot); cell_base[c] = first cell of chromosome c.
+inline void stab_collect_entries(std::vector<int64_t>& cell_base, int64_t& n_merged, std::vector<StabEntry>& ent,
+                                 int n_chrom, const int64_t* chrom_off, const int32_t* L, const int32_t* R,
+                                 const uint32_t* slot, int shift, int ext) {
+    const int64_t csize = (int64_t)1 << shift;
+    cell_base.assign((size_t)n_chrom + 1, 0);
+    for (int c = 0; c < n_chrom; ++c) {
+        int32_t maxc = 0;
+        for (int64_t i = chrom_off[c]; i < chrom_off[c + 1]; ++i) maxc = std::max(maxc, R[i]);
+        cell_base[(size_t)c + 1] = cell_base[(size_t)c] + (((int64_t)maxc >> shift) + 1);
+    }
+    // Chromosomes own disjoint, ascending cell ranges, so each one is built and sorted on its own (a
+    // thread per chromosome at a time) and the concatenation in chromosome order is globally sorted.
+    struct Iv { uint32_t slot; int32_t L, R; };
+    std::vector<std::vector<StabEntry>> per((size_t)n_chrom);
+    std::vector<int64_t> merged((size_t)n_chrom, 0);
+    auto build_chrom = [&](int c) {
+        std::vector<Iv> iv;
+        std::vector<StabEntry>& e = per[(size_t)c];
+        iv.reserve((size_t)(chrom_off[c + 1] - chrom_off[c]));
+        for (int64_t i = chrom_off[c]; i < chrom_off[c + 1]; ++i)
+            if (R[i] > L[i]) iv.push_back({slot[i], L[i], R[i]});    // [L, R) empty: never stabbed
+        std::sort(iv.begin(), iv.end(), [](const Iv& a, const Iv& b) { return a.slot != b.slot ? a.slot < b.slot : a.L < b.L; });
+        e.reserve(iv.size() + iv.size() / 2);
+        const int64_t n_cells_c = cell_base[(size_t)c + 1] - cell_base[(size_t)c];
+        size_t i = 0;
+        while (i < iv.size()) {
+            const uint32_t s = iv[i].slot;
+            int64_t a = iv[i].L, b = iv[i].R;
+            size_t j = i + 1;
+            while (j < iv.size() && iv[j].slot == s && iv[j].L <= b) { b = std::max<int64_t>(b, iv[j].R); ++j; }
+            merged[(size_t)c]++;
+            for (int64_t k = std::max<int64_t>(0, (a - ext) >> shift); k <= (b - 1) >> shift && k < n_cells_c; ++k) {
+                const int64_t c0 = k << shift;
+                const int64_t lo = std::max(a, c0), hi = std::min(b, c0 + csize + ext);
+                if (hi <= lo) continue;
+                e.push_back({cell_base[(size_t)c] + k, (uint32_t)(lo - c0), (uint32_t)(hi - lo), s});
+            }
+            i = j;
+        }
+        std::sort(e.begin(), e.end(), [](const StabEntry& a, const StabEntry& b) {
+            if (a.cell != b.cell) return a.cell < b.cell;
+            if (a.s != b.s) return a.s < b.s;
+            return a.slot < b.slot;
+        });
+    };
+    {
+        const int n_threads = (int)std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 16u, (unsigned)std::max(n_chrom, 1)}));
+        std::atomic<int> next{0};
+        std::vector<std::thread> pool;
+        auto work = [&] {
+            for (int c; (c = next.fetch_add(1)) < n_chrom;) build_chrom(c);
+        };
+        for (int k = 1; k < n_threads; ++k) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    }
+    size_t total = 0;
+    for (const auto& v : per) total += v.size();
+    ent.clear();
+    ent.reserve(total);
+    n_merged = 0;
+    for (int c = 0; c < n_chrom; ++c) {
+        n_merged += merged[(size_t)c];
+        ent.insert(ent.end(), per[(size_t)c].begin(), per[(size_t)c].end());
+        std::vector<StabEntry>().swap(per[(size_t)c]);
+    }
+}
+
 inline void stab_pack_sector(uint32_t* w, const StabEntry* e, int n, bool more, uint32_t link) {
     uint32_t sv[6], ev[6], sl[5];
     for (int i = 0; i < 6; ++i) { sv[i] = 2047u; ev[i] = 0u; }
@@ -108,74 +179,10 @@ inline void stab_build(StabTable& t, int n_chrom, const int64_t* chrom_off, cons
         if (ty == 0xFF) ty = 0;
         if (!(ty == 1 || ty == 2 || ty == 3)) t.all_counted = 0;     // TEC_T_GENE / TE / SNRNA
     }
-    const int64_t csize = (int64_t)1 << shift;
-    // cells per chromosome
-    t.cell_base.assign((size_t)n_chrom + 1, 0);
-    for (int c = 0; c < n_chrom; ++c) {
-        int32_t maxc = 0;
-        for (int64_t i = chrom_off[c]; i < chrom_off[c + 1]; ++i) maxc = std::max(maxc, R[i]);
-        t.cell_base[(size_t)c + 1] = t.cell_base[(size_t)c] + (((int64_t)maxc >> shift) + 1);
-    }
+    std::vector<StabEntry> ent;
+    stab_collect_entries(t.cell_base, t.n_merged, ent, n_chrom, chrom_off, L, R, slot, shift, STAB_EXT);
     t.n_primary = t.cell_base[(size_t)n_chrom];
     if ((uint64_t)t.n_primary >= 0xFFFFFFF0ull) { t.why_not = "too many cells"; return; }
-    // entries: per chromosome, per slot union of [L, R), clipped to cells.  Chromosomes own disjoint,
-    // ascending cell ranges, so each one is built and sorted on its own (a thread per chromosome at a
-    // time) and the concatenation in chromosome order is the globally sorted list.
-    struct Iv { uint32_t slot; int32_t L, R; };
-    std::vector<std::vector<StabEntry>> per((size_t)n_chrom);
-    std::vector<int64_t> merged((size_t)n_chrom, 0);
-    auto build_chrom = [&](int c) {
-        std::vector<Iv> iv;
-        std::vector<StabEntry>& ent = per[(size_t)c];
-        iv.reserve((size_t)(chrom_off[c + 1] - chrom_off[c]));
-        for (int64_t i = chrom_off[c]; i < chrom_off[c + 1]; ++i)
-            if (R[i] > L[i]) iv.push_back({slot[i], L[i], R[i]});    // [L, R) empty: never stabbed
-        std::sort(iv.begin(), iv.end(), [](const Iv& a, const Iv& b) { return a.slot != b.slot ? a.slot < b.slot : a.L < b.L; });
-        ent.reserve(iv.size() + iv.size() / 2);
-        const int64_t n_cells_c = t.cell_base[(size_t)c + 1] - t.cell_base[(size_t)c];
-        size_t i = 0;
-        while (i < iv.size()) {
-            const uint32_t s = iv[i].slot;
-            int64_t a = iv[i].L, b = iv[i].R;
-            size_t j = i + 1;
-            while (j < iv.size() && iv[j].slot == s && iv[j].L <= b) { b = std::max<int64_t>(b, iv[j].R); ++j; }
-            merged[(size_t)c]++;
-            for (int64_t k = std::max<int64_t>(0, (a - STAB_EXT) >> shift); k <= (b - 1) >> shift && k < n_cells_c; ++k) {
-                const int64_t c0 = k << shift;
-                const int64_t lo = std::max(a, c0), hi = std::min(b, c0 + csize + STAB_EXT);
-                if (hi <= lo) continue;
-                ent.push_back({t.cell_base[(size_t)c] + k, (uint32_t)(lo - c0), (uint32_t)(hi - lo), s});
-            }
-            i = j;
-        }
-        std::sort(ent.begin(), ent.end(), [](const StabEntry& a, const StabEntry& b) {
-            if (a.cell != b.cell) return a.cell < b.cell;
-            if (a.s != b.s) return a.s < b.s;
-            return a.slot < b.slot;
-        });
-    };
-    {
-        const int n_threads = (int)std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 16u, (unsigned)std::max(n_chrom, 1)}));
-        std::atomic<int> next{0};
-        std::vector<std::thread> pool;
-        auto work = [&] {
-            for (int c; (c = next.fetch_add(1)) < n_chrom;) build_chrom(c);
-        };
-        for (int k = 1; k < n_threads; ++k) pool.emplace_back(work);
-        work();
-        for (auto& th : pool) th.join();
-    }
-    std::vector<StabEntry> ent;
-    {
-        size_t total = 0;
-        for (const auto& v : per) total += v.size();
-        ent.reserve(total);
-        for (int c = 0; c < n_chrom; ++c) {
-            t.n_merged += merged[(size_t)c];
-            ent.insert(ent.end(), per[(size_t)c].begin(), per[(size_t)c].end());
-            std::vector<StabEntry>().swap(per[(size_t)c]);
-        }
-    }
     t.n_entries = (int64_t)ent.size();
     // overflow sectors: consecutive per cell, cells in order; links are relative to the block base
     int64_t n_over = 0;

@@ -211,8 +211,34 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
         ctx->launches++;
         TEC_CUDA(cudaGetLastError());
     }
-    // cell table for the bulk fast path
+    // cell table, layout 2, for the two-pass bulk kernels (bulk2.cuh): the default bulk path
     {
+        StabTable2 st;
+        const int want = ctx->opt_stab_shift ? std::min(ctx->opt_stab_shift, 10) : TEC_BULK_STAB2_SHIFT;
+        stab2_build(st, n_chrom, chrom_off, L, R, fslot.data(), type_code, n_ensg, want, bucket_size);
+        if (st.why_not.empty()) {
+            std::vector<uint2> cells((size_t)n_chrom + 1, make_uint2(0u, 0u));      // + sentinel for ids outside the index
+            for (int c = 0; c < n_chrom; ++c)
+                if (chrom_valid[(size_t)c])
+                    cells[(size_t)c] = make_uint2((unsigned)st.cell_base[(size_t)c], (unsigned)(st.cell_base[(size_t)c + 1] - st.cell_base[(size_t)c]));
+            TEC_CUDA(cudaMalloc(&ix.s2_sectors, std::max<size_t>(st.sectors.size(), 8) * 4));
+            TEC_CUDA(cudaMalloc(&ix.s2_cells, cells.size() * sizeof(uint2)));
+            TEC_CUDA(cudaMalloc(&ix.s2_slot_type, st.slot_type.size()));
+            TEC_CUDA(cudaMalloc(&ix.s2_ovf_first, st.ovf_first.size() * 4));
+            TEC_CUDA(cudaMemcpyAsync(ix.s2_sectors, st.sectors.data(), st.sectors.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            TEC_CUDA(cudaMemcpyAsync(ix.s2_cells, cells.data(), cells.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+            TEC_CUDA(cudaMemcpyAsync(ix.s2_slot_type, st.slot_type.data(), st.slot_type.size(), cudaMemcpyHostToDevice, ctx->stream));
+            TEC_CUDA(cudaMemcpyAsync(ix.s2_ovf_first, st.ovf_first.data(), st.ovf_first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+            ix.s2_shift = st.shift; ix.s2_ext = st.ext; ix.s2_all_counted = st.all_counted; ix.has_stab2 = true; ix.stab2_bytes = st.bytes();
+            ix.s2_primary = st.n_primary; ix.s2_overflow = st.n_overflow; ix.s2_entries = st.n_entries;
+            ix.s2_edge_cells = st.n_edge_cells; ix.s2_twin_sectors = st.n_twin_sectors;
+        } else {
+            ix.stab_why_not = st.why_not;
+        }
+    }
+    // cell table, layout 1, of the round-1 kernel with in-kernel rings: only on request (bulk_algo=1)
+    if (ctx->opt_bulk_algo == 1) {
         StabTable st;
         stab_build(st, n_chrom, chrom_off, L, R, fslot.data(), type_code, n_ensg, ctx->opt_stab_shift ? ctx->opt_stab_shift : TEC_BULK_STAB_SHIFT);
         if (st.why_not.empty()) {
@@ -233,7 +259,7 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
             ix.st_shift = st.shift; ix.st_all_counted = st.all_counted; ix.has_stab = true; ix.stab_bytes = st.bytes();
             ix.st_primary = st.n_primary; ix.st_overflow = st.n_overflow; ix.st_entries = st.n_entries;
         } else {
-            ctx->err = "cell table not built: " + st.why_not;      // informational; exact kernel is used
+            ix.stab_why_not = st.why_not;
         }
     }
     // cell table of the single-cell Part 3: intervals [L-1, R+1), one slot per (ensg, strand) pair
@@ -300,12 +326,92 @@ extern "C" int tec_bulk_begin(tec_ctx* ctx, int paired, int qual) {
 
 #define TEC_LAUNCH_UNITS (int64_t(1) << 28)      // units per kernel launch (32-bit unit indices; slow list = 4 B per unit)
 
+// the fast kernel of bulk2.cuh loads the records of two units with one instruction per column
+static bool bulk2_aligned(int paired, const int32_t* start, const int32_t* end, const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
+    const uintptr_t a = paired ? 15 : 7, c = paired ? 7 : 3, b = paired ? 3 : 1;
+    return !(((uintptr_t)start & a) || (!paired && ((uintptr_t)end & a)) || ((uintptr_t)chrom & c) || ((uintptr_t)mapq & b) || ((uintptr_t)flag & b));
+}
+
+// two-pass bulk kernels: fast kernel (two units per thread, one sector per unit), second pass over the deferred
+// units, exact search on what the second pass flags
+static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, const int32_t* end,
+                            const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
+    IndexView iv = ctx->idx.view();
+    Stab2View sv = ctx->idx.stab2_view();
+    u64* counts = ctx->d_counts;
+    u64* stats = ctx->d_counts + ctx->idx.n_ensg;
+    const int64_t n_tiles = (n_units + 63) / 64;
+    const size_t all_bytes = (size_t)ctx->idx.n_ensg * 4;
+    const bool allhot = ctx->opt_all_hot != 0 && all_bytes + 2048 <= (size_t)ctx->smem_optin;
+    const int nt = allhot ? 1024 : 512;
+    const u32 n_hot = allhot ? (u32)ctx->idx.n_ensg : (u32)std::min<int64_t>(TEC_HOT_SLOTS, ctx->idx.n_ensg);
+    const size_t dyn = (size_t)n_hot * 4 + 128;            // + one scratch word per lane (b2_bump)
+    const int per_sm = allhot ? 1 : ctx->opt_ctas_per_sm;
+    const int wpb = nt / 32;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + wpb - 1) / wpb, (int64_t)ctx->n_sm * per_sm));
+    const int64_t n_warps = (int64_t)blocks * wpb;
+    const int64_t seg_cap = ((n_tiles + n_warps - 1) / n_warps) * 64;
+    if (n_warps * seg_cap > ctx->defer_cap || n_warps > ctx->defer_warps) {
+        TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_defer_list); cudaFree(ctx->d_defer_count);
+        ctx->d_defer_list = nullptr; ctx->d_defer_count = nullptr; ctx->defer_cap = 0; ctx->defer_warps = 0;
+        const int64_t cap = std::max<int64_t>(n_warps * seg_cap, 1 << 16), wcap = std::max<int64_t>(n_warps, 148 * 32);
+        TEC_CUDA(cudaMalloc(&ctx->d_defer_list, (size_t)cap * 4));
+        TEC_CUDA(cudaMalloc(&ctx->d_defer_count, (size_t)wcap * 4));
+        ctx->defer_cap = cap; ctx->defer_warps = wcap;
+    }
+    if (n_units + 1 > ctx->slow_cap) {
+        TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_slow_list);
+        ctx->d_slow_list = nullptr;
+        ctx->slow_cap = 0;
+        const int64_t cap = std::max<int64_t>(n_units + 1, 1 << 16);
+        TEC_CUDA(cudaMalloc(&ctx->d_slow_list, (size_t)cap * 4));
+        ctx->slow_cap = cap;
+    }
+    TEC_CUDA(cudaMemsetAsync(ctx->d_slow_list, 0, 4, ctx->stream));
+#define TEC_LAUNCH_FAST2(P, NT, AH)                                                                                        \
+    do {                                                                                                                   \
+        auto kfn = bulk2_fast_kernel<P, NT, AH>;                                                                           \
+        TEC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                        \
+        kfn<<<blocks, NT, dyn, ctx->stream>>>(sv, ctx->idx.n_chrom, (u32)n_units, ctx->qual, start, end, chrom, mapq, flag, \
+                                              counts, stats, ctx->d_defer_list, ctx->d_defer_count, (u32)seg_cap, n_hot);  \
+    } while (0)
+    if (ctx->paired) { if (allhot) TEC_LAUNCH_FAST2(true, 1024, true); else TEC_LAUNCH_FAST2(true, 512, false); }
+    else { if (allhot) TEC_LAUNCH_FAST2(false, 1024, true); else TEC_LAUNCH_FAST2(false, 512, false); }
+#undef TEC_LAUNCH_FAST2
+    ctx->launches++;
+    TEC_CUDA(cudaGetLastError());
+    const int b2 = (int)std::min<int64_t>((n_warps + 7) / 8, (int64_t)ctx->n_sm * 8);
+    if (ctx->paired)
+        bulk2_second_kernel<true><<<b2, 256, 0, ctx->stream>>>(sv, start, end, chrom, flag, counts, stats, ctx->d_defer_list, ctx->d_defer_count,
+                                                               (u32)seg_cap, (u32)n_warps, ctx->d_slow_list, (u32)ctx->idx.n_chrom);
+    else
+        bulk2_second_kernel<false><<<b2, 256, 0, ctx->stream>>>(sv, start, end, chrom, flag, counts, stats, ctx->d_defer_list, ctx->d_defer_count,
+                                                                (u32)seg_cap, (u32)n_warps, ctx->d_slow_list, (u32)ctx->idx.n_chrom);
+    ctx->launches++;
+    TEC_CUDA(cudaGetLastError());
+    // exact search on the units of EDGE cells / large ensg sets (has_stab = 0: no layout-1 table lookups)
+    const int sblocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)ctx->n_sm * 4);
+    StabView none = StabView();
+    if (ctx->paired)
+        bulk_slow_kernel<true><<<sblocks, 256, 0, ctx->stream>>>(iv, none, 0, start, end, chrom, counts, stats, ctx->d_slow_list);
+    else
+        bulk_slow_kernel<false><<<sblocks, 256, 0, ctx->stream>>>(iv, none, 0, start, end, chrom, counts, stats, ctx->d_slow_list);
+    ctx->launches++;
+    TEC_CUDA(cudaGetLastError());
+    return TEC_OK;
+}
+
 static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, const int32_t* end,
                            const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
     IndexView iv = ctx->idx.view();
     u64* counts = ctx->d_counts;
     u64* stats = ctx->d_counts + ctx->idx.n_ensg;
-    const bool use_stab = ctx->idx.has_stab && ctx->opt_bulk_algo != 0;
+    const bool use_stab2 = ctx->idx.has_stab2 && (ctx->opt_bulk_algo == -1 || ctx->opt_bulk_algo == 2) &&
+                           bulk2_aligned(ctx->paired, start, end, chrom, mapq, flag);
+    if (use_stab2) return bulk2_launch_one(ctx, n_units, start, end, chrom, mapq, flag);
+    const bool use_stab = ctx->idx.has_stab && ctx->opt_bulk_algo == 1;
     if (use_stab) {
         // fast kernel: one warp per 32 units, persistent grid; then the exact kernel on flagged units
         const int64_t n_tiles = (n_units + 31) / 32;
@@ -373,7 +479,8 @@ static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, 
 static int bulk_launch(tec_ctx* ctx, int64_t n_rec, const int32_t* start, const int32_t* end,
                        const uint16_t* chrom, const uint8_t* mapq, const uint8_t* flag) {
     const int64_t n_units = ctx->paired ? n_rec / 2 : n_rec;
-    if (ctx->opt_bulk_algo == 1 && !ctx->idx.has_stab) TEC_FAIL(TEC_ERR_STATE, "bulk_algo=1 but the index has no cell table");
+    if (ctx->opt_bulk_algo == 1 && !ctx->idx.has_stab) TEC_FAIL(TEC_ERR_STATE, "bulk_algo=1 but the index has no layout-1 cell table (set the option before tec_index_upload)");
+    if (ctx->opt_bulk_algo == 2 && !ctx->idx.has_stab2) TEC_FAIL(TEC_ERR_STATE, "bulk_algo=2 but the index has no cell table: " + ctx->idx.stab_why_not);
     const int64_t rpu = ctx->paired ? 2 : 1;
     for (int64_t off = 0; off < n_units; off += TEC_LAUNCH_UNITS) {
         const int64_t n = std::min<int64_t>(TEC_LAUNCH_UNITS, n_units - off);
@@ -461,7 +568,7 @@ extern "C" void* tec_bulk_counts_dev(tec_ctx* ctx) { return ctx ? (void*)ctx->d_
 extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return TEC_ERR_ARG;
     const std::string k(key);
-    if (k == "bulk_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "bulk_algo: -1, 0 or 1"); ctx->opt_bulk_algo = (int)value; }
+    if (k == "bulk_algo") { if (value < -1 || value > 2) TEC_FAIL(TEC_ERR_ARG, "bulk_algo: -1, 0, 1 or 2"); ctx->opt_bulk_algo = (int)value; }
     else if (k == "stab_shift") { if (value && (value < 8 || value > STAB_MAX_SHIFT)) TEC_FAIL(TEC_ERR_ARG, "stab_shift: 0 (default) or 8..11"); ctx->opt_stab_shift = (int)value; }
     else if (k == "sc_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "sc_algo: -1, 0 or 1"); ctx->opt_sc_algo = (int)value; }
     else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
@@ -476,8 +583,21 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
 extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
     if (!ctx || !key) return -1;
     const std::string k(key);
-    if (k == "has_stab") return ctx->idx.has_stab ? 1 : 0;
-    if (k == "stab_bytes") return (int64_t)ctx->idx.stab_bytes;
+    if (k == "has_stab") return (ctx->idx.has_stab || ctx->idx.has_stab2) ? 1 : 0;
+    if (k == "stab_bytes") return (int64_t)(ctx->idx.has_stab2 ? ctx->idx.stab2_bytes : ctx->idx.stab_bytes);
+    if (k == "has_stab2") return ctx->idx.has_stab2 ? 1 : 0;
+    if (k == "stab2_sector_bytes") return (ctx->idx.s2_primary + ctx->idx.s2_overflow) * 32;
+    if (k == "stab2_edge_cells") return ctx->idx.s2_edge_cells;
+    if (k == "stab2_twin_sectors") return ctx->idx.s2_twin_sectors;
+    if (k == "last_deferred_units") {      // units the last fast-kernel launch handed to the second pass
+        if (!ctx->d_defer_count || !ctx->defer_warps) return 0;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+        std::vector<u32> h((size_t)ctx->defer_warps);
+        if (cudaMemcpy(h.data(), ctx->d_defer_count, h.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        int64_t n = 0;
+        for (u32 x : h) n += x;
+        return n;
+    }
     if (k == "has_sc_stab") return ctx->idx.has_sc_stab ? 1 : 0;
     if (k == "sc_stab_bytes") return (int64_t)ctx->idx.sc_stab_bytes;
     if (k == "n_sm") return ctx->n_sm;
@@ -489,9 +609,9 @@ extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
         if (cudaMemcpy(&n, ctx->d_slow_list, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         return (int64_t)n;
     }
-    if (k == "stab_primary") return ctx->idx.st_primary;
-    if (k == "stab_overflow") return ctx->idx.st_overflow;
-    if (k == "stab_entries") return ctx->idx.st_entries;
+    if (k == "stab_primary") return ctx->idx.has_stab2 ? ctx->idx.s2_primary : ctx->idx.st_primary;
+    if (k == "stab_overflow") return ctx->idx.has_stab2 ? ctx->idx.s2_overflow : ctx->idx.st_overflow;
+    if (k == "stab_entries") return ctx->idx.has_stab2 ? ctx->idx.s2_entries : ctx->idx.st_entries;
     return -1;
 }
 

@@ -24,11 +24,12 @@ def test_bulk_golden_through_mirror(monkeypatch, tmp_path, name):
     run_bulk_case(monkeypatch, tmp_path, name, _lib.Engine, batch=1024)
 
 
-@pytest.mark.parametrize("algo,shift", [(0, 11), (1, 11), (1, 9), (1, 8)])
+@pytest.mark.parametrize("algo,shift", [(0, 11), (1, 11), (1, 9), (1, 8), (2, 10), (2, 9), (2, 8)])
 @pytest.mark.parametrize("paired", [False, True])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_bulk_matches_oracle_seeded(engine, paired, seed, algo, shift):
-    """algo 0 = exact search kernel, 1 = stab-table kernel (several cell sizes)."""
+    """algo 0 = exact search kernel, 1 = cell-table kernel with in-kernel rings (round 1), 2 = two-pass kernels of
+    bulk2.cuh (the default), several cell sizes."""
     idx = synth.synth_index(seed, n_te=30000, n_exon=9000, n_gene=600, chrom_len=3_000_000, n_chrom=3)
     r = synth.synth_bulk_reads(seed + 10, idx, 60000, paired=paired, edge_frac=0.1)
     engine.set_option("bulk_algo", algo)
@@ -49,7 +50,7 @@ def test_bulk_matches_oracle_seeded(engine, paired, seed, algo, shift):
     engine.set_option("stab_shift", 0)
 
 
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_bulk_dense_overlaps_and_gapped_reads(engine, algo):
     """Dense TE pile-ups on a tiny chromosome (sets larger than the register set -> exact path),
     long N-gapped SE reads whose two points fall in different cells."""
