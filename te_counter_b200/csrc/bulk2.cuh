@@ -124,21 +124,39 @@ __device__ __forceinline__ u32 b2_hi16(u32 w) { return __byte_perm(w, 0u, 0x4432
 // what a thread of the fast kernel carries across tiles
 struct B2Thread {
     u32 n_assigned, n_lowq, n_badchrom, n_qcfail;
-    u32* wp;                      // next free entry of the warp's segment of the deferred list (warp-uniform)
+    uint4* wp;                    // next free entry of the warp's segment of the deferred list (warp-uniform)
 };
 struct B2Const {
-    u32 reject2, lim, lt_mask, hot_addr, scratch_addr, one, n_hot, n_units;
+    u32 reject2, lim, lt_mask, hot_addr, scratch_addr, one, n_hot, n_units, mode;
     int shift, cmask, qual, n_chrom;
+    u64 pol_table;                // L2 policy of the table loads (evict_last when mode & B2_MODE_KEEP)
+};
+#define B2_DEF_GATHER 0x80000000u
+#define B2_MODE_KEEP 1u           // table sectors: L2 evict_last (the records stream through with evict_first)
+#define B2_MODE_PREFETCH 2u       // request the next tile's sectors into L2 one turn ahead
+
+__device__ __forceinline__ Sector ld_sector_pol(const u32* sectors, u32 idx, u64 pol) {
+    Sector r;
+    const u32* p = sectors + (size_t)idx * 8;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p), "l"(pol));
+    return r;
+}
+
+// what phase A leaves for phase B: per unit the sector and the two cell-relative points; per tile the flag bits
+struct B2Stage {
+    u32 sec[B2_UPT];              // sector index (0 when the unit is not answered in place)
+    u32 pts[B2_UPT];              // ra | rb << 16
+    u32 flags;                    // bit 2j: unit j passed the filter, bit 2j+1: one sector covers both points
 };
 
-// One turn of a warp: 64 consecutive units, two per lane.  FULL: every unit of the tile exists.
-template <bool PAIRED, bool ALLHOT, bool FULL>
-__device__ __forceinline__ void b2_tile(const B2Raw<PAIRED>& cur, const u32 u0, const Stab2View& sv, const B2Const& k,
-                                        B2Thread& t, u64* __restrict__ counts, u64* __restrict__ stats) {
-    bool look[B2_UPT], ok[B2_UPT];
-    int ra[B2_UPT], rb[B2_UPT];
-    u32 rmax[B2_UPT], sec[B2_UPT];
-    // ---- filter (te_count.py:78-102 / :203-218) and the sector each unit needs
+// Phase A of a warp's turn (64 consecutive units, two per lane): filter (te_count.py:78-102 / :203-218) and
+// the sector each unit needs.  FULL: every unit of the tile exists.
+template <bool PAIRED, bool FULL>
+__device__ __forceinline__ void b2_phase_a(const B2Raw<PAIRED>& cur, const u32 u0, const Stab2View& sv, const B2Const& k,
+                                           B2Thread& t, B2Stage& st) {
+    st.flags = 0;
 #pragma unroll
     for (int j = 0; j < B2_UPT; ++j) {
         u32 fl, q, c;
@@ -156,30 +174,49 @@ __device__ __forceinline__ void b2_tile(const B2Raw<PAIRED>& cur, const u32 u0, 
         t.n_lowq += live & !f_qc & f_lq;
         t.n_badchrom += live & !(f_qc | f_lq | f_nm) & f_bc;
         // a name mismatch (the reference dies there, :92-94) is left to the second pass, like every rare case
-        look[j] = live & !(f_qc | f_lq) & (f_nm | !f_bc);
+        const bool look = live & !(f_qc | f_lq) & (f_nm | !f_bc);
         // point A x = loc1, point B x = loc2 - 1 (bulk.cuh header); the cell of the smaller one
         const int xa = loc1, xb = loc2 - 1;
         const int mn = min(xa, xb);
         const int kc = mn >> k.shift;                         // arithmetic shift: negative stays negative
         const int base = mn & ~k.cmask;
-        ra[j] = xa - base;
-        rb[j] = xb - base;
-        rmax[j] = (u32)(max(xa, xb) - base);
-        ok[j] = look[j] & !f_nm & ((u32)kc < cell.y) & (rmax[j] < k.lim);
-        sec[j] = ok[j] ? cell.x + (u32)kc : 0u;
-        asm volatile("" : "+r"(sec[j]));                      // select the index, not the 64-bit address
+        const u32 ra = (u32)(xa - base), rb = (u32)(xb - base);
+        const u32 rmax = (u32)(max(xa, xb) - base);
+        const bool ok = look & !f_nm & ((u32)kc < cell.y) & (rmax < k.lim);
+        st.sec[j] = ok ? cell.x + (u32)kc : 0u;
+        asm volatile("" : "+r"(st.sec[j]));                   // select the index, not the 64-bit address
+        st.pts[j] = ra | (rb << 16);                          // garbage unless ok
+        st.flags |= ((u32)look << (2 * j)) | ((u32)ok << (2 * j + 1));
     }
-    Sector s[B2_UPT];
-#pragma unroll
-    for (int j = 0; j < B2_UPT; ++j) s[j] = ld_sector(sv.sectors, sec[j]);
+}
+
+__device__ __forceinline__ void b2_prefetch(const B2Stage& st, const Stab2View& sv, const B2Const& k) {
 #pragma unroll
     for (int j = 0; j < B2_UPT; ++j) {
+        const u32* p = sv.sectors + (size_t)st.sec[j] * 8;
+        if (k.mode & B2_MODE_KEEP) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(p));
+        else asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    }
+}
+
+// Phase B: the sector test, the tally and the deferred list.
+template <bool ALLHOT>
+__device__ __forceinline__ void b2_phase_b(const B2Stage& st, const u32 u0, const Stab2View& sv, const B2Const& k,
+                                           B2Thread& t, u64* __restrict__ counts, u64* __restrict__ stats) {
+    Sector s[B2_UPT];
+#pragma unroll
+    for (int j = 0; j < B2_UPT; ++j) s[j] = ld_sector_pol(sv.sectors, st.sec[j], k.pol_table);
+#pragma unroll
+    for (int j = 0; j < B2_UPT; ++j) {
+        const bool look = (st.flags >> (2 * j)) & 1u, ok = (st.flags >> (2 * j + 1)) & 1u;
+        const u32 ra = st.pts[j] & 0xFFFFu, rb = st.pts[j] >> 16;
+        const u32 rmax = max(ra, rb);
         const u32 w2 = s[j].w[2];
-        const u32 thr = (w2 >> 16) & 0x7FFu;
-        const bool inplace = ok[j] & (rmax[j] < thr);
-        const bool defer = look[j] & !inplace;
+        const u32 thr = (w2 >> 16) & S2_THR_MASK;
+        const bool inplace = ok & (rmax < thr);
+        const bool defer = look & !inplace;
         // ---- five interval tests, both points at once (16-bit lanes, stab_build.h)
-        const PointK pa = make_point((u32)ra[j]), pb = make_point((u32)rb[j]);
+        const PointK pa = make_point(ra), pb = make_point(rb);
         const u32 m = inplace ? 0x80008000u : 0u;
         u32 a0 = (((pa.xg - s[j].w[0]) & (s[j].w[3] + pa.kg)) | ((pb.xg - s[j].w[0]) & (s[j].w[3] + pb.kg))) & m;
         u32 a1 = (((pa.xg - s[j].w[1]) & (s[j].w[4] + pa.kg)) | ((pb.xg - s[j].w[1]) & (s[j].w[4] + pb.kg))) & m;
@@ -212,8 +249,10 @@ __device__ __forceinline__ void b2_tile(const B2Raw<PAIRED>& cur, const u32 u0, 
         b2_bump<ALLHOT>(a1 & 0x80000000u, b2_hi16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
         b2_bump<ALLHOT>(a2 != 0, b2_hi16(s[j].w[5]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
         // ---- everything else goes to the second pass: the warp's own segment of the list, no atomics
+        // {unit, sector | B2_DEF_GATHER, points}: a unit that one sector covers is walked from there; the others
+        // (points far apart, outside the cells, name mismatch) are looked up again from their records
         const u32 dm = __ballot_sync(0xFFFFFFFFu, defer);
-        if (defer) t.wp[__popc(dm & k.lt_mask)] = u0 + j;
+        if (defer) t.wp[__popc(dm & k.lt_mask)] = make_uint4(u0 + j, ok ? st.sec[j] : B2_DEF_GATHER, st.pts[j], 0u);
         t.wp += __popc(dm);
     }
 }
@@ -224,7 +263,7 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                   const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ mapq,
                   const uint8_t* __restrict__ flag, u64* __restrict__ counts, u64* __restrict__ stats,
-                  u32* __restrict__ defer_list, u32* __restrict__ defer_count, u32 seg_cap, u32 n_hot) {
+                  uint4* __restrict__ defer_list, u32* __restrict__ defer_count, u32 seg_cap, u32 n_hot, u32 mode) {
     constexpr int WARPS = NT / 32;
     __shared__ u64 s_stats[TEC_BULK_NSTATS];
     extern __shared__ __align__(16) u32 s_hot_dyn[];
@@ -251,35 +290,55 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
     k.n_units = n_units;
     k.qual = qual;
     k.n_chrom = n_chrom;
+    k.mode = mode;
+    if (mode & B2_MODE_KEEP) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(k.pol_table));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(k.pol_table));
     const u32 gw = blockIdx.x * WARPS + wib;
-    u32* const my_list = defer_list + (size_t)gw * seg_cap;
+    uint4* const my_list = defer_list + (size_t)gw * seg_cap;
     B2Thread t;
     t.n_assigned = t.n_lowq = t.n_badchrom = t.n_qcfail = 0;
     t.wp = my_list;
-    // full tiles of 64 units, warp-strided; the records of the next tile are requested before the current
-    // one is looked up (two register buffers, swapped by unrolling)
+    // Full tiles of 64 units, warp-strided, software-pipelined over three turns: the records of tile i+2 are
+    // requested, tile i+1 is filtered and its sectors are requested into L2, tile i is tested and tallied.
     const u32 n_full = n_units >> 6;
     const u32 stride = gridDim.x * WARPS;
+    const bool pf = (mode & B2_MODE_PREFETCH) != 0;
     u32 tile = gw;
-    B2Raw<PAIRED> ra, rb;
-    if (tile < n_full) b2_load<PAIRED, true>(ra, tile * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+    B2Raw<PAIRED> raw;
+    B2Stage sa, sb;
+    if (tile < n_full) {
+        b2_load<PAIRED, true>(raw, tile * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+        b2_phase_a<PAIRED, true>(raw, tile * 64 + 2 * lane, sv, k, t, sa);
+        if (pf) b2_prefetch(sa, sv, k);
+        if (tile + stride < n_full) b2_load<PAIRED, true>(raw, (tile + stride) * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+    }
     while (tile < n_full) {
+        // here: sa = stage of `tile`; raw = records of tile + stride (if it exists)
         u32 nx = tile + stride;
-        if (nx < n_full) b2_load<PAIRED, true>(rb, nx * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
-        b2_tile<PAIRED, ALLHOT, true>(ra, tile * 64 + 2 * lane, sv, k, t, counts, stats);
+        if (nx < n_full) {
+            b2_phase_a<PAIRED, true>(raw, nx * 64 + 2 * lane, sv, k, t, sb);
+            if (pf) b2_prefetch(sb, sv, k);
+            if (nx + stride < n_full) b2_load<PAIRED, true>(raw, (nx + stride) * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+        }
+        b2_phase_b<ALLHOT>(sa, tile * 64 + 2 * lane, sv, k, t, counts, stats);
         tile = nx;
         if (tile >= n_full) break;
         nx = tile + stride;
-        if (nx < n_full) b2_load<PAIRED, true>(ra, nx * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
-        b2_tile<PAIRED, ALLHOT, true>(rb, tile * 64 + 2 * lane, sv, k, t, counts, stats);
+        if (nx < n_full) {
+            b2_phase_a<PAIRED, true>(raw, nx * 64 + 2 * lane, sv, k, t, sa);
+            if (pf) b2_prefetch(sa, sv, k);
+            if (nx + stride < n_full) b2_load<PAIRED, true>(raw, (nx + stride) * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+        }
+        b2_phase_b<ALLHOT>(sb, tile * 64 + 2 * lane, sv, k, t, counts, stats);
         tile = nx;
     }
     // the last, partial tile belongs to the warp whose turn it would be
     if ((n_units & 63u) && (n_full % stride) == gw) {
         const u32 u0 = n_full * 64 + 2 * lane;
-        ra = B2Raw<PAIRED>();
-        b2_load<PAIRED, false>(ra, u0, n_units, start, end, chrom, mapq, flag, pol);
-        b2_tile<PAIRED, ALLHOT, false>(ra, u0, sv, k, t, counts, stats);
+        raw = B2Raw<PAIRED>();
+        b2_load<PAIRED, false>(raw, u0, n_units, start, end, chrom, mapq, flag, pol);
+        b2_phase_a<PAIRED, false>(raw, u0, sv, k, t, sa);
+        b2_phase_b<ALLHOT>(sa, u0, sv, k, t, counts, stats);
     }
     if (lane == 0) defer_count[gw] = (u32)(t.wp - my_list);
     u64 v[4] = {t.n_assigned, t.n_lowq, t.n_badchrom, t.n_qcfail};
@@ -299,8 +358,9 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Second pass: the units the fast kernel deferred (they passed the filter).  One thread per unit; warp gw
-// reads the segment warp gw of the fast kernel wrote.
+// Second pass: the units the fast kernel deferred (they passed the filter).  One thread per unit.  The deferred
+// list is partitioned by the warps of the fast kernel (n_seg segments of seg_cap entries, defer_count[] used);
+// here `parts` warps share a segment, 32 entries at a time.
 __device__ __forceinline__ u32 b2_sector_hits(const Sector& s, const PointK a, const PointK b) {
     const u32 a0 = ((a.xg - s.w[0]) & (s.w[3] + a.kg)) | ((b.xg - s.w[0]) & (s.w[3] + b.kg));
     const u32 a1 = ((a.xg - s.w[1]) & (s.w[4] + a.kg)) | ((b.xg - s.w[1]) & (s.w[4] + b.kg));
@@ -309,10 +369,10 @@ __device__ __forceinline__ u32 b2_sector_hits(const Sector& s, const PointK a, c
 }
 
 template <bool PAIRED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                     const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ flag, u64* __restrict__ counts, u64* __restrict__ stats,
-                    const u32* __restrict__ defer_list, const u32* __restrict__ defer_count, u32 seg_cap, u32 n_warps,
+                    const uint4* __restrict__ defer_list, const u32* __restrict__ defer_count, u32 seg_cap, u32 n_seg, u32 parts,
                     u32* __restrict__ slow_list, u32 sv_n_chrom) {
     // hot ensg counters privatised per CTA (a Zipf-hot TE name would otherwise serialise in one L2 slice)
     __shared__ u32 s_hot[TEC_HOT_SLOTS];
@@ -324,31 +384,36 @@ bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32
     const int cmask = (1 << shift) - 1;
     const u32 lim = (u32)(cmask + 1 + sv.ext);
     u32 n_assigned = 0;
-    for (u32 gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gw < n_warps; gw += gridDim.x * (blockDim.x >> 5)) {
-        const u32 cnt = __ldg(defer_count + gw);
-        const u32* const list = defer_list + (size_t)gw * seg_cap;
-        for (u32 i0 = 0; i0 < cnt; i0 += 32) {
+    const u32 n_w = n_seg * parts;
+    for (u32 w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_w; w += gridDim.x * (blockDim.x >> 5)) {
+        const u32 seg = w % n_seg, part = w / n_seg;
+        const u32 cnt = __ldg(defer_count + seg);
+        const uint4* const list = defer_list + (size_t)seg * seg_cap;
+        for (u32 i0 = part * 32; i0 < cnt; i0 += parts * 32) {
             const bool live = i0 + lane < cnt;
             bool exact = false;
             u32 u = 0;
             if (live) {
-                u = __ldg(list + i0 + lane);
-                int c, loc1, loc2;
-                bool name_crash = false;
-                if (PAIRED) {
-                    c = chrom[2 * (size_t)u];
-                    const int2 s2 = *reinterpret_cast<const int2*>(start + 2 * (size_t)u);
-                    loc1 = s2.x; loc2 = s2.y;
-                    name_crash = (flag[2 * (size_t)u] & TEC_F_NAME_MISMATCH) != 0;
-                } else { c = chrom[u]; loc1 = start[u]; loc2 = end[u]; }
-                if (name_crash) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);                // :92-94
-                // (a unit with a name mismatch may sit on a chromosome without cells: zero cells, no probe)
-                const uint2 cell = name_crash ? make_uint2(0u, 0u) : __ldg(sv.cells + min((u32)c, sv_n_chrom));
-                const int xa = loc1, xb = loc2 - 1;
+                const uint4 rec = __ldg(list + i0 + lane);
+                u = rec.x;
                 // probes: one sector chain holding both points, or one chain per point
                 u32 prim[2], pts[2];                                       // pts = ra | rb << 16 (S2_R_NONE = none)
                 int np = 0;
-                {
+                if (!(rec.y & B2_DEF_GATHER)) {
+                    prim[0] = rec.y; pts[0] = rec.z; np = 1;
+                } else {
+                    int c, loc1, loc2;
+                    bool name_crash = false;
+                    if (PAIRED) {
+                        c = chrom[2 * (size_t)u];
+                        const int2 s2 = *reinterpret_cast<const int2*>(start + 2 * (size_t)u);
+                        loc1 = s2.x; loc2 = s2.y;
+                        name_crash = (flag[2 * (size_t)u] & TEC_F_NAME_MISMATCH) != 0;
+                    } else { c = chrom[u]; loc1 = start[u]; loc2 = end[u]; }
+                    if (name_crash) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);            // :92-94
+                    // (a unit with a name mismatch may sit on a chromosome without cells: zero cells, no probe)
+                    const uint2 cell = name_crash ? make_uint2(0u, 0u) : __ldg(sv.cells + min((u32)c, sv_n_chrom));
+                    const int xa = loc1, xb = loc2 - 1;
                     const int mn = min(xa, xb), k = mn >> shift, base = mn & ~cmask;
                     const u32 rm = (u32)(max(xa, xb) - base);
                     if ((u32)k < cell.y && rm < lim) {
@@ -369,6 +434,7 @@ bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32
                     const PointK pa = make_point(ra), pb = make_point(rb);
                     const int rm = max(ra == S2_R_NONE ? -1 : (int)ra, rb == S2_R_NONE ? -1 : (int)rb);
                     u32 sec = prim[p];
+                    const u32 ovf = __ldg(sv.ovf_first + sec);             // requested together with the primary sector
                     for (;;) {
                         const Sector s = ld_sector(sv.sectors, sec);
                         const u32 header = s.w[2] >> 16;
@@ -390,8 +456,8 @@ bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32
                             }
                         }
                         if (!(header & S2_H_MORE)) break;
-                        if (!(first && (header & S2_H_EDGE)) && rm < (int)(header & 0x7FFu)) break;
-                        sec = first ? __ldg(sv.ovf_first + sec) : sec + 1;
+                        if (!(first && (header & S2_H_EDGE)) && rm < (int)(header & S2_THR_MASK)) break;
+                        sec = first ? ovf : sec + 1;
                     }
                 }
                 if (nd > B2_MAXD) exact = true;

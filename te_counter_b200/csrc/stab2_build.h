@@ -8,16 +8,16 @@
 //        w0 = s0 | s1 << 16     w1 = s2 | s3 << 16     w2 = s4 | header << 16
 //        w3 = e0 | e1 << 16     w4 = e2 | e3 << 16     w5 = e4 | slot4  << 16
 //        w6 = slot0 | slot1 << 16                       w7 = slot2 | slot3 << 16
-//   header bits 0..10  thr: a unit whose larger cell-relative point is >= thr cannot be answered from this
-//                      sector alone.  0x7FF = never (no point reaches it), 0 = always.
-//               bit 11 EDGE  the cell covers a position where the reference's two-bucket candidate set can
+//   header bits 0..11  thr: a unit whose larger cell-relative point is >= thr cannot be answered from this
+//                      sector alone.  0xFFF = never (no point reaches it), 0 = always.
+//               bit 12 EDGE  the cell covers a position where the reference's two-bucket candidate set can
 //                      differ from a plain stab query (a feature with L % bs == 0 or (R + 1) % bs == 0,
 //                      bulk.cuh header): such units take the exact search.  thr = 0.
-//               bit 12 (unused)
 //               bit 13 MORE  the cell's list continues in overflow sectors
 //               bit 14 TW23  entries 2 and 3 carry the same ensg        (w2 bit 30)
 //               bit 15 TW01  entries 0 and 1 carry the same ensg        (w2 bit 31)
-//   unused entries: s = 0x7FF, e = 0 (never contain a point), slot = 0xFFFF.
+//   unused entries: s = 0xFFF, e = 0 (never contain a point), slot = 0xFFFF.  Cell-relative positions are below
+//   2^shift + ext <= 2304, so they fit the 12 bits.
 //
 // The entries with the smallest starts stay in the primary sector (at most five), so with thr = start of
 // the first entry that did not fit a point below thr cannot touch anything in the overflow sectors.
@@ -32,8 +32,9 @@
 #include "stab_build.h"
 
 #define S2_ENTRIES 5
-#define S2_THR_NEVER 0x7FFu
-#define S2_H_EDGE (1u << 11)
+#define S2_THR_NEVER 0xFFFu
+#define S2_THR_MASK 0xFFFu
+#define S2_H_EDGE (1u << 12)
 #define S2_H_MORE (1u << 13)
 #define S2_H_TW23 (1u << 14)
 #define S2_H_TW01 (1u << 15)
@@ -55,7 +56,7 @@ struct StabTable2 {
 
 inline void stab2_pack(uint32_t* w, const StabEntry* const* e, int n, uint32_t header) {
     uint32_t sv[5], ev[5], sl[5];
-    for (int i = 0; i < 5; ++i) { sv[i] = 0x7FFu; ev[i] = 0u; sl[i] = 0xFFFFu; }
+    for (int i = 0; i < 5; ++i) { sv[i] = 0xFFFu; ev[i] = 0u; sl[i] = 0xFFFFu; }
     for (int i = 0; i < n; ++i) {
         if (!e[i]) continue;
         sv[i] = e[i]->s; ev[i] = e[i]->s + e[i]->len - 1; sl[i] = e[i]->slot & 0xFFFFu;
@@ -83,7 +84,7 @@ inline void stab2_build(StabTable2& t, int n_chrom, const int64_t* chrom_off, co
                         const uint32_t* slot, const uint8_t* type, int n_slots, int shift, int bs) {
     t = StabTable2();
     t.shift = shift;
-    if (shift < 8 || shift > 10) { t.why_not = "cell shift out of range (8..10)"; return; }   // relative positions < 2^shift + ext < 0x7FF
+    if (shift < 8 || shift > 11) { t.why_not = "cell shift out of range (8..11)"; return; }   // relative positions < 2^shift + ext < 0xFFF
     if (n_slots > STAB_MAX_SLOTS) { t.why_not = "more than 65535 ensg (16-bit slots)"; return; }
     t.n_slots = n_slots;
     t.slot_type.assign((size_t)std::max(n_slots, 1), 0xFF);
@@ -216,7 +217,7 @@ inline int stab2_unit(const StabTable2& t, int c, int64_t xa, int64_t xb, std::v
     if (k >= 0 && k < ncc && rmax < S + t.ext) {
         const uint32_t* w = &t.sectors[(size_t)(t.cell_base[(size_t)c] + k) * 8];
         const uint32_t header = w[2] >> 16;
-        if (rmax < (int64_t)(header & 0x7FFu)) {
+        if (rmax < (int64_t)(header & S2_THR_MASK)) {
             bool hit[5];
             for (int i = 0; i < 5; ++i) hit[i] = stab2_entry_hit(w, i, (uint32_t)(xa - base)) || stab2_entry_hit(w, i, (uint32_t)(xb - base));
             if ((header & S2_H_TW01) && hit[0]) hit[1] = false;
@@ -247,7 +248,7 @@ inline int stab2_unit(const StabTable2& t, int c, int64_t xa, int64_t xb, std::v
                 if (stab2_entry_hit(w, i, pr[p].ra) || stab2_entry_hit(w, i, pr[p].rb)) out.push_back(stab2_entry_slot(w, i));
             if (!(header & S2_H_MORE)) break;
             const bool forced = sec == pr[p].prim && (header & S2_H_EDGE);
-            if (!forced && rm < (int)(header & 0x7FFu)) break;
+            if (!forced && rm < (int)(header & S2_THR_MASK)) break;
             sec = (sec == pr[p].prim) ? (int64_t)t.ovf_first[(size_t)sec] : sec + 1;
         }
     }

@@ -214,7 +214,7 @@ extern "C" int tec_index_upload(tec_ctx* ctx, int32_t n_chrom, const int64_t* ch
     // cell table, layout 2, for the two-pass bulk kernels (bulk2.cuh): the default bulk path
     {
         StabTable2 st;
-        const int want = ctx->opt_stab_shift ? std::min(ctx->opt_stab_shift, 10) : TEC_BULK_STAB2_SHIFT;
+        const int want = ctx->opt_stab_shift ? ctx->opt_stab_shift : TEC_BULK_STAB2_SHIFT;
         stab2_build(st, n_chrom, chrom_off, L, R, fslot.data(), type_code, n_ensg, want, bucket_size);
         if (st.why_not.empty()) {
             std::vector<uint2> cells((size_t)n_chrom + 1, make_uint2(0u, 0u));      // + sentinel for ids outside the index
@@ -356,7 +356,7 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
         cudaFree(ctx->d_defer_list); cudaFree(ctx->d_defer_count);
         ctx->d_defer_list = nullptr; ctx->d_defer_count = nullptr; ctx->defer_cap = 0; ctx->defer_warps = 0;
         const int64_t cap = std::max<int64_t>(n_warps * seg_cap, 1 << 16), wcap = std::max<int64_t>(n_warps, 148 * 32);
-        TEC_CUDA(cudaMalloc(&ctx->d_defer_list, (size_t)cap * 4));
+        TEC_CUDA(cudaMalloc(&ctx->d_defer_list, (size_t)cap * 16));
         TEC_CUDA(cudaMalloc(&ctx->d_defer_count, (size_t)wcap * 4));
         ctx->defer_cap = cap; ctx->defer_warps = wcap;
     }
@@ -375,20 +375,22 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
         auto kfn = bulk2_fast_kernel<P, NT, AH>;                                                                           \
         TEC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                        \
         kfn<<<blocks, NT, dyn, ctx->stream>>>(sv, ctx->idx.n_chrom, (u32)n_units, ctx->qual, start, end, chrom, mapq, flag, \
-                                              counts, stats, ctx->d_defer_list, ctx->d_defer_count, (u32)seg_cap, n_hot);  \
+                                              counts, stats, (uint4*)ctx->d_defer_list, ctx->d_defer_count, (u32)seg_cap, n_hot, \
+                                              (u32)ctx->opt_bulk_mode);                                                    \
     } while (0)
     if (ctx->paired) { if (allhot) TEC_LAUNCH_FAST2(true, 1024, true); else TEC_LAUNCH_FAST2(true, 512, false); }
     else { if (allhot) TEC_LAUNCH_FAST2(false, 1024, true); else TEC_LAUNCH_FAST2(false, 512, false); }
 #undef TEC_LAUNCH_FAST2
     ctx->launches++;
     TEC_CUDA(cudaGetLastError());
-    const int b2 = (int)std::min<int64_t>((n_warps + 7) / 8, (int64_t)ctx->n_sm * 8);
+    const int parts = std::max(1, ctx->opt_second_parts);
+    const int b2 = (int)std::min<int64_t>((n_warps * parts + 7) / 8, (int64_t)ctx->n_sm * 6);
     if (ctx->paired)
-        bulk2_second_kernel<true><<<b2, 256, 0, ctx->stream>>>(sv, start, end, chrom, flag, counts, stats, ctx->d_defer_list, ctx->d_defer_count,
-                                                               (u32)seg_cap, (u32)n_warps, ctx->d_slow_list, (u32)ctx->idx.n_chrom);
+        bulk2_second_kernel<true><<<b2, 256, 0, ctx->stream>>>(sv, start, end, chrom, flag, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count,
+                                                               (u32)seg_cap, (u32)n_warps, (u32)parts, ctx->d_slow_list, (u32)ctx->idx.n_chrom);
     else
-        bulk2_second_kernel<false><<<b2, 256, 0, ctx->stream>>>(sv, start, end, chrom, flag, counts, stats, ctx->d_defer_list, ctx->d_defer_count,
-                                                                (u32)seg_cap, (u32)n_warps, ctx->d_slow_list, (u32)ctx->idx.n_chrom);
+        bulk2_second_kernel<false><<<b2, 256, 0, ctx->stream>>>(sv, start, end, chrom, flag, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count,
+                                                                (u32)seg_cap, (u32)n_warps, (u32)parts, ctx->d_slow_list, (u32)ctx->idx.n_chrom);
     ctx->launches++;
     TEC_CUDA(cudaGetLastError());
     // exact search on the units of EDGE cells / large ensg sets (has_stab = 0: no layout-1 table lookups)
@@ -573,6 +575,8 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_algo") { if (value < -1 || value > 1) TEC_FAIL(TEC_ERR_ARG, "sc_algo: -1, 0 or 1"); ctx->opt_sc_algo = (int)value; }
     else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
     else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }
+    else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }
+    else if (k == "bulk_mode") { if (value < 0 || value > 3) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch"); ctx->opt_bulk_mode = (int)value; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else if (k == "bam_lanes") { if (value < 1 || value > 32) TEC_FAIL(TEC_ERR_ARG, "bam_lanes: 1..32"); ctx->opt_bam_lanes = (int)value; }
     else if (k == "bam_window_blocks") { if (value < 1 || value > (1 << 20)) TEC_FAIL(TEC_ERR_ARG, "bam_window_blocks: 1..1048576"); ctx->opt_bam_window_blocks = (int)value; }

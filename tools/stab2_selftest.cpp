@@ -22,7 +22,7 @@ int main(int argc, char** argv) {
     std::mt19937_64 rng(777);
     long checked = 0, fast = 0, second = 0, exact = 0, twin_sectors = 0, forced = 0;
     for (int round = 0; round < rounds; ++round) {
-        const int shift = 8 + round % 3;                       // 8..10
+        const int shift = 8 + round % 4;                       // 8..11
         const int n_chrom = 1 + round % 3;
         const int64_t len = 3000 + (int64_t)(rng() % 30000);
         const int n_slots = 2 + (int)(rng() % (round % 2 ? 6 : 40));      // few slots: many twins
