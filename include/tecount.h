@@ -120,15 +120,21 @@ int64_t tec_launch_count(const tec_ctx* ctx);
 /* release cached device scratch (the single-cell finalize keeps its temporaries for the next call) */
 int tec_trim(tec_ctx* ctx);
 
-/* tuning knobs: "bulk_algo" (-1 auto, 0 exact search kernel, 1 cell-table kernel), "stab_shift"
- * (log2 of the cell size, 8..11, or 0 = default: 10 for bulk, 11 for the single-cell pair table; used by the
- * next tec_index_upload), "ctas_per_sm", "all_hot" (counters
- * of every ensg in shared memory when they fit), "sc_algo" (-1 auto, 0 exact search in Part 3, 1 cell
- * table), "sc_pack_umi" (2-bit UMI sort keys when possible).
+/* tuning knobs: "bulk_algo" (-1 auto, 0 exact search kernel, 1 round-1 cell-table kernel -- set before
+ * tec_index_upload --, 2 two-pass kernels), "stab_shift" (log2 of the cell size, 8..11, or 0 = default: 10 for
+ * bulk, 11 for the single-cell pair table; used by the next tec_index_upload), "bulk_mode" (bit 0 table sectors
+ * evict_last in L2, bit 1 sector prefetch, bit 2 tally by the hit lanes only), "second_parts", "ctas_per_sm",
+ * "all_hot" (counters of every ensg in shared memory when they fit), "sc_algo" (-1 auto, 0 exact search in
+ * Part 3, 1 cell table), "sc_pack_umi" (2-bit UMI sort keys when possible).
  * tec_get_info: "has_stab", "stab_bytes", "has_sc_stab", "sc_stab_bytes", "n_sm", "n_features",
- * "stab_primary", "stab_overflow", "stab_entries", "last_slow_units"; -1 for unknown keys. */
+ * "stab_primary", "stab_overflow", "stab_entries", "last_slow_units", "last_deferred_units", "stab_refused";
+ * -1 for unknown keys. */
 int tec_set_option(tec_ctx* ctx, const char* key, int64_t value);
 int64_t tec_get_info(tec_ctx* ctx, const char* key);
+/* why the last tec_index_upload could not build the bulk cell table ("" when it could): with such an index
+ * (more than 65535 ensg, or an ensg that carries two feature types) bulk counting runs on the exact search kernel,
+ * about ten times slower.  The caller should log it (te_counter_b200/te_count.py does). */
+const char* tec_index_note(const tec_ctx* ctx);
 
 /* ---- index ------------------------------------------------------------------------------
  * Replaces load_genome() + the structures of genelist._optimiseData that the read loops reach

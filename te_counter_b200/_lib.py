@@ -41,6 +41,7 @@ SIGNATURES = {
     "tec_trim": (ctypes.c_int, [_vp]),
     "tec_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
     "tec_get_info": (ctypes.c_int64, [_vp, ctypes.c_char_p]),
+    "tec_index_note": (ctypes.c_char_p, [_vp]),
     "tec_index_upload": (ctypes.c_int, [_vp, ctypes.c_int32, _c_i64p, _c_i32p, _c_i32p, _c_i32p, _c_u8p,
                                         _c_u8p, ctypes.c_int32, ctypes.c_int32]),
     "tec_bulk_begin": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
@@ -97,6 +98,7 @@ class TecError(RuntimeError):
         self.status = status
 
 
+ERR_NOMEM = -4
 ERR_IO, ERR_FORMAT, ERR_UNSUPPORTED = -7, -8, -9
 ERR_BAM_NO_BARCODE_TAG, ERR_BAM_NO_UMI_TAG, ERR_BAM_UMI, ERR_BAM_END_NONE, ERR_BAM_CHROM_NAME, ERR_BAM_REF_NONE = -10, -11, -12, -13, -14, -15
 
@@ -265,6 +267,10 @@ class Engine:
 
     def get_info(self, key):
         return int(self._lib.tec_get_info(self._h, key.encode()))
+
+    def index_note(self):
+        """Why the uploaded index has no bulk cell table ('' when it has one): see tec_index_note."""
+        return (self._lib.tec_index_note(self._h) or b"").decode()
 
     # -- index
     def upload_index(self, idx):

@@ -148,7 +148,7 @@ class AlignmentFile:
                 for op in struct.unpack_from("<%dI" % n_cig, rec, o):
                     if _CIGAR_REF[op & 0xF] if (op & 0xF) < 9 else 0:
                         span += op >> 4
-                end = pos + span
+                end = pos + (span or 1)          # htslib bam_endpos: pos + 1 when the CIGAR consumes no reference base
             r.reference_end = end
             o += 4 * n_cig + (l_seq + 1) // 2 + l_seq
             r._aux = rec[o:]
@@ -183,7 +183,7 @@ class AlignmentFile:
                         if ch in "MDN=X":
                             span += num
                         num = 0
-                end = r.reference_start + span
+                end = r.reference_start + (span or 1)
             r.reference_end = end
             r._aux = None
             r._aux_text = f[11:]

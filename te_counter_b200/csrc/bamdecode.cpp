@@ -416,7 +416,7 @@ inline Rec parse_core(const uint8_t *p, uint32_t n) {
             uint32_t v = le32(cg + 4 * i), op = v & 15;
             if ((0x18Du >> op) & 1) span += v >> 4;     // M D N = X consume the reference
         }
-        c.end = int32_t(uint32_t(c.pos) + span);
+        c.end = int32_t(uint32_t(c.pos) + (span ? span : 1u));      // htslib bam_endpos: pos + 1 when the CIGAR consumes no reference base
     }
     c.aux = p + o + size_t((l_seq + 1) / 2) + size_t(l_seq);
     c.aux_end = p + n;

@@ -139,9 +139,12 @@ struct BamGpuBackend {
         p = nullptr;
     }
     static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    bool nomem = false;                  // the last failure was an allocation failure (-> TEC_ERR_NOMEM)
     bool ok(cudaError_t e, const char* what) {
         if (e == cudaSuccess) return true;
         ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+        nomem = e == cudaErrorMemoryAllocation;
+        if (nomem) cudaGetLastError();   // not sticky: clear it, the caller may go on with the host decoder
         return false;
     }
 #define BAM_CK(call) do { if (!ok((call), #call)) return 1; } while (0)

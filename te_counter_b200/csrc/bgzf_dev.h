@@ -502,7 +502,7 @@ BGZF_HD Rec parse_core(const uint8_t* p, uint32_t n) {      // p behind block_si
             const uint32_t v = ld32(cg + 4 * i);
             if ((0x18Du >> (v & 15)) & 1) span += v >> 4;       // M D N = X
         }
-        c.end = (int32_t)((uint32_t)c.pos + span);
+        c.end = (int32_t)((uint32_t)c.pos + (span ? span : 1u));   // htslib bam_endpos: pos + 1 when the CIGAR consumes no reference base
     }
     c.aux = p + o + (uint64_t)((l_seq + 1) / 2) + (uint64_t)l_seq;
     c.aux_end = p + n;

@@ -106,9 +106,16 @@ __device__ __forceinline__ void b2_unpack(const B2Raw<PAIRED>& r, int j, u32& fl
 
 // +1 for an entry when its hit bit is set (ALLHOT: every counter in shared memory; the lanes that did not
 // hit add to a scratch word of their own behind the counters, so there is no branch)
-template <bool ALLHOT>
+template <bool ALLHOT, bool HITONLY>
 __device__ __forceinline__ void b2_bump(bool hit, u32 slot, u32 hot_addr, u32 scratch_addr, u32 n_hot, u64* __restrict__ counts, u32 one) {
-    if (ALLHOT) {
+    if (HITONLY) {
+        // only the lanes that hit take part: a branch per entry, but fewer shared-memory wavefronts (the scratch
+        // word of a lane shares its bank with the counters that map there)
+        if (hit) {
+            if (ALLHOT || slot < n_hot) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hot_addr + slot * 4u), "r"(one) : "memory");
+            else atomicAdd(counts + slot, 1ULL);
+        }
+    } else if (ALLHOT) {
         const u32 addr = hit ? (hot_addr + slot * 4u) : scratch_addr;
         asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(one) : "memory");
     } else {
@@ -134,6 +141,7 @@ struct B2Const {
 #define B2_DEF_GATHER 0x80000000u
 #define B2_MODE_KEEP 1u           // table sectors: L2 evict_last (the records stream through with evict_first)
 #define B2_MODE_PREFETCH 2u       // request the next tile's sectors into L2 one turn ahead
+#define B2_MODE_HITONLY 4u        // tally: only the lanes that hit issue the shared-memory reduction
 
 __device__ __forceinline__ Sector ld_sector_pol(const u32* sectors, u32 idx, u64 pol) {
     Sector r;
@@ -200,7 +208,7 @@ __device__ __forceinline__ void b2_prefetch(const B2Stage& st, const Stab2View& 
 }
 
 // Phase B: the sector test, the tally and the deferred list.
-template <bool ALLHOT>
+template <bool ALLHOT, bool HITONLY>
 __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const u32 u0, const Stab2View& sv, const B2Const& k,
                                            B2Thread& t, u64* __restrict__ counts, u64* __restrict__ stats) {
     Sector s[B2_UPT];
@@ -243,11 +251,11 @@ __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const u32 u0, cons
         } else {
             t.n_assigned += (a0 | a1 | a2) != 0;                                           // :128, :149
         }
-        b2_bump<ALLHOT>(a0 & 0x8000u, b2_lo16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
-        b2_bump<ALLHOT>(a0 & 0x80000000u, b2_hi16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
-        b2_bump<ALLHOT>(a1 & 0x8000u, b2_lo16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
-        b2_bump<ALLHOT>(a1 & 0x80000000u, b2_hi16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
-        b2_bump<ALLHOT>(a2 != 0, b2_hi16(s[j].w[5]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        b2_bump<ALLHOT, HITONLY>(a0 & 0x8000u, b2_lo16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        b2_bump<ALLHOT, HITONLY>(a0 & 0x80000000u, b2_hi16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        b2_bump<ALLHOT, HITONLY>(a1 & 0x8000u, b2_lo16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        b2_bump<ALLHOT, HITONLY>(a1 & 0x80000000u, b2_hi16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        b2_bump<ALLHOT, HITONLY>(a2 != 0, b2_hi16(s[j].w[5]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
         // ---- everything else goes to the second pass: the warp's own segment of the list, no atomics
         // {unit, sector | B2_DEF_GATHER, points}: a unit that one sector covers is walked from there; the others
         // (points far apart, outside the cells, name mismatch) are looked up again from their records
@@ -257,7 +265,7 @@ __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const u32 u0, cons
     }
 }
 
-template <bool PAIRED, int NT, bool ALLHOT>
+template <bool PAIRED, int NT, bool ALLHOT, bool HITONLY>
 __global__ void __launch_bounds__(NT, 2048 / NT / 2)
 bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
@@ -320,7 +328,7 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
             if (pf) b2_prefetch(sb, sv, k);
             if (nx + stride < n_full) b2_load<PAIRED, true>(raw, (nx + stride) * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
         }
-        b2_phase_b<ALLHOT>(sa, tile * 64 + 2 * lane, sv, k, t, counts, stats);
+        b2_phase_b<ALLHOT, HITONLY>(sa, tile * 64 + 2 * lane, sv, k, t, counts, stats);
         tile = nx;
         if (tile >= n_full) break;
         nx = tile + stride;
@@ -329,7 +337,7 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
             if (pf) b2_prefetch(sa, sv, k);
             if (nx + stride < n_full) b2_load<PAIRED, true>(raw, (nx + stride) * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
         }
-        b2_phase_b<ALLHOT>(sb, tile * 64 + 2 * lane, sv, k, t, counts, stats);
+        b2_phase_b<ALLHOT, HITONLY>(sb, tile * 64 + 2 * lane, sv, k, t, counts, stats);
         tile = nx;
     }
     // the last, partial tile belongs to the warp whose turn it would be
@@ -338,7 +346,7 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
         raw = B2Raw<PAIRED>();
         b2_load<PAIRED, false>(raw, u0, n_units, start, end, chrom, mapq, flag, pol);
         b2_phase_a<PAIRED, false>(raw, u0, sv, k, t, sa);
-        b2_phase_b<ALLHOT>(sa, u0, sv, k, t, counts, stats);
+        b2_phase_b<ALLHOT, HITONLY>(sa, u0, sv, k, t, counts, stats);
     }
     if (lane == 0) defer_count[gw] = (u32)(t.wp - my_list);
     u64 v[4] = {t.n_assigned, t.n_lowq, t.n_badchrom, t.n_qcfail};

@@ -57,7 +57,8 @@ __device__ __forceinline__ u64 warp_sum(u64 v) {
         cudaError_t e_ = (call);                                                         \
         if (e_ != cudaSuccess) {                                                         \
             ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
-            return (e_ == cudaErrorMemoryAllocation) ? TEC_ERR_NOMEM : TEC_ERR_CUDA;     \
+            if (e_ == cudaErrorMemoryAllocation) { cudaGetLastError(); return TEC_ERR_NOMEM; }   /* not sticky: clear it */ \
+            return TEC_ERR_CUDA;                                                         \
         }                                                                                \
     } while (0)
 

@@ -23,6 +23,15 @@ extern "C" const char* tec_strerror(int s) {
         case TEC_ERR_NOMEM: return "out of memory";
         case TEC_ERR_LIMIT: return "input exceeds a documented limit";
         case TEC_ERR_UNIMPLEMENTED: return "not implemented";
+        case TEC_ERR_IO: return "file cannot be opened or read";
+        case TEC_ERR_FORMAT: return "corrupt or truncated BAM / BGZF data";
+        case TEC_ERR_UNSUPPORTED: return "file the device decoder refuses (decode it on the host)";
+        case TEC_ERR_BAM_NO_BARCODE_TAG: return "record without CB / CR tag";
+        case TEC_ERR_BAM_NO_UMI_TAG: return "record without UB / UR tag";
+        case TEC_ERR_BAM_UMI: return "UMI that cannot be coded (longer than 21 characters or not ACGTN)";
+        case TEC_ERR_BAM_END_NONE: return "mapped record without reference_end";
+        case TEC_ERR_BAM_CHROM_NAME: return "reference name the chromosome key rule cannot take";
+        case TEC_ERR_BAM_REF_NONE: return "record without a reference sequence";
         default: return "unknown status";
     }
 }
@@ -372,7 +381,7 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
     TEC_CUDA(cudaMemsetAsync(ctx->d_slow_list, 0, 4, ctx->stream));
 #define TEC_LAUNCH_FAST2(P, NT, AH)                                                                                        \
     do {                                                                                                                   \
-        auto kfn = bulk2_fast_kernel<P, NT, AH>;                                                                           \
+        auto kfn = (ctx->opt_bulk_mode & B2_MODE_HITONLY) ? bulk2_fast_kernel<P, NT, AH, true> : bulk2_fast_kernel<P, NT, AH, false>;                                                                           \
         TEC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                        \
         kfn<<<blocks, NT, dyn, ctx->stream>>>(sv, ctx->idx.n_chrom, (u32)n_units, ctx->qual, start, end, chrom, mapq, flag, \
                                               counts, stats, (uint4*)ctx->d_defer_list, ctx->d_defer_count, (u32)seg_cap, n_hot, \
@@ -576,7 +585,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
     else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }
     else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }
-    else if (k == "bulk_mode") { if (value < 0 || value > 3) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch"); ctx->opt_bulk_mode = (int)value; }
+    else if (k == "bulk_mode") { if (value < 0 || value > 7) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally by the hit lanes only"); ctx->opt_bulk_mode = (int)value; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else if (k == "bam_lanes") { if (value < 1 || value > 32) TEC_FAIL(TEC_ERR_ARG, "bam_lanes: 1..32"); ctx->opt_bam_lanes = (int)value; }
     else if (k == "bam_window_blocks") { if (value < 1 || value > (1 << 20)) TEC_FAIL(TEC_ERR_ARG, "bam_window_blocks: 1..1048576"); ctx->opt_bam_window_blocks = (int)value; }
@@ -584,12 +593,15 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     return TEC_OK;
 }
 
+extern "C" const char* tec_index_note(const tec_ctx* ctx) { return ctx ? ctx->idx.stab_why_not.c_str() : ""; }
+
 extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
     if (!ctx || !key) return -1;
     const std::string k(key);
     if (k == "has_stab") return (ctx->idx.has_stab || ctx->idx.has_stab2) ? 1 : 0;
     if (k == "stab_bytes") return (int64_t)(ctx->idx.has_stab2 ? ctx->idx.stab2_bytes : ctx->idx.stab_bytes);
     if (k == "has_stab2") return ctx->idx.has_stab2 ? 1 : 0;
+    if (k == "stab_refused") return ctx->idx.stab_why_not.empty() ? 0 : 1;   // text: tec_index_note()
     if (k == "stab2_sector_bytes") return (ctx->idx.s2_primary + ctx->idx.s2_overflow) * 32;
     if (k == "stab2_edge_cells") return ctx->idx.s2_edge_cells;
     if (k == "stab2_twin_sectors") return ctx->idx.s2_twin_sectors;
@@ -628,7 +640,7 @@ int BamGpuBackend::deliver(int64_t n, int mode) {
     return rc ? 1 : 0;
 }
 
-static int bam_status(tec_ctx* ctx, const bamorch::Reader& r, int rc) {
+static int bam_status(tec_ctx* ctx, const bamorch::Reader& r, int rc, const BamGpuBackend* be = nullptr) {
     if (rc == bamorch::OK) return TEC_OK;
     if (rc != bamorch::E_BACKEND) ctx->err = r.err;         // the backend left the CUDA text in ctx->err
     switch (rc) {
@@ -637,9 +649,13 @@ static int bam_status(tec_ctx* ctx, const bamorch::Reader& r, int rc) {
     case bamorch::E_NOT_BGZF: return TEC_ERR_UNSUPPORTED;
     case bamorch::E_UNSUPPORTED: return TEC_ERR_UNSUPPORTED;
     case bamorch::E_ARG: return TEC_ERR_ARG;
-    case bamorch::E_BACKEND: return TEC_ERR_CUDA;
+    case bamorch::E_BACKEND: return (be && be->nomem) ? TEC_ERR_NOMEM : TEC_ERR_CUDA;
     }
-    if (rc <= bamorch::E_RECORD) return -(bamorch::E_RECORD - rc);      // TEC_ERR_BAM_*: -10 ... -15 (and -2 for a malformed record)
+    if (rc <= bamorch::E_RECORD) {
+        const int rec = bamorch::E_RECORD - rc;                         // bgzfdev::E_*
+        if (rec == bgzfdev::E_FORMAT) return TEC_ERR_FORMAT;            // a malformed record is a format error, not a bad argument
+        return -rec;                                                    // TEC_ERR_BAM_*: -10 ... -15
+    }
     return TEC_ERR_FORMAT;
 }
 
@@ -691,7 +707,7 @@ extern "C" int tec_bam_count(tec_bam* b, int mode, int qual, int64_t* n_records)
     int64_t n = 0;
     const int rc = bamorch::decode_all(b->reader, b->be, mode, qual, ctx->opt_bam_window_blocks, &n);
     if (n_records) *n_records = n;
-    return bam_status(ctx, b->reader, rc);
+    return bam_status(ctx, b->reader, rc, &b->be);
 }
 
 extern "C" int64_t tec_bam_info(const tec_bam* b, int what) {

@@ -62,12 +62,16 @@ class ChromMap:
         return key, cid
 
     def bulk_id(self, reference_name):
+        """Bulk mode only asks `chrom in buckets` (te_count.py:100 / :216): a name that is not an index
+        chromosome needs no id of its own (a header may list far more sequences than there are u16 ids)."""
         cid = self._name_bulk.get(reference_name)
         if cid is None:
             if reference_name is None:
                 cid = CHROM_INVALID
             else:
-                _, cid = self._key(reference_name)
+                cid = self._key_id.get(reference_name.replace("chr", ""), CHROM_INVALID)
+                if cid >= self.n_index:
+                    cid = CHROM_INVALID
             self._name_bulk[reference_name] = cid
         return cid
 

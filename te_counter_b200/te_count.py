@@ -128,6 +128,11 @@ class measureTE:
         if not self._index_on_device:
             self._engine_obj.upload_index(self.genome)
             self._index_on_device = True
+            note = self._engine_obj.index_note()
+            if note:                                         # no silent slow path (exact search kernel, ~10x slower in bulk)
+                import logging
+                logging.getLogger('te_count').warning(
+                    'bulk cell table not built (%s): bulk counting uses the exact search kernel, about ten times slower', note)
         return self._engine_obj
 
     def _qual(self):
@@ -174,8 +179,9 @@ class measureTE:
             except (_lib.BamUnsupported, OSError):
                 more = True                                   # start over with a host reader
             except _lib.TecError as e:
-                if 'out of memory' not in str(e):             # no room for the decode window next to the other
+                if e.status != _lib.ERR_NOMEM:                # no room for the decode window next to the other
                     raise                                     # buffers of this GPU: decode on the host instead
+                eng.trim()                                    # the decoder's buffers went back to the block cache
                 more = True
             while done >= next_log:
                 log.info('Processed {:,} {}'.format(next_log, label))
@@ -274,8 +280,9 @@ class measureTE:
             except (_lib.BamUnsupported, OSError):
                 more = True
             except _lib.TecError as e:
-                if 'out of memory' not in str(e):
+                if e.status != _lib.ERR_NOMEM:
                     raise
+                eng.trim()
                 more = True
             while done >= next_log:
                 log.info('  Processed {:,} SE valid reads'.format(next_log))

@@ -15,6 +15,8 @@ def _bgzf_block(data):
 
 
 def _cigar_for(rec):
+    if rec.get("cigar") is not None:                     # explicit list of (length, op) pairs
+        return list(rec["cigar"])
     span = rec["end"] - rec["start"]
     if rec.get("flag", 0) & 0x4 or span <= 0:
         return []

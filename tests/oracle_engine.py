@@ -85,3 +85,9 @@ class OracleEngine:
         _, hits, _ = self._out
         order = sorted(hits, key=lambda t: (-t[1], t[0]))[:maxcells]
         return np.array([c for c, _ in order], np.uint32)
+
+    def index_note(self):
+        return ""
+
+    def trim(self):
+        pass

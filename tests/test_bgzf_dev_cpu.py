@@ -200,7 +200,7 @@ def test_committed_bam_fixtures(lib, mode, window_blocks):
     a.n = b.n = 600
     a.chrom, b.chrom = want["%s_chrom" % mode], got["chrom"]
     n_index = len(idx.chrom_keys)
-    assert np.array_equal(_canon_chrom([(a, False)], n_index)[0], _canon_chrom([(b, False)], n_index)[0])
+    assert np.array_equal(_canon_chrom([(a, False)], n_index, mode != "sc")[0], _canon_chrom([(b, False)], n_index, mode != "sc")[0])
     for k in ("start", "end", "mapq", "flag") + (("cell", "umi") if mode == "sc" else ()):
         assert np.array_equal(want["%s_%s" % (mode, k)], got[k]), k
 

@@ -61,7 +61,7 @@ def _mte(monkeypatch, case, exc, push_first=False):
 
 @pytest.mark.parametrize("exc,push_first", [(_lib.BamUnsupported("x"), False), (_lib.BamUnsupported("x"), True),
                                             (OSError("cannot open"), False),
-                                            (_lib.TecError(-1, "cudaMalloc: out of memory"), True)])
+                                            (_lib.TecError(_lib.ERR_NOMEM, "cudaMalloc: out of memory"), True)])
 def test_bulk_starts_over_on_the_host(monkeypatch, tmp_path, exc, push_first):
     case = H.load_case("bulk_pe_rand_a")
     path = str(tmp_path / "x.bam")
@@ -89,10 +89,12 @@ def test_other_device_errors_propagate(monkeypatch, tmp_path):
     case = H.load_case("bulk_pe_rand_a")
     path = str(tmp_path / "x.bam")
     write_bam(path, [dict(r, name=r.get("name", "r%d" % i)) for i, r in enumerate(case["records"])])
-    mte = _mte(monkeypatch, case, _lib.TecError(-1, "an illegal memory access was encountered"))
-    mte.load_genome()
-    with pytest.raises(_lib.TecError):                  # "memory" alone is not "out of memory"
-        mte.parse_bampe(path, strand=False, log=CaptureLog())
+    # only the status TEC_ERR_NOMEM means "no room": other CUDA errors propagate, whatever their text says
+    for exc in (_lib.TecError(-1, "an illegal memory access was encountered"), _lib.TecError(-1, "x: out of memory")):
+        mte = _mte(monkeypatch, case, exc)
+        mte.load_genome()
+        with pytest.raises(_lib.TecError):
+            mte.parse_bampe(path, strand=False, log=CaptureLog())
     mte = _mte(monkeypatch, case, AssertionError("CB or CR tag not found!"))
     mte.load_genome()
     with pytest.raises(AssertionError):

@@ -67,15 +67,20 @@ def _native_batches(path, mode, cm, wl, qual, cap, threads):
     return out
 
 
-def _canon_chrom(batches, n_index):
-    """Chromosomes outside the index get fresh ids >= n_index: in order of first use in the Python
-    packing, in header order in the library.  Only their identity matters (reads.ChromMap), so
-    compare after relabelling by first appearance."""
+def _canon_chrom(batches, n_index, bulk=False):
+    """Chromosomes outside the index get fresh ids >= n_index in single-cell mode: in order of first use in
+    the Python packing, in header order in the library.  Only their identity matters (reads.ChromMap), so
+    compare after relabelling by first appearance.  bulk: "not in the index" is all that matters
+    (te_count.py:100 / :216), every such id is the same."""
     seen = {}
     out = []
     for b, _ in batches:
         c = b.chrom[:b.n].astype(np.int64)
         lab = c.copy()
+        if bulk:
+            lab[c >= n_index] = reads.CHROM_INVALID
+            out.append(lab)
+            continue
         for i in np.flatnonzero((c >= n_index) & (c < reads.MAX_CHROM_IDS)).tolist():
             lab[i] = seen.setdefault(int(c[i]), 1000000 + len(seen))
         out.append(lab)
