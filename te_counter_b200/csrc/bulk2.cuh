@@ -8,7 +8,11 @@
 //                        two points are covered by ONE primary sector (the cell of the smaller point also
 //                        covers `ext` bp of the next cell) and lie below the sector's threshold is filtered,
 //                        tested against the five entries (16-bit lanes, both points at once), de-duplicated
-//                        (twin flags) and tallied into shared-memory counters right there.  Every other unit
+//                        (twin flags) and tallied into shared-memory counters: the ensg of the hit entries go
+//                        through a per-warp queue in shared memory and are added 32 at a time (a shared-memory
+//                        reduction costs ~18 SM cycles per warp instruction whatever the number of active
+//                        lanes, tools/microbench2.cu, so ten sparse ones per tile become about three full ones).
+//                        Every other unit
 //                        that passed the filter is appended to the warp's own segment of the deferred list
 //                        (no atomics: the list is partitioned by warp).
 //   bulk2_second_kernel  the deferred units (about 6 % of a paired-end workload): one or two sector chains,
@@ -132,16 +136,21 @@ __device__ __forceinline__ u32 b2_hi16(u32 w) { return __byte_perm(w, 0u, 0x4432
 struct B2Thread {
     u32 n_assigned, n_lowq, n_badchrom, n_qcfail;
     uint4* wp;                    // next free entry of the warp's segment of the deferred list (warp-uniform)
+    u32 q_head, q_tail;           // hit queue of the warp (warp-uniform): entries [q_head, q_tail) are pending
 };
 struct B2Const {
     u32 reject2, lim, lt_mask, hot_addr, scratch_addr, one, n_hot, n_units, mode;
     int shift, cmask, qual, n_chrom;
     u64 pol_table;                // L2 policy of the table loads (evict_last when mode & B2_MODE_KEEP)
+    u32 q_addr;                   // shared-memory address of the warp's hit queue (B2_QCAP 16-bit entries)
 };
+#define B2_QCAP 256u              // per warp; a unit adds at most 5 x 32 entries between two drains
 #define B2_DEF_GATHER 0x80000000u
+#define B2_DEF_NAME 0x40000000u
 #define B2_MODE_KEEP 1u           // table sectors: L2 evict_last (the records stream through with evict_first)
 #define B2_MODE_PREFETCH 2u       // request the next tile's sectors into L2 one turn ahead
-#define B2_MODE_HITONLY 4u        // tally: only the lanes that hit issue the shared-memory reduction
+#define B2_MODE_QUEUE 4u          // tally through the per-warp hit queue instead of one reduction per entry
+#define B2_MODE_DEEP 8u           // 512-thread CTAs with 128 registers per thread: three tiles in flight per warp
 
 __device__ __forceinline__ Sector ld_sector_pol(const u32* sectors, u32 idx, u64 pol) {
     Sector r;
@@ -156,7 +165,7 @@ __device__ __forceinline__ Sector ld_sector_pol(const u32* sectors, u32 idx, u64
 struct B2Stage {
     u32 sec[B2_UPT];              // sector index (0 when the unit is not answered in place)
     u32 pts[B2_UPT];              // ra | rb << 16
-    u32 flags;                    // bit 2j: unit j passed the filter, bit 2j+1: one sector covers both points
+    u32 flags;                    // bit j: unit j passed the filter and one sector covers both points
 };
 
 // Phase A of a warp's turn (64 consecutive units, two per lane): filter (te_count.py:78-102 / :203-218) and
@@ -194,7 +203,15 @@ __device__ __forceinline__ void b2_phase_a(const B2Raw<PAIRED>& cur, const u32 u
         st.sec[j] = ok ? cell.x + (u32)kc : 0u;
         asm volatile("" : "+r"(st.sec[j]));                   // select the index, not the 64-bit address
         st.pts[j] = ra | (rb << 16);                          // garbage unless ok
-        st.flags |= ((u32)look << (2 * j)) | ((u32)ok << (2 * j + 1));
+        st.flags |= (u32)ok << j;
+        // units that no single sector covers (points far apart or outside the cells, name mismatch) go to the
+        // second pass with their coordinates: {unit, chromosome | B2_DEF_GATHER | name mismatch, loc1, loc2}
+        const bool far = look & !ok;
+        const u32 fm = __ballot_sync(0xFFFFFFFFu, far);
+        if (fm) {
+            if (far) t.wp[__popc(fm & k.lt_mask)] = make_uint4(u0 + j, c | B2_DEF_GATHER | (f_nm ? B2_DEF_NAME : 0u), (u32)loc1, (u32)loc2);
+            t.wp += __popc(fm);
+        }
     }
 }
 
@@ -207,22 +224,51 @@ __device__ __forceinline__ void b2_prefetch(const B2Stage& st, const Stab2View& 
     }
 }
 
+// hit queue: the lanes whose entry hit append its ensg slot (ballot + popc, no atomics)
+__device__ __forceinline__ void b2_q_push(bool hit, u32 slot, const B2Const& k, B2Thread& t) {
+    const u32 m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (hit) {
+        const u32 at = (t.q_tail + __popc(m & k.lt_mask)) & (B2_QCAP - 1u);
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(k.q_addr + at * 2u), "h"((unsigned short)slot) : "memory");
+    }
+    t.q_tail += __popc(m);
+}
+// add the pending entries to the counters, 32 at a time (all == false: only full groups)
+template <bool ALLHOT>
+__device__ __forceinline__ void b2_q_drain(const B2Const& k, B2Thread& t, u64* __restrict__ counts, int lane, bool all) {
+    __syncwarp();
+    while (t.q_tail - t.q_head >= (all ? 1u : 32u)) {
+        const bool on = (u32)lane < t.q_tail - t.q_head;
+        unsigned short sl = 0;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sl) : "r"(k.q_addr + ((t.q_head + (u32)lane) & (B2_QCAP - 1u)) * 2u) : "memory");
+        const u32 slot = sl;
+        if (on) {
+            if (ALLHOT || slot < k.n_hot) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(k.hot_addr + slot * 4u), "r"(k.one) : "memory");
+            else atomicAdd(counts + slot, 1ULL);
+        }
+        t.q_head += min(32u, t.q_tail - t.q_head);
+    }
+    __syncwarp();
+}
+
 // Phase B: the sector test, the tally and the deferred list.
-template <bool ALLHOT, bool HITONLY>
-__device__ __forceinline__ void b2_phase_b(const B2Stage& st, const u32 u0, const Stab2View& sv, const B2Const& k,
-                                           B2Thread& t, u64* __restrict__ counts, u64* __restrict__ stats) {
-    Sector s[B2_UPT];
+__device__ __forceinline__ void b2_load_sectors(Sector (&s)[B2_UPT], const B2Stage& st, const Stab2View& sv, const B2Const& k) {
 #pragma unroll
     for (int j = 0; j < B2_UPT; ++j) s[j] = ld_sector_pol(sv.sectors, st.sec[j], k.pol_table);
+}
+
+template <bool ALLHOT, bool QUEUE>
+__device__ __forceinline__ void b2_phase_b(const B2Stage& st, const Sector (&s)[B2_UPT], const u32 u0, const Stab2View& sv, const B2Const& k,
+                                           B2Thread& t, u64* __restrict__ counts, u64* __restrict__ stats) {
 #pragma unroll
     for (int j = 0; j < B2_UPT; ++j) {
-        const bool look = (st.flags >> (2 * j)) & 1u, ok = (st.flags >> (2 * j + 1)) & 1u;
+        const bool ok = (st.flags >> j) & 1u;
         const u32 ra = st.pts[j] & 0xFFFFu, rb = st.pts[j] >> 16;
         const u32 rmax = max(ra, rb);
         const u32 w2 = s[j].w[2];
         const u32 thr = (w2 >> 16) & S2_THR_MASK;
         const bool inplace = ok & (rmax < thr);
-        const bool defer = look & !inplace;
+        const bool defer = ok & !inplace;
         // ---- five interval tests, both points at once (16-bit lanes, stab_build.h)
         const PointK pa = make_point(ra), pb = make_point(rb);
         const u32 m = inplace ? 0x80008000u : 0u;
@@ -251,22 +297,30 @@ __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const u32 u0, cons
         } else {
             t.n_assigned += (a0 | a1 | a2) != 0;                                           // :128, :149
         }
-        b2_bump<ALLHOT, HITONLY>(a0 & 0x8000u, b2_lo16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
-        b2_bump<ALLHOT, HITONLY>(a0 & 0x80000000u, b2_hi16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
-        b2_bump<ALLHOT, HITONLY>(a1 & 0x8000u, b2_lo16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
-        b2_bump<ALLHOT, HITONLY>(a1 & 0x80000000u, b2_hi16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
-        b2_bump<ALLHOT, HITONLY>(a2 != 0, b2_hi16(s[j].w[5]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        if (QUEUE) {
+            b2_q_push(a0 & 0x8000u, s[j].w[6], k, t);
+            b2_q_push(a0 & 0x80000000u, s[j].w[6] >> 16, k, t);
+            b2_q_push(a1 & 0x8000u, s[j].w[7], k, t);
+            b2_q_push(a1 & 0x80000000u, s[j].w[7] >> 16, k, t);
+            b2_q_push(a2 != 0, s[j].w[5] >> 16, k, t);
+            b2_q_drain<ALLHOT>(k, t, counts, (int)(threadIdx.x & 31), false);
+        } else {
+            b2_bump<ALLHOT, false>(a0 & 0x8000u, b2_lo16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+            b2_bump<ALLHOT, false>(a0 & 0x80000000u, b2_hi16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+            b2_bump<ALLHOT, false>(a1 & 0x8000u, b2_lo16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+            b2_bump<ALLHOT, false>(a1 & 0x80000000u, b2_hi16(s[j].w[7]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+            b2_bump<ALLHOT, false>(a2 != 0, b2_hi16(s[j].w[5]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
+        }
         // ---- everything else goes to the second pass: the warp's own segment of the list, no atomics
-        // {unit, sector | B2_DEF_GATHER, points}: a unit that one sector covers is walked from there; the others
-        // (points far apart, outside the cells, name mismatch) are looked up again from their records
+        // {unit, sector, points}: the chain of that sector is walked from there (phase A wrote the other kind)
         const u32 dm = __ballot_sync(0xFFFFFFFFu, defer);
-        if (defer) t.wp[__popc(dm & k.lt_mask)] = make_uint4(u0 + j, ok ? st.sec[j] : B2_DEF_GATHER, st.pts[j], 0u);
+        if (defer) t.wp[__popc(dm & k.lt_mask)] = make_uint4(u0 + j, st.sec[j], st.pts[j], 0u);
         t.wp += __popc(dm);
     }
 }
 
-template <bool PAIRED, int NT, bool ALLHOT, bool HITONLY>
-__global__ void __launch_bounds__(NT, 2048 / NT / 2)
+template <bool PAIRED, int NT, bool ALLHOT, bool QUEUE, bool DEEP>
+__global__ void __launch_bounds__(NT, DEEP ? 1 : 2048 / NT / 2)
 bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                   const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ mapq,
@@ -275,6 +329,7 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
     constexpr int WARPS = NT / 32;
     __shared__ u64 s_stats[TEC_BULK_NSTATS];
     extern __shared__ __align__(16) u32 s_hot_dyn[];
+    // dynamic shared memory: n_hot counters, 32 scratch words, then one hit queue of B2_QCAP 16-bit entries per warp
     for (u32 i = threadIdx.x; i < n_hot + 32; i += blockDim.x) s_hot_dyn[i] = 0;
     if (threadIdx.x < TEC_BULK_NSTATS) s_stats[threadIdx.x] = 0;
     __syncthreads();
@@ -290,6 +345,7 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
     k.hot_addr = (u32)__cvta_generic_to_shared(&s_hot_dyn[0]);
     asm volatile("" : "+r"(k.hot_addr));                      // keep it in a register (not recomputed per use)
     k.scratch_addr = k.hot_addr + (n_hot + (u32)lane) * 4u;
+    k.q_addr = k.hot_addr + (n_hot + 32u) * 4u + (u32)wib * (B2_QCAP * 2u);
     // the increment as a run-time value: a literal 1 makes ptxas pick ATOMS.POPC.INC, which needs a
     // converged warp and therefore a branch around every reduction
     k.one = (u32)(n_units > 0);
@@ -306,14 +362,45 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
     B2Thread t;
     t.n_assigned = t.n_lowq = t.n_badchrom = t.n_qcfail = 0;
     t.wp = my_list;
-    // Full tiles of 64 units, warp-strided, software-pipelined over three turns: the records of tile i+2 are
-    // requested, tile i+1 is filtered and its sectors are requested into L2, tile i is tested and tallied.
+    t.q_head = t.q_tail = 0;
     const u32 n_full = n_units >> 6;
     const u32 stride = gridDim.x * WARPS;
     const bool pf = (mode & B2_MODE_PREFETCH) != 0;
     u32 tile = gw;
     B2Raw<PAIRED> raw;
+    if constexpr (DEEP) {
+        // Full tiles of 64 units, warp-strided, three tiles in flight per warp (128 registers per thread, one CTA of
+        // NT threads per SM): while tile i is tested and tallied, the sectors of tiles i+1 and i+2 and the records of
+        // tile i+3 are on their way -- the warp's own arithmetic hides its own L2 / HBM latency.
+        B2Stage st[3];
+        Sector sec[3][B2_UPT];
+        auto fill = [&](B2Stage& stg, Sector (&sc)[B2_UPT], u32 tl) {       // records of `tl` are in raw
+            b2_phase_a<PAIRED, true>(raw, tl * 64 + 2 * lane, sv, k, t, stg);
+            if (tl + stride < n_full && tl + stride >= tl)
+                b2_load<PAIRED, true>(raw, (tl + stride) * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+            b2_load_sectors(sc, stg, sv, k);
+        };
+        if (tile < n_full) {
+            b2_load<PAIRED, true>(raw, tile * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
+            fill(st[0], sec[0], tile);
+            if (tile + stride < n_full) fill(st[1], sec[1], tile + stride);
+        }
+        while (tile < n_full) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (tile < n_full) {
+                    const u32 t2 = tile + 2 * stride;
+                    if (t2 < n_full) fill(st[(r + 2) % 3], sec[(r + 2) % 3], t2);
+                    b2_phase_b<ALLHOT, QUEUE>(st[r], sec[r], tile * 64 + 2 * lane, sv, k, t, counts, stats);
+                    tile += stride;
+                }
+            }
+        }
+    } else {
+    // Full tiles of 64 units, warp-strided, software-pipelined over three turns: the records of tile i+2 are
+    // requested, tile i+1 is filtered and its sectors are requested into L2, tile i is tested and tallied.
     B2Stage sa, sb;
+    Sector sec[B2_UPT];
     if (tile < n_full) {
         b2_load<PAIRED, true>(raw, tile * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
         b2_phase_a<PAIRED, true>(raw, tile * 64 + 2 * lane, sv, k, t, sa);
@@ -328,7 +415,8 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
             if (pf) b2_prefetch(sb, sv, k);
             if (nx + stride < n_full) b2_load<PAIRED, true>(raw, (nx + stride) * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
         }
-        b2_phase_b<ALLHOT, HITONLY>(sa, tile * 64 + 2 * lane, sv, k, t, counts, stats);
+        b2_load_sectors(sec, sa, sv, k);
+        b2_phase_b<ALLHOT, QUEUE>(sa, sec, tile * 64 + 2 * lane, sv, k, t, counts, stats);
         tile = nx;
         if (tile >= n_full) break;
         nx = tile + stride;
@@ -337,17 +425,23 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
             if (pf) b2_prefetch(sa, sv, k);
             if (nx + stride < n_full) b2_load<PAIRED, true>(raw, (nx + stride) * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
         }
-        b2_phase_b<ALLHOT, HITONLY>(sb, tile * 64 + 2 * lane, sv, k, t, counts, stats);
+        b2_load_sectors(sec, sb, sv, k);
+        b2_phase_b<ALLHOT, QUEUE>(sb, sec, tile * 64 + 2 * lane, sv, k, t, counts, stats);
         tile = nx;
+    }
     }
     // the last, partial tile belongs to the warp whose turn it would be
     if ((n_units & 63u) && (n_full % stride) == gw) {
         const u32 u0 = n_full * 64 + 2 * lane;
         raw = B2Raw<PAIRED>();
+        B2Stage sl;
+        Sector secl[B2_UPT];
         b2_load<PAIRED, false>(raw, u0, n_units, start, end, chrom, mapq, flag, pol);
-        b2_phase_a<PAIRED, false>(raw, u0, sv, k, t, sa);
-        b2_phase_b<ALLHOT, HITONLY>(sa, u0, sv, k, t, counts, stats);
+        b2_phase_a<PAIRED, false>(raw, u0, sv, k, t, sl);
+        b2_load_sectors(secl, sl, sv, k);
+        b2_phase_b<ALLHOT, QUEUE>(sl, secl, u0, sv, k, t, counts, stats);
     }
+    if (QUEUE) b2_q_drain<ALLHOT>(k, t, counts, lane, true);
     if (lane == 0) defer_count[gw] = (u32)(t.wp - my_list);
     u64 v[4] = {t.n_assigned, t.n_lowq, t.n_badchrom, t.n_qcfail};
 #pragma unroll
@@ -376,23 +470,41 @@ __device__ __forceinline__ u32 b2_sector_hits(const Sector& s, const PointK a, c
     return (a0 & 0x80008000u) | ((a1 & 0x80008000u) >> 1) | ((a2 & 0x8000u) >> 2);     // HB0..HB4 of bulk.cuh
 }
 
+#define B2_QCAP2 512u             // per warp: at most B2_MAXD x 32 entries are added between two drains
+
 template <bool PAIRED>
 __global__ void __launch_bounds__(256, 6)
-bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
-                    const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ flag, u64* __restrict__ counts, u64* __restrict__ stats,
+bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ stats,
                     const uint4* __restrict__ defer_list, const u32* __restrict__ defer_count, u32 seg_cap, u32 n_seg, u32 parts,
                     u32* __restrict__ slow_list, u32 sv_n_chrom) {
     // hot ensg counters privatised per CTA (a Zipf-hot TE name would otherwise serialise in one L2 slice)
     __shared__ u32 s_hot[TEC_HOT_SLOTS];
+    __shared__ unsigned short s_q[8][B2_QCAP2];                    // per warp: ensg slots waiting to be counted
     for (int i = threadIdx.x; i < TEC_HOT_SLOTS; i += blockDim.x) s_hot[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    unsigned short* const q = s_q[threadIdx.x >> 5];
+    u32 q_head = 0, q_tail = 0;                                    // warp-uniform
     const u32 lt_mask = (1u << lane) - 1u;
     const int shift = sv.shift;
     const int cmask = (1 << shift) - 1;
     const u32 lim = (u32)(cmask + 1 + sv.ext);
     u32 n_assigned = 0;
     const u32 n_w = n_seg * parts;
+    // add pending queue entries to the counters, 32 at a time (a shared-memory reduction costs the same with 1 or 32
+    // active lanes); all: also the last, partial group
+    auto drain = [&](bool all) {
+        __syncwarp();
+        while (q_tail - q_head >= (all ? 1u : 32u)) {
+            const u32 slot = q[(q_head + (u32)lane) & (B2_QCAP2 - 1u)];
+            if ((u32)lane < q_tail - q_head) {
+                if (slot < TEC_HOT_SLOTS) atomicAdd(&s_hot[slot], 1u);
+                else atomicAdd(counts + slot, 1ULL);
+            }
+            q_head += min(32u, q_tail - q_head);
+        }
+        __syncwarp();
+    };
     for (u32 w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_w; w += gridDim.x * (blockDim.x >> 5)) {
         const u32 seg = w % n_seg, part = w / n_seg;
         const u32 cnt = __ldg(defer_count + seg);
@@ -400,7 +512,10 @@ bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32
         for (u32 i0 = part * 32; i0 < cnt; i0 += parts * 32) {
             const bool live = i0 + lane < cnt;
             bool exact = false;
-            u32 u = 0;
+            u32 u = 0, nd = 0;
+            u32 dist[B2_MAXD];
+#pragma unroll
+            for (int i = 0; i < B2_MAXD; ++i) dist[i] = 0xFFFFFFFFu;
             if (live) {
                 const uint4 rec = __ldg(list + i0 + lane);
                 u = rec.x;
@@ -410,17 +525,12 @@ bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32
                 if (!(rec.y & B2_DEF_GATHER)) {
                     prim[0] = rec.y; pts[0] = rec.z; np = 1;
                 } else {
-                    int c, loc1, loc2;
-                    bool name_crash = false;
-                    if (PAIRED) {
-                        c = chrom[2 * (size_t)u];
-                        const int2 s2 = *reinterpret_cast<const int2*>(start + 2 * (size_t)u);
-                        loc1 = s2.x; loc2 = s2.y;
-                        name_crash = (flag[2 * (size_t)u] & TEC_F_NAME_MISMATCH) != 0;
-                    } else { c = chrom[u]; loc1 = start[u]; loc2 = end[u]; }
+                    const u32 c = rec.y & 0xFFFFu;
+                    const int loc1 = (int)rec.z, loc2 = (int)rec.w;
+                    const bool name_crash = PAIRED && (rec.y & B2_DEF_NAME);
                     if (name_crash) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);            // :92-94
                     // (a unit with a name mismatch may sit on a chromosome without cells: zero cells, no probe)
-                    const uint2 cell = name_crash ? make_uint2(0u, 0u) : __ldg(sv.cells + min((u32)c, sv_n_chrom));
+                    const uint2 cell = name_crash ? make_uint2(0u, 0u) : __ldg(sv.cells + min(c, sv_n_chrom));
                     const int xa = loc1, xb = loc2 - 1;
                     const int mn = min(xa, xb), k = mn >> shift, base = mn & ~cmask;
                     const u32 rm = (u32)(max(xa, xb) - base);
@@ -433,10 +543,6 @@ bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32
                         if (xb >= 0 && (u32)(xb >> shift) < cell.y) { prim[np] = cell.x + (u32)(xb >> shift); pts[np] = S2_R_NONE | ((u32)(xb & cmask) << 16); ++np; }
                     }
                 }
-                u32 dist[B2_MAXD];
-#pragma unroll
-                for (int i = 0; i < B2_MAXD; ++i) dist[i] = 0xFFFFFFFFu;
-                u32 nd = 0;
                 for (int p = 0; p < np; ++p) {
                     const u32 ra = pts[p] & 0xFFFFu, rb = pts[p] >> 16;
                     const PointK pa = make_point(ra), pb = make_point(rb);
@@ -469,9 +575,9 @@ bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32
                     }
                 }
                 if (nd > B2_MAXD) exact = true;
-                if (!exact && nd) {                                                    // :128 result not empty
+                if (exact) nd = 0;
+                if (nd) {                                                              // :128 result not empty
                     n_assigned++;                                                      // :149
-                    bool count_it = true;
                     if (!sv.all_counted) {
                         u32 typemask = 0;
 #pragma unroll
@@ -479,23 +585,25 @@ bulk2_second_kernel(Stab2View sv, const int32_t* __restrict__ start, const int32
                         const u32 counted = (1u << TEC_T_GENE) | (1u << TEC_T_TE) | (1u << TEC_T_SNRNA);
                         if (!(typemask & counted)) {
                             if (typemask & (1u << TEC_T_ENHANCER)) atomicAdd(stats + TEC_BS_CRASH_ENHANCER, 1ULL);   // :145-147
-                            count_it = false;
-                        }
-                    }
-                    if (count_it) {
-#pragma unroll
-                        for (int j = 0; j < B2_MAXD; ++j) {
-                            if ((u32)j < nd) {
-                                if (dist[j] < TEC_HOT_SLOTS) atomicAdd(&s_hot[dist[j]], 1u);
-                                else atomicAdd(counts + dist[j], 1ULL);
-                            }
+                            nd = 0;
                         }
                     }
                 }
             }
+            // the warp is converged here: the ensg to count go through the queue
+#pragma unroll
+            for (int j = 0; j < B2_MAXD; ++j) {
+                const bool on = (u32)j < nd;
+                const u32 m = __ballot_sync(0xFFFFFFFFu, on);
+                if (!m) break;
+                if (on) q[(q_tail + __popc(m & lt_mask)) & (B2_QCAP2 - 1u)] = (unsigned short)dist[j];
+                q_tail += __popc(m);
+            }
+            drain(false);
             flag_slow_warp(slow_list, exact, u, lt_mask);
         }
     }
+    drain(true);
     const u64 a_sum = warp_sum((u64)n_assigned);
     if (lane == 0 && a_sum) atomicAdd(stats + TEC_BS_ASSIGNED, a_sum);
     __syncthreads();

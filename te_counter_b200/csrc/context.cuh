@@ -163,7 +163,8 @@ struct tec_ctx {
     // options (tec_set_option)
     int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 cell-table kernel with in-kernel rings (round 1), 2 two-pass kernels (bulk2.cuh)
     int opt_stab_shift = 0;               // log2 of the cell size; 0 = TEC_BULK_STAB_SHIFT / TEC_SC_STAB_SHIFT
-    int opt_bulk_mode = 1;                // fast bulk kernel: bit 0 table sectors evict_last in L2, bit 1 prefetch the next tile's sectors
+    int opt_bulk_mode = 13;               // fast bulk kernel: bit 0 table sectors evict_last in L2, bit 1 prefetch the next tile's sectors,
+                                          // bit 2 tally through the per-warp hit queue, bit 3 512-thread CTAs with three tiles in flight per warp
     int opt_second_parts = 2;             // warps of the second bulk pass per segment of the deferred list
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
     int opt_sc_pack_umi = 1;              // single cell: 2-bit UMI sort keys when every UMI is fixed-length ACGT

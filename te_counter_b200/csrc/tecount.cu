@@ -351,12 +351,15 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
     u64* stats = ctx->d_counts + ctx->idx.n_ensg;
     const int64_t n_tiles = (n_units + 63) / 64;
     const size_t all_bytes = (size_t)ctx->idx.n_ensg * 4;
-    const bool allhot = ctx->opt_all_hot != 0 && all_bytes + 2048 <= (size_t)ctx->smem_optin;
-    const int nt = allhot ? 1024 : 512;
+    const bool allhot = ctx->opt_all_hot != 0 && all_bytes + 2048 + 32 * B2_QCAP * 2 <= (size_t)ctx->smem_optin;
+    // every counter in shared memory: one CTA per SM, of 1024 threads (64 registers) or, B2_MODE_DEEP, of 512 threads
+    // with 128 registers and three tiles in flight per warp
+    const bool deep = allhot && (ctx->opt_bulk_mode & B2_MODE_DEEP);
+    const int nt = allhot && !deep ? 1024 : 512;
     const u32 n_hot = allhot ? (u32)ctx->idx.n_ensg : (u32)std::min<int64_t>(TEC_HOT_SLOTS, ctx->idx.n_ensg);
-    const size_t dyn = (size_t)n_hot * 4 + 128;            // + one scratch word per lane (b2_bump)
-    const int per_sm = allhot ? 1 : ctx->opt_ctas_per_sm;
     const int wpb = nt / 32;
+    const size_t dyn = (size_t)n_hot * 4 + 128 + (size_t)wpb * B2_QCAP * 2;   // + one scratch word per lane, + the warps' hit queues
+    const int per_sm = allhot ? 1 : ctx->opt_ctas_per_sm;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_tiles + wpb - 1) / wpb, (int64_t)ctx->n_sm * per_sm));
     const int64_t n_warps = (int64_t)blocks * wpb;
     const int64_t seg_cap = ((n_tiles + n_warps - 1) / n_warps) * 64;
@@ -379,26 +382,33 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
         ctx->slow_cap = cap;
     }
     TEC_CUDA(cudaMemsetAsync(ctx->d_slow_list, 0, 4, ctx->stream));
-#define TEC_LAUNCH_FAST2(P, NT, AH)                                                                                        \
+#define TEC_LAUNCH_FAST2(P, NT, AH, DP)                                                                                    \
     do {                                                                                                                   \
-        auto kfn = (ctx->opt_bulk_mode & B2_MODE_HITONLY) ? bulk2_fast_kernel<P, NT, AH, true> : bulk2_fast_kernel<P, NT, AH, false>;                                                                           \
+        auto kfn = (ctx->opt_bulk_mode & B2_MODE_QUEUE) ? bulk2_fast_kernel<P, NT, AH, true, DP> : bulk2_fast_kernel<P, NT, AH, false, DP>; \
         TEC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                        \
         kfn<<<blocks, NT, dyn, ctx->stream>>>(sv, ctx->idx.n_chrom, (u32)n_units, ctx->qual, start, end, chrom, mapq, flag, \
                                               counts, stats, (uint4*)ctx->d_defer_list, ctx->d_defer_count, (u32)seg_cap, n_hot, \
                                               (u32)ctx->opt_bulk_mode);                                                    \
     } while (0)
-    if (ctx->paired) { if (allhot) TEC_LAUNCH_FAST2(true, 1024, true); else TEC_LAUNCH_FAST2(true, 512, false); }
-    else { if (allhot) TEC_LAUNCH_FAST2(false, 1024, true); else TEC_LAUNCH_FAST2(false, 512, false); }
+    if (ctx->paired) {
+        if (deep) TEC_LAUNCH_FAST2(true, 512, true, true);
+        else if (allhot) TEC_LAUNCH_FAST2(true, 1024, true, false);
+        else TEC_LAUNCH_FAST2(true, 512, false, false);
+    } else {
+        if (deep) TEC_LAUNCH_FAST2(false, 512, true, true);
+        else if (allhot) TEC_LAUNCH_FAST2(false, 1024, true, false);
+        else TEC_LAUNCH_FAST2(false, 512, false, false);
+    }
 #undef TEC_LAUNCH_FAST2
     ctx->launches++;
     TEC_CUDA(cudaGetLastError());
     const int parts = std::max(1, ctx->opt_second_parts);
     const int b2 = (int)std::min<int64_t>((n_warps * parts + 7) / 8, (int64_t)ctx->n_sm * 6);
     if (ctx->paired)
-        bulk2_second_kernel<true><<<b2, 256, 0, ctx->stream>>>(sv, start, end, chrom, flag, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count,
+        bulk2_second_kernel<true><<<b2, 256, 0, ctx->stream>>>(sv, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count,
                                                                (u32)seg_cap, (u32)n_warps, (u32)parts, ctx->d_slow_list, (u32)ctx->idx.n_chrom);
     else
-        bulk2_second_kernel<false><<<b2, 256, 0, ctx->stream>>>(sv, start, end, chrom, flag, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count,
+        bulk2_second_kernel<false><<<b2, 256, 0, ctx->stream>>>(sv, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count,
                                                                 (u32)seg_cap, (u32)n_warps, (u32)parts, ctx->d_slow_list, (u32)ctx->idx.n_chrom);
     ctx->launches++;
     TEC_CUDA(cudaGetLastError());
@@ -585,7 +595,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
     else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }
     else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }
-    else if (k == "bulk_mode") { if (value < 0 || value > 7) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally by the hit lanes only"); ctx->opt_bulk_mode = (int)value; }
+    else if (k == "bulk_mode") { if (value < 0 || value > 15) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline"); ctx->opt_bulk_mode = (int)value; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else if (k == "bam_lanes") { if (value < 1 || value > 32) TEC_FAIL(TEC_ERR_ARG, "bam_lanes: 1..32"); ctx->opt_bam_lanes = (int)value; }
     else if (k == "bam_window_blocks") { if (value < 1 || value > (1 << 20)) TEC_FAIL(TEC_ERR_ARG, "bam_window_blocks: 1..1048576"); ctx->opt_bam_window_blocks = (int)value; }

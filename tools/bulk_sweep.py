@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--records", type=int, default=500_000_000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--configs", default="bulk_algo=2")
+    ap.add_argument("--shard", default="0,1", help="rank,world: reads restricted to that slice of the genome (how much of the table is touched)")
     a = ap.parse_args()
     import torch
     from te_counter_b200 import _lib, synth
@@ -26,7 +27,8 @@ def main():
     torch.cuda.set_device(0)
     paired = a.workload == "bulk_pe"
     idx = synth.synth_index()
-    reads = synth.synth_bulk_reads(synth.SEED, idx, a.records, paired=paired, device=dev, as_numpy=False)
+    reads = synth.synth_bulk_reads(synth.SEED, idx, a.records, paired=paired, device=dev, as_numpy=False,
+                                   shard=tuple(int(x) for x in a.shard.split(",")))
     ptrs = [reads[k].data_ptr() for k in ("start", "end", "chrom", "mapq", "flag")]
     torch.cuda.synchronize()
     ref = None
@@ -55,7 +57,7 @@ def main():
         chk = int((counts.astype(np.uint64) * (np.arange(len(counts), dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1))).sum() & np.uint64(0xFFFFFFFFFFFF))
         if ref is None:
             ref = (chk, st[:5].tolist())
-        out = {"config": cfg, "workload": a.workload, "records": a.records, "ms_mean": float(np.mean(ms)), "ms_min": float(np.min(ms)),
+        out = {"config": cfg, "shard": a.shard, "workload": a.workload, "records": a.records, "ms_mean": float(np.mean(ms)), "ms_min": float(np.min(ms)),
                "records_per_s": a.records / (float(np.mean(ms)) / 1e3), "deferred": eng.get_info("last_deferred_units"),
                "slow": eng.get_info("last_slow_units"), "table_bytes": eng.get_info("stab_bytes"), "checksum": chk,
                "same_as_first": (chk, st[:5].tolist()) == ref, "stats": [int(x) for x in st[:5]]}
