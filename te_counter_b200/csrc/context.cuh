@@ -167,6 +167,7 @@ struct tec_ctx {
                                           // bit 2 tally through the per-warp hit queue, bit 3 512-thread CTAs with three tiles in flight per warp
     int opt_second_parts = 2;             // warps of the second bulk pass per segment of the deferred list
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
+    int opt_sc_sort = 1;                  // single cell: packed 64-bit keys + the 11-bit radix sort of csrc/radix.cuh (0: library sort, two stages)
     int opt_sc_pack_umi = 1;              // single cell: 2-bit UMI sort keys when every UMI is fixed-length ACGT
     int opt_sc_algo = -1;                 // -1 auto, 0 exact search only, 1 cell table
     int opt_bam_lanes = 1;                // BGZF blocks decoded per warp by the inflate kernel (1..32): the streams of a warp

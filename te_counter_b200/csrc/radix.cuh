@@ -11,8 +11,8 @@
 //   rdx_scan_kernel     exclusive prefix sum over (digit major, CTA minor): where each CTA's run of each digit starts
 //   rdx_scatter_kernel  the same CTA walks its chunk tile by tile.  A tile (6144 pairs, 24 per thread, 72 KB of shared
 //                       memory, two CTAs per SM) is sorted by its digit inside shared memory with two stable
-//                       split steps (low 5 bits, then the high bits; ranks from match.any within the warp + per-warp
-//                       counters), so equal digits sit together and leave the SM as runs of consecutive addresses.
+//                       split steps (low 5 bits, then the high bits; ranks from ballots and per-lane running counts,
+//                       rdx_split), so equal digits sit together and leave the SM as runs of consecutive addresses.
 // Bytes per pass and pair: key read twice (histogram, scatter), value read once, both written once.
 #pragma once
 #include "common.cuh"
@@ -24,7 +24,6 @@
 #define RDX_WARP_ITEMS (32 * RDX_ITEMS)             // 768: a warp's items are tile positions [w * 768, w * 768 + 768)
 #define RDX_MAX_BITS 11
 #define RDX_MAX_BINS (1 << RDX_MAX_BITS)
-#define RDX_SPLIT_BINS 65                           // a split step ranks at most 64 bins + the bin of the padding items
 
 template <class K> __device__ __forceinline__ u32 rdx_digit(K key, int shift, u32 mask) { return (u32)(key >> shift) & mask; }
 
@@ -73,52 +72,66 @@ rdx_scan_kernel(u32* __restrict__ v, int64_t m) {
     for (int64_t i = a; i < b; ++i) { const u32 c = v[i]; v[i] = run; run += c; }
 }
 
-// One stable split step of a tile: dig[r] < nbins is the bin of the thread's r-th item (tile position
-// warp * 768 + r * 32 + lane); returns pos[r] = its position after a stable sort of the tile by bin.
-// cnt: shared [RDX_WARPS][RDX_SPLIT_BINS], base: shared [RDX_SPLIT_BINS].  Ends with the CTA synchronised.
-__device__ __forceinline__ void rdx_split(const u32 (&dig)[RDX_ITEMS], u32 (&pos)[RDX_ITEMS], u32 nbins, u32 (*cnt)[RDX_SPLIT_BINS], u32* base) {
+// One stable split step of a tile: dig[r] < 2^NB is the bin of the thread's r-th item (tile position
+// p0 + 32 r, p0 = warp * 768 + lane); returns pos[r] = its position after a stable sort of the tile by bin.  Items
+// at tile positions >= n_valid are padding (the last tile of the input): they keep their position, the others are
+// ranked among themselves and land below n_valid.
+// Ranks inside the warp need neither shared memory nor match.any: lane L keeps the running count of bin L (and of
+// bin L + 32 when NB == 6) in a register; per round NB ballots give every lane both the lanes that share its item's
+// bin (AND of the ballots or their complements by the item's bits) and the lanes whose item falls in ITS bin (the
+// same by the lane's bits); the base of an item's bin comes from the lane that owns the bin by one shuffle.
+// cnt: shared [RDX_WARPS][64], base: shared [64].  Ends with the CTA synchronised.
+template <int NB>
+__device__ __forceinline__ void rdx_split(const u32 (&dig)[RDX_ITEMS], u32 (&pos)[RDX_ITEMS], u32 p0, u32 n_valid, u32 (*cnt)[64], u32* base) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1u;
-    for (u32 i = threadIdx.x; i < RDX_WARPS * RDX_SPLIT_BINS; i += RDX_THREADS) (&cnt[0][0])[i] = 0;
-    __syncthreads();
-    // rank inside the warp: items of earlier rounds first, then lower lanes
+    u32 run0 = 0, run1 = 0;
 #pragma unroll
     for (int r = 0; r < RDX_ITEMS; ++r) {
-        const u32 peers = __match_any_sync(0xFFFFFFFFu, dig[r]);
-        const int leader = __ffs(peers) - 1;
-        u32 c = 0;
-        if (lane == leader) { c = cnt[w][dig[r]]; cnt[w][dig[r]] = c + __popc(peers); }
-        __syncwarp();
-        c = __shfl_sync(0xFFFFFFFFu, c, leader);
+        const u32 d = dig[r];
+        u32 peers = __ballot_sync(0xFFFFFFFFu, p0 + 32u * (u32)r < n_valid);
+        u32 mem0 = peers, mem1 = peers;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const u32 b = __ballot_sync(0xFFFFFFFFu, (d >> k) & 1u);
+            peers &= ((d >> k) & 1u) ? b : ~b;
+            if (k < 5) { const u32 x = ((lane >> k) & 1) ? b : ~b; mem0 &= x; mem1 &= x; }
+            else { mem0 &= ~b; mem1 &= b; }
+        }
+        u32 c = __shfl_sync(0xFFFFFFFFu, run0, (int)(d & 31u));
+        if (NB == 6) { const u32 c1 = __shfl_sync(0xFFFFFFFFu, run1, (int)(d & 31u)); c = (d & 32u) ? c1 : c; }
         pos[r] = c + __popc(peers & lt);
+        run0 += __popc(mem0);
+        if (NB == 6) run1 += __popc(mem1);
     }
+    cnt[w][lane] = run0;
+    cnt[w][lane + 32] = NB == 6 ? run1 : 0u;
     __syncthreads();
     // per bin: exclusive sum over the warps, bin totals
-    if (threadIdx.x < nbins) {
+    if (threadIdx.x < 64) {
         u32 run = 0;
 #pragma unroll
         for (int x = 0; x < RDX_WARPS; ++x) { const u32 c = cnt[x][threadIdx.x]; cnt[x][threadIdx.x] = run; run += c; }
         base[threadIdx.x] = run;
     }
     __syncthreads();
-    if (w == 0) {                                   // exclusive sum of up to 65 bin totals: three per lane
-        u32 v0 = (u32)lane * 3 < nbins ? base[lane * 3] : 0, v1 = (u32)lane * 3 + 1 < nbins ? base[lane * 3 + 1] : 0,
-            v2 = (u32)lane * 3 + 2 < nbins ? base[lane * 3 + 2] : 0;
-        const u32 s = v0 + v1 + v2;
-        u32 incl = s;
+    if (w == 0) {                                   // exclusive sum of the 64 bin totals: two per lane
+        const u32 v0 = base[lane * 2], v1 = base[lane * 2 + 1];
+        u32 incl = v0 + v1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= d) incl += t;
         }
-        const u32 ex = incl - s;
-        if ((u32)lane * 3 < nbins) base[lane * 3] = ex;
-        if ((u32)lane * 3 + 1 < nbins) base[lane * 3 + 1] = ex + v0;
-        if ((u32)lane * 3 + 2 < nbins) base[lane * 3 + 2] = ex + v0 + v1;
+        base[lane * 2] = incl - v0 - v1;
+        base[lane * 2 + 1] = incl - v1;
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RDX_ITEMS; ++r) pos[r] += base[dig[r]] + cnt[w][dig[r]];
+    for (int r = 0; r < RDX_ITEMS; ++r) {
+        const u32 p = p0 + 32u * (u32)r;
+        pos[r] = p < n_valid ? pos[r] + base[dig[r]] + cnt[w][dig[r]] : p;
+    }
     __syncthreads();
 }
 
@@ -127,8 +140,8 @@ template <class K> struct RdxSmem {
     u32 vals[RDX_TILE];
     u32 goff[RDX_MAX_BINS];                         // where the CTA's next item of each digit goes
     u32 delta[RDX_MAX_BINS];                        // per tile: goff[d] - (tile position of the digit's first item)
-    u32 cnt[RDX_WARPS][RDX_SPLIT_BINS];
-    u32 base[RDX_SPLIT_BINS + 3];
+    u32 cnt[RDX_WARPS][64];
+    u32 base[64];
 };
 
 template <class K, bool HAS_VALUES>
@@ -143,14 +156,13 @@ rdx_scatter_kernel(const K* __restrict__ keys_in, const u32* __restrict__ vals_i
     const int64_t n_tiles = (n + RDX_TILE - 1) / RDX_TILE;
     const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = min(n_tiles, t0 + tiles_per_cta);
     const int lo_bits = bits < 5 ? bits : 5;
-    const u32 lo_bins = 1u << lo_bits, lo_mask = lo_bins - 1u;
-    const u32 hi_bins = nb >> lo_bits;              // 1 .. 64
+    const u32 lo_mask = (1u << lo_bits) - 1u;
     const u32 p0 = (u32)w * RDX_WARP_ITEMS + (u32)lane;
     __syncthreads();
     for (int64_t tile = t0; tile < t1; ++tile) {
         const int64_t g0 = tile * RDX_TILE;
         // the items of a partial tile (the last one of the input) are padded; padding always sits at tile positions
-        // >= n_valid: it starts there and every split step sends it to an extra last bin
+        // >= n_valid: it starts there and the split steps leave it where it is
         const u32 n_valid = (u32)min((int64_t)RDX_TILE, n - g0);
         K key[RDX_ITEMS];
         u32 val[RDX_ITEMS], dig[RDX_ITEMS], pos[RDX_ITEMS];
@@ -162,8 +174,8 @@ rdx_scatter_kernel(const K* __restrict__ keys_in, const u32* __restrict__ vals_i
         }
         // ---- split 1: low bits of the digit
 #pragma unroll
-        for (int r = 0; r < RDX_ITEMS; ++r) dig[r] = (p0 + (u32)r * 32u < n_valid) ? (rdx_digit(key[r], shift, mask) & lo_mask) : lo_bins;
-        rdx_split(dig, pos, lo_bins + 1u, sm.cnt, sm.base);
+        for (int r = 0; r < RDX_ITEMS; ++r) dig[r] = rdx_digit(key[r], shift, mask) & lo_mask;
+        rdx_split<5>(dig, pos, p0, n_valid, sm.cnt, sm.base);
 #pragma unroll
         for (int r = 0; r < RDX_ITEMS; ++r) {
             sm.keys[pos[r]] = key[r];
@@ -176,9 +188,10 @@ rdx_scatter_kernel(const K* __restrict__ keys_in, const u32* __restrict__ vals_i
             const u32 p = p0 + (u32)r * 32u;
             key[r] = sm.keys[p];
             if (HAS_VALUES) val[r] = sm.vals[p];
-            dig[r] = p < n_valid ? (rdx_digit(key[r], shift, mask) >> lo_bits) : hi_bins;
+            dig[r] = rdx_digit(key[r], shift, mask) >> lo_bits;
         }
-        rdx_split(dig, pos, hi_bins + 1u, sm.cnt, sm.base);           // (synchronises before anything is overwritten)
+        __syncthreads();                                               // everything is read before anything is overwritten
+        rdx_split<6>(dig, pos, p0, n_valid, sm.cnt, sm.base);
 #pragma unroll
         for (int r = 0; r < RDX_ITEMS; ++r) {
             sm.keys[pos[r]] = key[r];

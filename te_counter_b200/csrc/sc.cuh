@@ -25,6 +25,7 @@
 #pragma once
 #include "context.cuh"
 #include <cub/cub.cuh>
+#include "radix.cuh"
 
 #define SC_NONE 0xFFFFFFFFu
 
@@ -125,18 +126,35 @@ struct SumU32 { __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { 
 
 // ------------------------------------------------------------------------------------ Part 1: filter
 // te_count.py:394-438.  keep[r] = 1 for survivors; statistics by warp-aggregated atomics.
+__device__ __forceinline__ u32 sc_filter_one(u32 f, u32 q, u32 cell, u32 chrom, int qual, u32& n_qc, u32& n_lowq, u32& n_badbc) {
+    if (f & (TEC_F_UNMAPPED | TEC_F_DUP | TEC_F_QCFAIL)) { n_qc++; return 0u; }          // :394
+    if ((int)q < qual) { n_lowq++; return 0u; }                                            // :398
+    if (cell == TEC_CELL_INVALID) { n_badbc++; return 0u; }                                // :412
+    return chrom != TEC_CHROM_SC_SKIP ? 1u : 0u;                                           // :432 silent skip
+}
+// VEC: four records per thread, one load per column (the arrays of a push are at least 16-byte aligned)
+template <bool VEC>
 __global__ void sc_filter_kernel(int64_t n, int qual, const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ mapq,
                                  const uint8_t* __restrict__ flag, const u32* __restrict__ cell,
                                  u32* __restrict__ keep, u64* __restrict__ stats) {
     u32 n_qc = 0, n_lowq = 0, n_badbc = 0;
-    SC_LOOP(r, n) {
-        const u32 f = flag[r];
-        u32 k = 0;
-        if (f & (TEC_F_UNMAPPED | TEC_F_DUP | TEC_F_QCFAIL)) n_qc++;                   // :394
-        else if ((int)mapq[r] < qual) n_lowq++;                                        // :398
-        else if (cell[r] == TEC_CELL_INVALID) n_badbc++;                               // :412
-        else if (chrom[r] != TEC_CHROM_SC_SKIP) k = 1;                                 // :432 silent skip
-        keep[r] = k;
+    if (VEC) {
+        const int64_t n4 = n >> 2;
+        SC_LOOP(g, n4) {
+            const u32 f4 = reinterpret_cast<const u32*>(flag)[g], q4 = reinterpret_cast<const u32*>(mapq)[g];
+            const uint2 c4 = reinterpret_cast<const uint2*>(chrom)[g];
+            const uint4 b4 = reinterpret_cast<const uint4*>(cell)[g];
+            uint4 k;
+            k.x = sc_filter_one(f4 & 0xFFu, q4 & 0xFFu, b4.x, c4.x & 0xFFFFu, qual, n_qc, n_lowq, n_badbc);
+            k.y = sc_filter_one((f4 >> 8) & 0xFFu, (q4 >> 8) & 0xFFu, b4.y, c4.x >> 16, qual, n_qc, n_lowq, n_badbc);
+            k.z = sc_filter_one((f4 >> 16) & 0xFFu, (q4 >> 16) & 0xFFu, b4.z, c4.y & 0xFFFFu, qual, n_qc, n_lowq, n_badbc);
+            k.w = sc_filter_one(f4 >> 24, q4 >> 24, b4.w, c4.y >> 16, qual, n_qc, n_lowq, n_badbc);
+            reinterpret_cast<uint4*>(keep)[g] = k;
+        }
+        const int64_t r = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // the last n % 4 records
+        if (r < n) keep[r] = sc_filter_one(flag[r], mapq[r], cell[r], chrom[r], qual, n_qc, n_lowq, n_badbc);
+    } else {
+        SC_LOOP(r, n) keep[r] = sc_filter_one(flag[r], mapq[r], cell[r], chrom[r], qual, n_qc, n_lowq, n_badbc);
     }
     const u64 a = warp_sum(n_qc), b = warp_sum(n_lowq), c = warp_sum(n_badbc);
     if ((threadIdx.x & 31) == 0) {
@@ -175,12 +193,64 @@ __global__ void sc_total_kernel(int64_t n, const u32* __restrict__ excl, const u
 
 // ------------------------------------------------------------------------------------ helpers
 __global__ void sc_iota_kernel(int64_t n, u32* __restrict__ v) { SC_LOOP(i, n) v[i] = (u32)i; }
-__global__ void sc_or_kernel(int64_t n, const u64* __restrict__ v, u64* __restrict__ out) {
+// out[0] = OR of the UMI codes, out[1] = OR of the chrom:strand words (how many bits the sort keys need)
+__global__ void sc_or_kernel(int64_t n, const u64* __restrict__ v, const uint4* __restrict__ frag, u64* __restrict__ out) {
     u64 acc = 0;
-    SC_LOOP(i, n) acc |= v[i];
+    u32 acc_cs = 0;
+    SC_LOOP(i, n) { acc |= v[i]; acc_cs |= frag[i].x; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = 16; o > 0; o >>= 1) { acc |= __shfl_xor_sync(0xffffffffu, acc, o); acc_cs |= __shfl_xor_sync(0xffffffffu, acc_cs, o); }
     if ((threadIdx.x & 31) == 0 && acc) atomicOr(out, acc);
+    if ((threadIdx.x & 31) == 0 && acc_cs) atomicOr(out + 1, (u64)acc_cs);
+}
+
+// One 64-bit sort key per survivor: cell | UMI at 2 bits per character | chrom:strand word.  Only for UMIs of exactly
+// L <= 16 characters over {A, C, G, T} (3-bit codes 1, 2, 3, 5 left aligned in 63 bits, reads.py); anything else raises
+// *bad and the caller takes the two-sort path.  The 21 groups are converted at once: g - 1 - (g >> 2) maps 1, 2, 3, 5
+// to 0..3 without borrows, then four shift-and-mask steps close the gaps between the 2-bit fields.
+__global__ void sc_pack_key_kernel(int64_t n, const u32* __restrict__ cell, const u64* __restrict__ umi, const uint4* __restrict__ frag,
+                                   int L, int cs_bits, u64* __restrict__ key, u32* __restrict__ idx, u32* __restrict__ bad) {
+    const u64 M1 = 0x1249249249249249ULL;
+    const int drop = 3 * (21 - L);
+    const u64 low = (1ULL << drop) - 1ULL;                    // L >= 1: drop <= 60
+    const u64 ML = M1 & ((1ULL << (3 * L)) - 1ULL);           // L <= 16: 3 L <= 48
+    bool any_bad = false;
+    SC_LOOP(i, n) {
+        const u64 code = umi[i];
+        const u64 x = code >> drop;
+        const u64 b0 = x & ML, b1 = (x >> 1) & ML, b2 = (x >> 2) & ML;
+        any_bad |= ((code & low) | (code >> 63) | (ML & ~(b0 | b1 | b2)) | (b2 & ((ML & ~b0) | b1))) != 0;
+        u64 y = x - ML - b2;
+        y = (y & 0x30C30C30C30C30C3ULL) | ((y >> 1) & (0x30C30C30C30C30C3ULL << 2));
+        y = (y & 0xF00F00F00F00F00FULL) | ((y >> 2) & (0xF00F00F00F00F00FULL << 4));
+        y = (y & 0x00FF0000FF0000FFULL) | ((y >> 4) & (0x00FF0000FF0000FFULL << 8));
+        y = (y & 0xFFFF00000000FFFFULL) | ((y >> 8) & (0xFFFF00000000FFFFULL << 16));
+        const u64 u2 = y & 0xFFFFFFFFULL;
+        key[i] = ((u64)cell[i] << (2 * L + cs_bits)) | (u2 << cs_bits) | (u64)frag[i].x;
+        idx[i] = (u32)i;
+    }
+    if (__any_sync(0xFFFFFFFFu, any_bad) && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
+}
+
+// sorted packed keys -> the columns the rest of the pipeline reads (cell, UMI, chrom:strand word in sorted order),
+// key-group heads, and prev[i] = previous survivor with the same (cell, UMI)
+__global__ void sc_unpack_keyhead_kernel(int64_t n, const u64* __restrict__ skey, const u32* __restrict__ perm, int umi_bits, int cs_bits,
+                                         u32* __restrict__ scell, u64* __restrict__ sumi, u32* __restrict__ scs,
+                                         u32* __restrict__ prev, u32* __restrict__ khead_pos) {
+    const u64 umi_mask = (1ULL << umi_bits) - 1ULL;           // umi_bits <= 32
+    const u32 cs_mask = (u32)((1ULL << cs_bits) - 1ULL);
+    SC_LOOP(j, n) {
+        const u64 k = skey[j];
+        const bool head = (j == 0) || ((skey[j - 1] ^ k) >> cs_bits) != 0;
+        scell[j] = (u32)(k >> (umi_bits + cs_bits));
+        sumi[j] = (k >> cs_bits) & umi_mask;
+        scs[j] = (u32)k & cs_mask;
+        prev[perm[j]] = head ? SC_NONE : perm[j - 1];
+        khead_pos[j] = head ? (u32)j : 0u;
+    }
+}
+__global__ void sc_gather_cs_kernel(int64_t n, const u32* __restrict__ perm, const uint4* __restrict__ frag, u32* __restrict__ scs) {
+    SC_LOOP(j, n) scs[j] = __ldg(&frag[perm[j]].x);
 }
 // UMI codes are 3 bits per character (reads.py: A 1, C 2, G 3, N 4, T 5, 0 = end), left aligned in 63 bits.
 // When every UMI has exactly L characters over {A, C, G, T} the same order is kept by 2 bits per
@@ -627,8 +697,11 @@ __global__ void sc_winlist_kernel(int64_t n, const u32* __restrict__ excl, const
 // a warp's fragments are appended with one atomic per warp.
 __global__ void sc_part3_kernel(int64_t n, int64_t n_win, const u32* __restrict__ wlist, IndexView iv, ScTableView tv, int strand_mode,
                                 const u32* __restrict__ ensg_of_slot, const u32* __restrict__ scell, const u32* __restrict__ shead_pos,
-                                const u32* __restrict__ cs, const int32_t* __restrict__ left,
-                                const int32_t* __restrict__ rite, ScOut o) {
+                                const u32* __restrict__ cs, const u32* __restrict__ perm, const uint4* __restrict__ frag, ScOut o) {
+    // the coordinates of a fragment are read where they lie (file order) through perm: only the winners' heads, and the
+    // rare fragments of a line on another chrom:strand, need them
+    auto left = [&](int64_t jj) { return (int)__ldg(&frag[perm[jj]].y); };
+    auto rite = [&](int64_t jj) { return (int)__ldg(&frag[perm[jj]].z); };
     const int lane = threadIdx.x & 31;
     u32 n_assigned = 0, n_crash = 0;
     const int64_t n_round = ((n_win + 31) / 32) * 32;            // whole warps stay in the loop together
@@ -641,7 +714,7 @@ __global__ void sc_part3_kernel(int64_t n, int64_t n_win, const u32* __restrict_
         if (win) {
             cell = scell[j];
             const u32 cs0 = cs[j];
-            sc_count_fragment(iv, tv, strand_mode, ensg_of_slot, cell, cs0, left[j], rite[j], o, fo);
+            sc_count_fragment(iv, tv, strand_mode, ensg_of_slot, cell, cs0, left(j), rite(j), o, fo);
             if (fo.hit) atomicAdd(o.cell_hits + cell, 1u);
             n_assigned += fo.assigned;
             n_crash += fo.crash;
@@ -671,17 +744,17 @@ __global__ void sc_part3_kernel(int64_t n, int64_t n_win, const u32* __restrict_
         for (int64_t a = e - 1; a > j; --a) {
             const u32 csa = cs[a];
             if (csa == cs0) continue;
-            const int la = left[a], ra = rite[a];
+            const int la = left(a), ra = rite(a);
             bool first = true;                       // first occurrence of this exact fragment?
             for (int64_t b = j + 1; b < a && first; ++b)
-                first = !(cs[b] == csa && left[b] == la && rite[b] == ra);
+                first = !(cs[b] == csa && left(b) == la && rite(b) == ra);
             if (!first) continue;
             bool later = false;                      // a later first occurrence with the same chrom:strand wins
             for (int64_t b = a + 1; b < e && !later; ++b) {
                 if (cs[b] != csa) continue;
                 bool fb = true;
                 for (int64_t d = j + 1; d < b && fb; ++d)
-                    fb = !(cs[d] == csa && left[d] == left[b] && rite[d] == rite[b]);
+                    fb = !(cs[d] == csa && left(d) == left(b) && rite(d) == rite(b));
                 later = fb;
             }
             if (later) continue;
@@ -778,7 +851,10 @@ static int sc_ingest_dev(tec_ctx* ctx, int64_t n, const int32_t* start, const in
     u32* keep = s->pos;                 // [n]  flags, then their exclusive scan
     u32* lastflag = s->pos + n;         // [1]  copy of keep[n-1]
     u32* total = s->pos + n + 1;        // [1]
-    sc_filter_kernel<<<SC_GRID(n)>>>(n, s->qual, chrom, mapq, flag, cell, keep, s->d_stats);
+    if (!(((uintptr_t)chrom & 7) || ((uintptr_t)mapq & 3) || ((uintptr_t)flag & 3) || ((uintptr_t)cell & 15)))
+        sc_filter_kernel<true><<<SC_GRID((n + 3) / 4)>>>(n, s->qual, chrom, mapq, flag, cell, keep, s->d_stats);
+    else
+        sc_filter_kernel<false><<<SC_GRID(n)>>>(n, s->qual, chrom, mapq, flag, cell, keep, s->d_stats);
     ctx->launches++;
     TEC_CUDA(cudaMemcpyAsync(lastflag, keep + n - 1, 4, cudaMemcpyDeviceToDevice, ctx->stream));
     size_t tb = 0;
@@ -1111,70 +1187,112 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
     u64* pairs_sorted = nullptr;
     u32 h_npairs = 0;
     if (N > 0 || s->world > 1) {          // with several ranks every rank walks the same sequence of collectives
-        // ---- key groups: stable LSD sort of i by umi, then by cell
+        // ---- key groups: survivors in (cell, UMI, file position) order
         u64* d_or = nullptr;
-        TEC_CUDA(A.get(&d_or, 1));
-        TEC_CUDA(cudaMemsetAsync(d_or, 0, 8, ctx->stream));
-        sc_or_kernel<<<SC_GRID(N)>>>(N, s->umi, d_or);
-        u64 h_or = 0;
-        TEC_CUDA(cudaMemcpyAsync(&h_or, d_or, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TEC_CUDA(A.get(&d_or, 2));
+        TEC_CUDA(cudaMemsetAsync(d_or, 0, 16, ctx->stream));
+        sc_or_kernel<<<SC_GRID(N)>>>(N, s->umi, s->frag, d_or);
+        u64 h_or[2] = {0, 0};
+        TEC_CUDA(cudaMemcpyAsync(h_or, d_or, 16, cudaMemcpyDeviceToHost, ctx->stream));
         TEC_CUDA(cudaStreamSynchronize(ctx->stream));
         int b0 = 0, b1 = 1;
-        if (h_or) { b0 = __builtin_ctzll(h_or); b1 = 64 - __builtin_clzll(h_or); }
-        u32 *iota = nullptr, *perm1 = nullptr, *perm = nullptr, *ck = nullptr, *scell = nullptr;
-        u64 *uk = nullptr, *sumi = nullptr;
-        TEC_CUDA(A.get(&iota, (size_t)N));
-        TEC_CUDA(A.get(&perm1, (size_t)N));
-        TEC_CUDA(A.get(&uk, (size_t)N));
-        sc_iota_kernel<<<SC_GRID(N)>>>(N, iota);
+        if (h_or[0]) { b0 = __builtin_ctzll(h_or[0]); b1 = 64 - __builtin_clzll(h_or[0]); }
+        const int umi_len = h_or[0] ? 21 - b0 / 3 : 0;
+        const int cs_bits = h_or[1] ? 64 - __builtin_clzll(h_or[1]) : 1;
+        const int cell_bits = std::max(1, ceil_log2_i64(W));
+        u32 *perm = nullptr, *scell = nullptr, *scs = nullptr, *prev = nullptr, *khead = nullptr;
+        u64* sumi = nullptr;
         int rc = TEC_OK;
-        // 32-bit keys when every UMI is a fixed-length string over {A, C, G, T} (2 bits per character)
-        bool packed = false;
-        const int umi_len = h_or ? 21 - b0 / 3 : 0;
-        if (ctx->opt_sc_pack_umi && umi_len >= 1 && umi_len <= 16) {
-            u32 *k32 = nullptr, *k32s = nullptr, *d_bad = nullptr;
-            TEC_CUDA(A.get(&k32, (size_t)N));
-            TEC_CUDA(A.get(&k32s, (size_t)N));
+        bool done = false;
+        // (a) one packed 64-bit key per survivor, 11-bit LSD passes of csrc/radix.cuh over its cell and UMI bits; the
+        //     chrom:strand word rides in the low bits, so the sorted keys ARE the sorted columns: nothing is gathered
+        if (ctx->opt_sc_sort != 0 && umi_len >= 1 && umi_len <= 16 && cell_bits + 2 * umi_len + cs_bits <= 64 && N > 0) {
+            u64 *ka = nullptr, *kb = nullptr;
+            u32 *va = nullptr, *vb = nullptr, *d_bad = nullptr, *scratch = nullptr;
+            const RdxPlan plan = rdx_plan(N, ctx->n_sm);
+            TEC_CUDA(A.get(&ka, (size_t)N));
+            TEC_CUDA(A.get(&va, (size_t)N));
             TEC_CUDA(A.get(&d_bad, 1));
             TEC_CUDA(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
-            sc_umi_pack2_kernel<<<SC_GRID(N)>>>(N, s->umi, umi_len, k32, d_bad);
-            ctx->launches++;
+            sc_pack_key_kernel<<<SC_GRID(N)>>>(N, s->cell, s->umi, s->frag, umi_len, cs_bits, ka, va, d_bad);
+            ctx->launches += 2;
             u32 h_bad = 0;
             TEC_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
             TEC_CUDA(cudaStreamSynchronize(ctx->stream));
             if (!h_bad) {
-                rc = sc_sort_pairs(ctx, k32, k32s, iota, perm1, N, 0, 2 * umi_len);
-                if (rc) return rc;
-                packed = true;
+                TEC_CUDA(A.get(&kb, (size_t)N));
+                TEC_CUDA(A.get(&vb, (size_t)N));
+                TEC_CUDA(A.get(&scratch, plan.counts_bytes / 4));
+                bool in_b = false;
+                int n_pass = 0;
+                TEC_CUDA((rdx_sort<u64, true>(ka, va, kb, vb, N, cs_bits, cs_bits + 2 * umi_len + cell_bits, ctx->n_sm, scratch, ctx->stream, &in_b, &n_pass)));
+                ctx->launches += 3 * n_pass;
+                const u64* skey = in_b ? kb : ka;
+                perm = in_b ? vb : va;
+                A.release(in_b ? va : vb);
+                TEC_CUDA(A.get(&scell, (size_t)N));
+                TEC_CUDA(A.get(&sumi, (size_t)N));
+                TEC_CUDA(A.get(&scs, (size_t)N));
+                TEC_CUDA(A.get(&prev, (size_t)N));
+                TEC_CUDA(A.get(&khead, (size_t)N));
+                sc_unpack_keyhead_kernel<<<SC_GRID(N)>>>(N, skey, perm, 2 * umi_len, cs_bits, scell, sumi, scs, prev, khead);
+                ctx->launches++;
+                A.release(ka); A.release(kb); A.release(scratch);
+                done = true;
+            } else {
+                A.release(ka); A.release(va);
             }
-            A.release(k32); A.release(k32s); A.release(d_bad);
+            A.release(d_bad);
         }
-        if (!packed) {
-            rc = sc_sort_pairs(ctx, s->umi, uk, iota, perm1, N, b0, b1);
+        // (b) any other UMI alphabet / length: stable LSD sort of i by UMI, then by cell (library sort), columns gathered
+        if (!done) {
+            u32 *iota = nullptr, *perm1 = nullptr, *ck = nullptr;
+            u64* uk = nullptr;
+            TEC_CUDA(A.get(&iota, (size_t)N));
+            TEC_CUDA(A.get(&perm1, (size_t)N));
+            TEC_CUDA(A.get(&uk, (size_t)N));
+            sc_iota_kernel<<<SC_GRID(N)>>>(N, iota);
+            // 32-bit keys when every UMI is a fixed-length string over {A, C, G, T} (2 bits per character)
+            bool packed = false;
+            if (ctx->opt_sc_pack_umi && umi_len >= 1 && umi_len <= 16) {
+                u32 *k32 = nullptr, *k32s = nullptr, *d_bad = nullptr;
+                TEC_CUDA(A.get(&k32, (size_t)N));
+                TEC_CUDA(A.get(&k32s, (size_t)N));
+                TEC_CUDA(A.get(&d_bad, 1));
+                TEC_CUDA(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+                sc_umi_pack2_kernel<<<SC_GRID(N)>>>(N, s->umi, umi_len, k32, d_bad);
+                ctx->launches++;
+                u32 h_bad = 0;
+                TEC_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (!h_bad) {
+                    rc = sc_sort_pairs(ctx, k32, k32s, iota, perm1, N, 0, 2 * umi_len);
+                    if (rc) return rc;
+                    packed = true;
+                }
+                A.release(k32); A.release(k32s); A.release(d_bad);
+            }
+            if (!packed) {
+                rc = sc_sort_pairs(ctx, s->umi, uk, iota, perm1, N, b0, b1);
+                if (rc) return rc;
+            }
+            A.release(uk); uk = nullptr;
+            TEC_CUDA(A.get(&ck, (size_t)N));
+            TEC_CUDA(A.get(&scell, (size_t)N));
+            sc_gather_kernel<u32><<<SC_GRID(N)>>>(N, perm1, s->cell, ck);
+            perm = iota;                          // reuse
+            rc = sc_sort_pairs(ctx, ck, scell, perm1, perm, N, 0, cell_bits);
             if (rc) return rc;
+            A.release(ck); A.release(perm1);
+            TEC_CUDA(A.get(&sumi, (size_t)N));
+            sc_gather_kernel<u64><<<SC_GRID(N)>>>(N, perm, s->umi, sumi);
+            TEC_CUDA(A.get(&scs, (size_t)N));
+            sc_gather_cs_kernel<<<SC_GRID(N)>>>(N, perm, s->frag, scs);
+            TEC_CUDA(A.get(&prev, (size_t)N));
+            TEC_CUDA(A.get(&khead, (size_t)N));
+            sc_keyhead_kernel<<<SC_GRID(N)>>>(N, perm, scell, sumi, prev, khead);
+            ctx->launches += 6;
         }
-        A.release(uk); uk = nullptr;
-        TEC_CUDA(A.get(&ck, (size_t)N));
-        TEC_CUDA(A.get(&scell, (size_t)N));
-        sc_gather_kernel<u32><<<SC_GRID(N)>>>(N, perm1, s->cell, ck);
-        perm = iota;                          // reuse
-        rc = sc_sort_pairs(ctx, ck, scell, perm1, perm, N, 0, std::max(1, ceil_log2_i64(W)));
-        if (rc) return rc;
-        A.release(ck); A.release(perm1);
-        TEC_CUDA(A.get(&sumi, (size_t)N));
-        sc_gather_kernel<u64><<<SC_GRID(N)>>>(N, perm, s->umi, sumi);
-        u32* scs = nullptr;
-        int32_t *sleft = nullptr, *srite = nullptr;
-        TEC_CUDA(A.get(&scs, (size_t)N));
-        TEC_CUDA(A.get(&sleft, (size_t)N));
-        TEC_CUDA(A.get(&srite, (size_t)N));
-        sc_gather3_kernel<<<SC_GRID(N)>>>(N, perm, s->frag, scs, sleft, srite);
-        ctx->launches++;
-        u32 *prev = nullptr, *khead = nullptr;
-        TEC_CUDA(A.get(&prev, (size_t)N));
-        TEC_CUDA(A.get(&khead, (size_t)N));
-        sc_keyhead_kernel<<<SC_GRID(N)>>>(N, perm, scell, sumi, prev, khead);
-        ctx->launches += 5;
         rc = sc_incl_scan(ctx, khead, N, MaxU32());
         if (rc) return rc;
         // ---- bundle boundaries (te_count.py:377): a bundle closes after the survivor that brings
@@ -1321,7 +1439,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
             tv.pair_key = ctx->idx.sc_pair_key; tv.pair_type = ctx->idx.sc_pair_type;
             tv.present = (ctx->idx.has_sc_stab && ctx->opt_sc_algo != 0) ? 1 : 0;
             sc_part3_kernel<<<SC_GRID(h_nwin)>>>(N, (int64_t)h_nwin, wlist, ctx->idx.view(), tv, s->strand, d_ensg_of_slot, scell, shead,
-                                                 scs, sleft, srite, o);
+                                                 scs, perm, s->frag, o);
             ctx->launches++;
             u32 h_over = 0;
             TEC_CUDA(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1334,7 +1452,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         }
         // release what Part 3 no longer needs before sorting the pair list
         A.release(wflag); A.release(wlist); A.release(minumi); A.release(present); A.release(bundle); A.release(shead); A.release(khead);
-        A.release(sumi); A.release(scell); A.release(perm); A.release(scs); A.release(sleft); A.release(srite);
+        A.release(sumi); A.release(scell); A.release(perm); A.release(scs);
         // ---- triples: sort (ensg, cell) keys, run-length encode
         if (h_npairs) {
             TEC_CUDA(A.get(&pairs_sorted, (size_t)h_npairs));
