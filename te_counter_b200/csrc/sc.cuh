@@ -1226,7 +1226,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
                 bool in_b = false;
                 int n_pass = 0;
                 TEC_CUDA((rdx_sort<u64, true>(ka, va, kb, vb, N, cs_bits, cs_bits + 2 * umi_len + cell_bits, ctx->n_sm, scratch, ctx->stream, &in_b, &n_pass)));
-                ctx->launches += 3 * n_pass;
+                ctx->launches += RDX_LAUNCHES_PER_PASS * n_pass;
                 const u64* skey = in_b ? kb : ka;
                 perm = in_b ? vb : va;
                 A.release(in_b ? va : vb);

@@ -595,6 +595,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
     else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }
     else if (k == "sc_sort") { if (value < 0 || value > 1) TEC_FAIL(TEC_ERR_ARG, "sc_sort: 0 library sort in two stages, 1 packed keys + csrc/radix.cuh"); ctx->opt_sc_sort = (int)value; }
+    else if (k == "sc_sort_chunk") { if (value < 1 || value > 64) TEC_FAIL(TEC_ERR_ARG, "sc_sort_chunk: tiles per chunk of csrc/radix.cuh, 1..64"); g_rdx_chunk_tiles = (int)value; }
     else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }
     else if (k == "bulk_mode") { if (value < 0 || value > 15) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline"); ctx->opt_bulk_mode = (int)value; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }

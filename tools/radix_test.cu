@@ -63,6 +63,15 @@ int main(int argc, char** argv) {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     const int n_sm = p.multiProcessorCount;
     int fails = 0;
+    if (getenv("RDX_BITS")) g_rdx_max_bits = atoi(getenv("RDX_BITS"));
+    if (getenv("RDX_CHUNK")) g_rdx_chunk_tiles = atoi(getenv("RDX_CHUNK"));
+    if (getenv("RDX_BIG_ONLY")) {
+        const int64_t big = argc > 1 ? atoll(argv[1]) : 400000000;
+        fails += run<u64>(big, 18, 59, 1, n_sm);
+        fails += run<u64>(big, 18, 59, 0, n_sm);
+        printf(fails ? "FAILED %d\n" : "all ok\n", fails);
+        return fails ? 1 : 0;
+    }
     const int64_t sizes[] = {1, 31, 6143, 6144, 6145, 100000, 1000003, 20000000};
     for (int64_t n : sizes) {
         fails += run<u64>(n, 0, 11, 0, n_sm);
