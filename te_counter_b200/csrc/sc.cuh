@@ -40,7 +40,8 @@ struct ScState {
     uint4* frag = nullptr;          // {cs = chrom << 2 | strand code (0 '+', 1 '-', 2 'NA'), left, rite, 0}: one 16-byte
                                     // record, so the gather into sorted order is one random read per survivor
     int64_t n = 0, cap = 0;         // n is exact only after sc_sync_count()
-    u64* d_n = nullptr;             // survivors held (device): pushes do not wait for the host
+    u64* d_n = nullptr;             // [0] survivors held (device): pushes do not wait for the host; [1] OR of their UMI codes, [2] of their chrom:strand words
+    bool or_tracked = false;        // d_n[1..2] cover every survivor held (false after tec_sc_import_packed_dev)
     int64_t n_bound = 0;            // upper bound of n (everything pushed so far), sizes the columns
     bool n_pending = false;
     void* packed = nullptr;         // multi-GPU: survivors packed for the exchange (tec_sc_partition_dev)
@@ -165,21 +166,33 @@ __global__ void sc_filter_kernel(int64_t n, int qual, const uint16_t* __restrict
 }
 
 // stable compaction of the survivors behind the ones already held (pos = exclusive scan of keep)
-__global__ void sc_scatter_kernel(int64_t n, int strand, const u64* __restrict__ d_base, const u32* __restrict__ keep_pos, const u32* __restrict__ keep_last,
+__global__ void sc_scatter_kernel(int64_t n, int strand, const u64* __restrict__ d_base, u64* __restrict__ d_or, const u32* __restrict__ keep_pos, const u32* __restrict__ keep_last,
                                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                                   const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ flag,
                                   const u32* __restrict__ cell, const u64* __restrict__ umi,
                                   u32* __restrict__ o_cell, u64* __restrict__ o_umi, uint4* __restrict__ o_frag) {
     const int64_t base = (int64_t)*d_base;
+    u64 or_umi = 0;                                   // how many bits the sort keys need (tec_sc_finalize)
+    u32 or_cs = 0;
     SC_LOOP(r, n) {
         const u32 p = keep_pos[r];
         const u32 nxt = (r + 1 < n) ? keep_pos[r + 1] : *keep_last;
         if (nxt == p) continue;
         const int64_t o = base + p;
         o_cell[o] = cell[r];
-        o_umi[o] = umi[r];
+        const u64 u = umi[r];
+        o_umi[o] = u;
         const u32 sc = strand ? ((flag[r] & TEC_F_REVERSE) ? 1u : 0u) : 2u;            // :437-438
-        o_frag[o] = make_uint4(((u32)chrom[r] << 2) | sc, (u32)start[r], (u32)end[r], 0u);   // :434-435
+        const u32 cs = ((u32)chrom[r] << 2) | sc;
+        o_frag[o] = make_uint4(cs, (u32)start[r], (u32)end[r], 0u);                      // :434-435
+        or_umi |= u;
+        or_cs |= cs;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { or_umi |= __shfl_xor_sync(0xffffffffu, or_umi, d); or_cs |= __shfl_xor_sync(0xffffffffu, or_cs, d); }
+    if ((threadIdx.x & 31) == 0) {
+        if (or_umi) atomicOr(d_or, or_umi);
+        if (or_cs) atomicOr(d_or + 1, (u64)or_cs);
     }
 }
 
@@ -804,8 +817,9 @@ extern "C" int tec_sc_begin(tec_ctx* ctx, int qual, int strand, int64_t n_whitel
     sc_free_results(ctx, s);
     s->qual = qual; s->strand = strand ? 1 : 0; s->n_wl = n_whitelist;
     s->n = 0; s->n_bound = 0; s->n_pending = false; s->units = 0; s->active = true; s->finalized = false; s->has_gidx = false;
-    if (!s->d_n) TEC_CUDA(cudaMalloc(&s->d_n, 8));
-    TEC_CUDA(cudaMemsetAsync(s->d_n, 0, 8, ctx->stream));
+    if (!s->d_n) TEC_CUDA(cudaMalloc(&s->d_n, 24));
+    TEC_CUDA(cudaMemsetAsync(s->d_n, 0, 24, ctx->stream));
+    s->or_tracked = true;
     if (!s->d_stats) TEC_CUDA(cudaMalloc(&s->d_stats, TEC_SC_NSTATS * 8));
     TEC_CUDA(cudaMemsetAsync(s->d_stats, 0, TEC_SC_NSTATS * 8, ctx->stream));
     memset(s->stats, 0, sizeof(s->stats));
@@ -875,7 +889,7 @@ static int sc_ingest_dev(tec_ctx* ctx, int64_t n, const int32_t* start, const in
         TEC_CUDA(sc_grow(&s->frag, s->n, cap, ctx->stream));
         s->cap = cap;
     }
-    sc_scatter_kernel<<<SC_GRID(n)>>>(n, s->strand, s->d_n, keep, total, start, end, chrom, flag, cell, umi,
+    sc_scatter_kernel<<<SC_GRID(n)>>>(n, s->strand, s->d_n, s->d_n + 1, keep, total, start, end, chrom, flag, cell, umi,
                                       s->cell, s->umi, s->frag);
     sc_advance_kernel<<<1, 32, 0, ctx->stream>>>(s->d_n, total);
     ctx->launches += 2;
@@ -1125,6 +1139,7 @@ extern "C" int tec_sc_import_packed_dev(tec_ctx* ctx, int64_t n, const void* rec
     s->n_pending = false;
     TEC_CUDA(cudaMemcpy(s->d_n, &n, 8, cudaMemcpyHostToDevice));
     s->has_gidx = true;
+    s->or_tracked = false;
     return TEC_OK;
 }
 
@@ -1188,10 +1203,12 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
     u32 h_npairs = 0;
     if (N > 0 || s->world > 1) {          // with several ranks every rank walks the same sequence of collectives
         // ---- key groups: survivors in (cell, UMI, file position) order
-        u64* d_or = nullptr;
-        TEC_CUDA(A.get(&d_or, 2));
-        TEC_CUDA(cudaMemsetAsync(d_or, 0, 16, ctx->stream));
-        sc_or_kernel<<<SC_GRID(N)>>>(N, s->umi, s->frag, d_or);
+        u64* d_or = s->d_n + 1;                 // kept up to date by the pushes
+        if (!s->or_tracked) {
+            TEC_CUDA(cudaMemsetAsync(d_or, 0, 16, ctx->stream));
+            sc_or_kernel<<<SC_GRID(N)>>>(N, s->umi, s->frag, d_or);
+            ctx->launches++;
+        }
         u64 h_or[2] = {0, 0};
         TEC_CUDA(cudaMemcpyAsync(h_or, d_or, 16, cudaMemcpyDeviceToHost, ctx->stream));
         TEC_CUDA(cudaStreamSynchronize(ctx->stream));
