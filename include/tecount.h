@@ -209,6 +209,29 @@ int tec_sc_survivors(tec_ctx* ctx, int64_t* n);
 int tec_sc_partition_dev(tec_ctx* ctx, int world, int64_t gidx_base, int64_t* counts, void** records);
 int tec_sc_import_packed_dev(tec_ctx* ctx, int64_t n, const void* records);
 
+/* ---- collectives issued by the library (NCCL, bound at run time with dlopen; SURVEY.md 8b proposed
+ * tec_reduce(ctx, ncclComm), 8e lists the exchange steps) ---------------------------------------
+ * One communicator per context: rank 0 calls tec_comm_unique_id, the TEC_COMM_ID_BYTES bytes travel to
+ * the other ranks by any means (te_counter_b200/dist.py: torch.distributed broadcast), every rank calls
+ * tec_comm_init.  From then on the library runs its collectives itself, on its own stream and buffers:
+ *   tec_bulk_allreduce        sum of the ranks' counter blocks, in place, behind the pushes; tec_bulk_finish
+ *                             then returns the job's counts on every rank (te_count.py:128-149 summed)
+ *   tec_sc_exchange           after the pushes: all-to-all of the survivors by owner rank cell % world
+ *                             (tec_sc_partition_dev + grouped send / receive + tec_sc_import_packed_dev);
+ *                             tec_sc_finalize then all-reduces through NCCL where tec_sc_set_collective
+ *                             would have called back
+ *   tec_sc_allgather_triples  after tec_sc_finalize: every rank holds the job's triples, ascending in
+ *                             (ensg, cell); tec_sc_fetch returns them
+ * Every rank must make the same sequence of these calls.  TEC_ERR_UNSUPPORTED: libnccl.so.2 not found. */
+#define TEC_COMM_ID_BYTES 128
+int tec_comm_unique_id(tec_ctx* ctx, void* id, int32_t capacity);
+int tec_comm_init(tec_ctx* ctx, const void* id, int32_t rank, int32_t world);
+int tec_comm_destroy(tec_ctx* ctx);
+int tec_comm_info(tec_ctx* ctx, int32_t* rank, int32_t* world);
+int tec_bulk_allreduce(tec_ctx* ctx);
+int tec_sc_exchange(tec_ctx* ctx, int64_t* n_owned);
+int tec_sc_allgather_triples(tec_ctx* ctx, int64_t* n_triples);
+
 /* sc_save_result's choice of rows (te_count.py:724-733): hit cells by count descending, ties by
  * ascending id, at most maxcells.  cells_out must hold min(maxcells, n_hit_cells) entries. */
 int tec_sc_select(tec_ctx* ctx, int64_t maxcells, uint32_t* cells_out, int64_t* n_out);

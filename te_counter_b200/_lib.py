@@ -69,7 +69,16 @@ SIGNATURES = {
     "tec_sc_survivors": (ctypes.c_int, [_vp, _c_i64p]),
     "tec_sc_partition_dev": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, _c_i64p, ctypes.POINTER(_vp)]),
     "tec_sc_import_packed_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
+    "tec_comm_unique_id": (ctypes.c_int, [_vp, _vp, ctypes.c_int32]),
+    "tec_comm_init": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32]),
+    "tec_comm_destroy": (ctypes.c_int, [_vp]),
+    "tec_comm_info": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "tec_bulk_allreduce": (ctypes.c_int, [_vp]),
+    "tec_sc_exchange": (ctypes.c_int, [_vp, _c_i64p]),
+    "tec_sc_allgather_triples": (ctypes.c_int, [_vp, _c_i64p]),
 }
+
+COMM_ID_BYTES = 128
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int)
 
@@ -396,6 +405,42 @@ class Engine:
 
     def sc_import_packed_dev(self, n, records):
         self._check(self._lib.tec_sc_import_packed_dev(self._h, int(n), records))
+
+    # ---- collectives issued by the library (NCCL; include/tecount.h)
+    def comm_unique_id(self):
+        """bytes of a fresh communicator id (rank 0; carry them to the other ranks, then comm_init everywhere)"""
+        buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+        self._check(self._lib.tec_comm_unique_id(self._h, buf, COMM_ID_BYTES))
+        return buf.raw
+
+    def comm_init(self, comm_id, rank, world):
+        if len(comm_id) != COMM_ID_BYTES:
+            raise ValueError("communicator id must be %d bytes" % COMM_ID_BYTES)
+        self._check(self._lib.tec_comm_init(self._h, ctypes.c_char_p(bytes(comm_id)), int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._check(self._lib.tec_comm_destroy(self._h))
+
+    def comm_world(self):
+        r, w = ctypes.c_int32(0), ctypes.c_int32(1)
+        self._check(self._lib.tec_comm_info(self._h, ctypes.byref(r), ctypes.byref(w)))
+        return r.value, w.value
+
+    def bulk_allreduce(self):
+        """sum of the ranks' counter blocks in place (behind the pushes, on the library's stream)"""
+        self._check(self._lib.tec_bulk_allreduce(self._h))
+
+    def sc_exchange(self):
+        """all-to-all of the survivors by owner rank; returns the number of records this rank now owns"""
+        n = ctypes.c_int64(0)
+        self._check(self._lib.tec_sc_exchange(self._h, ctypes.byref(n)))
+        return n.value
+
+    def sc_allgather_triples(self):
+        """after sc_finalize: the job's triples on every rank; returns their number (pass it to sc_fetch)"""
+        n = ctypes.c_int64(0)
+        self._check(self._lib.tec_sc_allgather_triples(self._h, ctypes.byref(n)))
+        return n.value
 
     def sc_select(self, maxcells, n_hit_cells):
         out = np.zeros(max(1, min(int(maxcells), int(n_hit_cells))), dtype=np.uint32)

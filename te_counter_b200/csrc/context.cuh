@@ -168,6 +168,7 @@ struct tec_ctx {
     int opt_second_parts = 2;             // warps of the second bulk pass per segment of the deferred list
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
     int opt_sc_sort = 1;                  // single cell: packed 64-bit keys + the 11-bit radix sort of csrc/radix.cuh (0: library sort, two stages)
+    int opt_sc_prev_partition = 1;        // single cell: prev[] placed through one radix pass on the position (0: random 4-byte stores)
     int opt_sc_pack_umi = 1;              // single cell: 2-bit UMI sort keys when every UMI is fixed-length ACGT
     int opt_sc_algo = -1;                 // -1 auto, 0 exact search only, 1 cell table
     int opt_bam_lanes = 1;                // BGZF blocks decoded per warp by the inflate kernel (1..32): the streams of a warp
@@ -182,6 +183,8 @@ struct tec_ctx {
     int stage_next = 0;
 
     ScState* sc = nullptr;
+    void* comm = nullptr;                 // ncclComm_t of tec_comm_init (collective.cuh); the library's own collectives run on `stream`
+    int comm_rank = 0, comm_world = 1;
     uint8_t* bam_pinned[2] = {nullptr, nullptr};    // staging chunks of the device BAM decoder (bamgpu.cuh)
     cudaEvent_t bam_ev[3] = {nullptr, nullptr, nullptr};
     cudaStream_t bam_stream2 = nullptr;

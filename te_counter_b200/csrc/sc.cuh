@@ -247,6 +247,10 @@ __global__ void sc_pack_key_kernel(int64_t n, const u32* __restrict__ cell, cons
 
 // sorted packed keys -> the columns the rest of the pipeline reads (cell, UMI, chrom:strand word in sorted order),
 // key-group heads, and prev[i] = previous survivor with the same (cell, UMI)
+// SCATTER: prev[perm[j]] is written in place (a random 4-byte store per survivor).  Otherwise the value goes to
+// prev[j] in sorted order and reaches its place in two coalesced steps (one radix pass on the high bits of perm,
+// then sc_prev_place_kernel inside L2-sized windows).
+template <bool SCATTER>
 __global__ void sc_unpack_keyhead_kernel(int64_t n, const u64* __restrict__ skey, const u32* __restrict__ perm, int umi_bits, int cs_bits,
                                          u32* __restrict__ scell, u64* __restrict__ sumi, u32* __restrict__ scs,
                                          u32* __restrict__ prev, u32* __restrict__ khead_pos) {
@@ -258,9 +262,17 @@ __global__ void sc_unpack_keyhead_kernel(int64_t n, const u64* __restrict__ skey
         scell[j] = (u32)(k >> (umi_bits + cs_bits));
         sumi[j] = (k >> cs_bits) & umi_mask;
         scs[j] = (u32)k & cs_mask;
-        prev[perm[j]] = head ? SC_NONE : perm[j - 1];
+        const u32 pv = head ? SC_NONE : perm[j - 1];
+        if (SCATTER) prev[perm[j]] = pv; else prev[j] = pv;
         khead_pos[j] = head ? (u32)j : 0u;
     }
+}
+// (position, value) pairs grouped by the high bits of the position: every CTA's stores fall into a few windows of
+// 2^shift positions that stay in L2 until their sectors are complete
+__global__ void sc_prev_place_kernel(int64_t n, const u32* __restrict__ at, const u32* __restrict__ val, u32* __restrict__ prev) {
+    const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;        // contiguous slice per CTA
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+    for (int64_t t = lo + threadIdx.x; t < hi; t += blockDim.x) prev[at[t]] = val[t];
 }
 __global__ void sc_gather_cs_kernel(int64_t n, const u32* __restrict__ perm, const uint4* __restrict__ frag, u32* __restrict__ scs) {
     SC_LOOP(j, n) scs[j] = __ldg(&frag[perm[j]].x);
@@ -959,7 +971,8 @@ extern "C" int tec_sc_push(tec_ctx* ctx, int64_t n_rec, const int32_t* start, co
 // all-reduce of a device buffer over the ranks (no-op on one GPU); dtype 0 u32, 1 u64, 2 i64; op 0 sum, 1 min, 2 max
 static int sc_allreduce(tec_ctx* ctx, void* dev, int64_t count, int dtype, int op) {
     ScState* s = ctx->sc;
-    if (s->world <= 1 || !s->coll) return TEC_OK;
+    if (s->world <= 1) return TEC_OK;
+    if (!s->coll) return ctx->comm ? comm_allreduce(ctx, dev, count, dtype, op) : TEC_OK;      // NCCL on the library's stream: no host round trip
     TEC_CUDA(cudaStreamSynchronize(ctx->stream));
     if (s->coll(s->coll_user, dev, count, dtype, op) != 0) TEC_FAIL(TEC_ERR_STATE, "single-cell collective callback failed");
     return TEC_OK;
@@ -1246,15 +1259,29 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
                 ctx->launches += RDX_LAUNCHES_PER_PASS * n_pass;
                 const u64* skey = in_b ? kb : ka;
                 perm = in_b ? vb : va;
-                A.release(in_b ? va : vb);
+                u32* free_v = in_b ? va : vb;                 // the other half of the ping-pong: free from here on
+                u64* free_k = in_b ? ka : kb;
                 TEC_CUDA(A.get(&scell, (size_t)N));
                 TEC_CUDA(A.get(&sumi, (size_t)N));
                 TEC_CUDA(A.get(&scs, (size_t)N));
                 TEC_CUDA(A.get(&prev, (size_t)N));
                 TEC_CUDA(A.get(&khead, (size_t)N));
-                sc_unpack_keyhead_kernel<<<SC_GRID(N)>>>(N, skey, perm, 2 * umi_len, cs_bits, scell, sumi, scs, prev, khead);
-                ctx->launches++;
-                A.release(ka); A.release(kb); A.release(scratch);
+                const int pos_bits = std::max(1, ceil_log2_i64(N));
+                const int part_bits = std::min(RDX_MAX_BITS, pos_bits);
+                if (ctx->opt_sc_prev_partition == 2 || (ctx->opt_sc_prev_partition && pos_bits > RDX_MAX_BITS + 4)) {   // 2: always (tests)
+                    // prev[] in file order without 894 M random read-modify-writes of a sector: the values are written in
+                    // sorted order, grouped by the top 11 bits of their position (one radix pass) and placed window by window
+                    sc_unpack_keyhead_kernel<false><<<SC_GRID(N)>>>(N, skey, perm, 2 * umi_len, cs_bits, scell, sumi, scs, free_v, khead);
+                    u32* at = reinterpret_cast<u32*>(free_k);
+                    u32* val = at + N;
+                    TEC_CUDA((rdx_pass<u32, true>(perm, free_v, at, val, N, pos_bits - part_bits, part_bits, plan, scratch, ctx->stream)));
+                    sc_prev_place_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(N, at, val, prev);
+                    ctx->launches += 2 + RDX_LAUNCHES_PER_PASS;
+                } else {
+                    sc_unpack_keyhead_kernel<true><<<SC_GRID(N)>>>(N, skey, perm, 2 * umi_len, cs_bits, scell, sumi, scs, prev, khead);
+                    ctx->launches++;
+                }
+                A.release(free_v); A.release(ka); A.release(kb); A.release(scratch);
                 done = true;
             } else {
                 A.release(ka); A.release(va);
@@ -1530,7 +1557,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
     s->stats[TEC_SS_UNITS] = s->units;
     s->stats[TEC_SS_BUNDLES] = n_b;
     s->stats[TEC_SS_SURVIVORS] = N;
-    if (s->world > 1 && s->coll) {
+    if (s->world > 1 && (s->coll || ctx->comm)) {
         // job-wide statistics: sums over the ranks, except the two that are already global
         u64 tmp[TEC_SC_NSTATS];
         for (int i = 0; i < TEC_SC_NSTATS; ++i) tmp[i] = (u64)s->stats[i];

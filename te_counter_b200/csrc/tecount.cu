@@ -3,7 +3,9 @@
 #include "bulk.cuh"
 #include "stab_build.h"
 #include "context.cuh"
+#include "collective.cuh"
 #include "sc.cuh"
+#include "sc_comm.cuh"
 #include "sc_text.cuh"
 #include "bamgpu.cuh"
 
@@ -66,6 +68,7 @@ extern "C" void tec_destroy(tec_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    tec_comm_destroy(ctx);
     ctx->free_all();
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage_ready[i]) cudaEventDestroy(ctx->stage_ready[i]);
@@ -595,6 +598,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
     else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }
     else if (k == "sc_sort") { if (value < 0 || value > 1) TEC_FAIL(TEC_ERR_ARG, "sc_sort: 0 library sort in two stages, 1 packed keys + csrc/radix.cuh"); ctx->opt_sc_sort = (int)value; }
+    else if (k == "sc_prev_partition") { if (value < 0 || value > 2) TEC_FAIL(TEC_ERR_ARG, "sc_prev_partition: 0 random stores, 1 radix pass on large inputs, 2 always"); ctx->opt_sc_prev_partition = (int)value; }
     else if (k == "sc_sort_chunk") { if (value < 1 || value > 64) TEC_FAIL(TEC_ERR_ARG, "sc_sort_chunk: tiles per chunk of csrc/radix.cuh, 1..64"); g_rdx_chunk_tiles = (int)value; }
     else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }
     else if (k == "bulk_mode") { if (value < 0 || value > 15) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline"); ctx->opt_bulk_mode = (int)value; }

@@ -30,10 +30,28 @@ def counts_tensor(engine, n_ensg, device):
     return torch.as_tensor(_DevArray(engine.bulk_counts_dev(), n_ensg + _lib.BULK_NSTATS, "<i8"), device=device)
 
 
+def comm_init(engine, group=None):
+    """Give the engine its own NCCL communicator over the ranks of `group` (the library then issues its
+    collectives itself: tec_bulk_allreduce, tec_sc_exchange, tec_sc_allgather_triples).  The 128-byte id is
+    the only thing that travels through torch.distributed.  Returns False where the backend is not NCCL
+    (CPU-side tests over gloo keep the callback path)."""
+    import torch.distributed as dist
+    if dist.get_backend(group) != "nccl":
+        return False
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    engine.comm_init(box[0], rank, world)
+    return True
+
+
 def allreduce_counts_device(engine, n_ensg, device, group=None):
     """Sum the counter blocks of all ranks in place (NCCL), ordered on the engine's stream."""
     import torch
     import torch.distributed as dist
+    if engine.comm_world()[1] > 1:                # the library's own communicator
+        engine.bulk_allreduce()
+        return counts_tensor(engine, n_ensg, device)
     t = counts_tensor(engine, n_ensg, device)
     with torch.cuda.stream(torch.cuda.ExternalStream(engine.stream, device=device)):
         dist.all_reduce(t, group=group)
@@ -121,6 +139,10 @@ def sc_exchange_by_cell(engine, device, group=None):
     tm = time.perf_counter()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     on_gpu = dist.get_backend(group) == "nccl"
+    if engine.comm_world()[1] == world and world > 1:        # comm_init was called: everything inside the library
+        n2 = engine.sc_exchange()
+        mark("library_exchange", tm)
+        return n2
     n = engine.sc_survivors()
     counts = [None] * world
     dist.all_gather_object(counts, int(n), group=group)
@@ -153,7 +175,8 @@ def sc_exchange_by_cell(engine, device, group=None):
 
 def sc_gather_triples(ensg, cell, count, group=None):
     """Concatenate the ranks' (ensg, cell, count) triples and sort by (ensg, cell): the job's
-    final_results.  Every rank gets the full list (numpy arrays)."""
+    final_results.  Every rank gets the full list (numpy arrays).  Host-side version for the gloo tests;
+    with a library communicator use Engine.sc_allgather_triples() before sc_fetch instead."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     parts = [None] * world

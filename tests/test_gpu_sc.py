@@ -169,6 +169,26 @@ def test_sc_umi_key_packing(engine):
     assert [encode_umi(u) for u in us] == sorted(encode_umi(u) for u in us)
 
 
+def test_sc_sort_variants(engine):
+    """The packed-key path in its three forms -- prev[] placed through a radix pass on the position (forced: the inputs
+    of a test are far below the size where it switches on), prev[] stored in place, and the library sort in two
+    stages -- over several bundles, with and without --strand, chunks of 1 and 3 tiles in csrc/radix.cuh."""
+    idx = synth.synth_index(11, n_te=30000, n_exon=9000, n_gene=600, chrom_len=3_000_000, n_chrom=3)
+    engine.upload_index(idx)
+    r = synth.synth_sc_reads(16, idx, 60000, n_whitelist=300, n_cells=70, umis_per_cell=50)
+    try:
+        for prev_part, sort, chunk in ((2, 1, 1), (2, 1, 3), (0, 1, 1), (1, 0, 1)):
+            engine.set_option("sc_prev_partition", prev_part)
+            engine.set_option("sc_sort", sort)
+            engine.set_option("sc_sort_chunk", chunk)
+            check_against_oracle(engine, idx, r, 20, True, 300, 2500, 40, 10)
+            check_against_oracle(engine, idx, r, 20, False, 300, 10_000_000, 40, 10)
+    finally:
+        engine.set_option("sc_prev_partition", 1)
+        engine.set_option("sc_sort", 1)
+        engine.set_option("sc_sort_chunk", 1)
+
+
 def _text_from_triples(n_ensg, ensg, cell, count, cells, barcodes):
     """te_count.py:752-754 restated on the triples: '\\t'.join([barcode] + [str(count or 0) ...])."""
     m = {(int(e), int(c)): int(v) for e, c, v in zip(ensg, cell, count)}

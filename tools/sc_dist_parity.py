@@ -39,6 +39,9 @@ def main():
     r = synth.synth_sc_reads(synth.SEED, idx, args.records_per_rank, n_whitelist=n_wl, device=dev, as_numpy=True, part=(rank, world))
     eng = _lib.Engine(local)
     eng.upload_index(idx)
+    in_library = tdist.comm_init(eng) and not os.environ.get("TEC_DIST_CALLBACKS")
+    if not in_library:
+        eng.comm_destroy()
     eng.sc_begin(20, strand, n_wl)
     n = len(r["start"])
     for a in range(0, n, 1 << 24):
@@ -47,9 +50,12 @@ def main():
     tdist.sc_exchange_by_cell(eng, dev)
     nt, nh = eng.sc_finalize(args.bundle_keys, maxcells, pad)
     t1 = time.perf_counter()
+    if in_library:
+        nt = eng.sc_allgather_triples()            # NCCL inside the library: every rank holds the job's triples
     ensg, cell, count, hcell, hcount, st = eng.sc_fetch(nt, nh)
     sel = eng.sc_select(maxcells, nh)
-    ensg, cell, count = tdist.sc_gather_triples(ensg, cell, count)
+    if not in_library:
+        ensg, cell, count = tdist.sc_gather_triples(ensg, cell, count)
     parts = [None] * world
     dist.all_gather_object(parts, {k: r[k] for k in cols})
     if rank == 0:
@@ -69,7 +75,8 @@ def main():
               and int(st[_lib.SS_UNITS]) + 1 == out["stats"]["total_reads"])
         print(json.dumps({"check": "multi-GPU single cell vs C++ oracle", "n_gpus": world, "records_total": int(n * world),
                           "bundles": out["stats"]["n_bundles"], "triples": int(len(o_ensg)), "hit_cells": int(nh),
-                          "bit_exact": bool(ok), "gpu_exchange_plus_finalize_s": t1 - t0, "oracle_s": tb - ta}))
+                          "bit_exact": bool(ok), "collectives": "library (NCCL: tec_sc_exchange, all-reduces inside tec_sc_finalize, tec_sc_allgather_triples)" if in_library else "torch.distributed + callback",
+                          "gpu_exchange_plus_finalize_s": t1 - t0, "oracle_s": tb - ta}))
         assert ok
     dist.barrier()
     eng.close()
