@@ -97,11 +97,15 @@ def _bulk_tally(idx, result, counts):
         raise ReferenceCrash("NameError", "barcode (te_count.py:147)")
 
 
-def bulk_count(idx, paired, qual, start, end, chrom, mapq, flag):
+def bulk_count(idx, paired, qual, start, end, chrom, mapq, flag, candidate=None):
     """te_count.py:42-165 (paired) / :167-277 (single end).
 
     Returns (counts list[n_ensg], stats dict) where stats['total_reads'] is the reference's
-    off-by-one `idx` (te_count.py:77,163)."""
+    off-by-one `idx` (te_count.py:77,163).
+
+    candidate: None for the reference's loop.  oracle/te_oracle_ext.py passes a predicate
+    (feature index, index of the unit's first record) -> bool to restate the opt-in extensions, which
+    are outside the parity claim."""
     counts = [0] * idx.n_ensg
     bs = idx.bs
     assigned = lowq = badchrom = qcfail = 0
@@ -154,6 +158,8 @@ def bulk_count(idx, paired, qual, start, end, chrom, mapq, flag):
                 loc_ids.update(idx.buckets[c][buck])
         result = []
         for i in loc_ids:
+            if candidate is not None and not candidate(i, r1):
+                continue
             if loc1 >= idx.L[i] and loc1 + 1 <= idx.R[i]:        # :122
                 result.append(i)
             if loc2 - 1 >= idx.L[i] and loc2 <= idx.R[i]:        # :125

@@ -84,21 +84,28 @@ struct BulkStatsLocal {
 // global memory (L2-resident, 8 B x n_ensg); statistics are reduced per warp, then per CTA.
 template <bool PAIRED>
 __global__ void __launch_bounds__(256)
-bulk_count_kernel(IndexView iv, int64_t n_units, int qual,
+bulk_count_kernel(IndexView iv, int64_t n_units, int qual, int strand_mode,
                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                   const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ mapq,
                   const uint8_t* __restrict__ flag, u64* __restrict__ counts, u64* __restrict__ stats) {
+    // strand_mode != 0 is the opt-in extension of tec_set_option("bulk_strand") -- the reference raises
+    // NotImplementedError for bulk --strand (te_count.py:58-59 / :183-184), so this is NOT part of the parity claim:
+    // a feature on '+' or '-' is a candidate only for units whose first record lies on that strand (flag 0x10 = '-');
+    // features with any other strand value stay candidates for both.  Restated in oracle/te_oracle_ext.py.
     BulkStatsLocal st = {0, 0, 0, 0, 0, 0, 0};
     const u32 reject = TEC_F_UNMAPPED | TEC_F_DUP | TEC_F_QCFAIL;
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units;
          u += (int64_t)gridDim.x * blockDim.x) {
         st.units++;
         int c, loc1, loc2;
+        u32 us = 0;                                   // strand of the unit's first record (extension only)
+        auto other_strand = [&](u32 w) { const u32 fs = info_strand(w); return strand_mode != 0 && fs <= 1u && fs != us; };
         if (PAIRED) {
             const uchar2 f2 = *reinterpret_cast<const uchar2*>(flag + 2 * u);
             if ((f2.x & reject) || (f2.y & reject)) { st.qcfail++; continue; }       // :81-86
             if ((int)mapq[2 * u] < qual) { st.lowq++; continue; }                      // :88 read1 only
             if (f2.x & TEC_F_NAME_MISMATCH) { st.crash_name++; continue; }             // :92-94
+            us = (f2.x & TEC_F_REVERSE) ? 1u : 0u;
             c = chrom[2 * u];                                                          // :96 read1 only
             const int2 s2 = *reinterpret_cast<const int2*>(start + 2 * u);
             loc1 = s2.x;                                                               // :97
@@ -106,6 +113,7 @@ bulk_count_kernel(IndexView iv, int64_t n_units, int qual,
         } else {
             if (flag[u] & reject) { st.qcfail++; continue; }                           // :204
             if ((int)mapq[u] < qual) { st.lowq++; continue; }                          // :208
+            us = (flag[u] & TEC_F_REVERSE) ? 1u : 0u;
             c = chrom[u];
             loc1 = start[u];                                                           // :213
             loc2 = end[u];                                                             // :214
@@ -116,6 +124,7 @@ bulk_count_kernel(IndexView iv, int64_t n_units, int qual,
         bool overflow = false;
         bulk_for_each_hit(iv, c, loc1, loc2, [&](int64_t fi) {
             const u32 w = __ldg(iv.info + fi);
+            if (other_strand(w)) return true;
             typemask |= 1u << info_type(w);
             const u32 e = info_ensg(w);
             bool found = false;
@@ -139,12 +148,15 @@ bulk_count_kernel(IndexView iv, int64_t n_units, int qual,
             // (in enumeration order) carries the same ensg -- O(h^2) re-walks, no storage
             int h = 0;
             bulk_for_each_hit(iv, c, loc1, loc2, [&](int64_t fi) {
-                const u32 e = info_ensg(__ldg(iv.info + fi));
+                const u32 wi = __ldg(iv.info + fi);
+                if (other_strand(wi)) { ++h; return true; }
+                const u32 e = info_ensg(wi);
                 int j = 0;
                 bool dup = false;
                 bulk_for_each_hit(iv, c, loc1, loc2, [&](int64_t fj) {
                     if (j++ >= h) return false;
-                    if (info_ensg(__ldg(iv.info + fj)) == e) { dup = true; return false; }
+                    const u32 wj = __ldg(iv.info + fj);
+                    if (!other_strand(wj) && info_ensg(wj) == e) { dup = true; return false; }
                     return true;
                 });
                 if (!dup) atomicAdd(counts + e, 1ULL);

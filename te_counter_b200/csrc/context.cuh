@@ -165,10 +165,12 @@ struct tec_ctx {
     int opt_stab_shift = 0;               // log2 of the cell size; 0 = TEC_BULK_STAB_SHIFT / TEC_SC_STAB_SHIFT
     int opt_bulk_mode = 13;               // fast bulk kernel: bit 0 table sectors evict_last in L2, bit 1 prefetch the next tile's sectors,
                                           // bit 2 tally through the per-warp hit queue, bit 3 512-thread CTAs with three tiles in flight per warp
+    int opt_bulk_strand = 0;              // extension (not in the reference): strand-aware bulk counting, exact kernel only
     int opt_second_parts = 2;             // warps of the second bulk pass per segment of the deferred list
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
     int opt_sc_sort = 1;                  // single cell: packed 64-bit keys + the 11-bit radix sort of csrc/radix.cuh (0: library sort, two stages)
-    int opt_sc_prev_partition = 1;        // single cell: prev[] placed through one radix pass on the position (0: random 4-byte stores)
+    int opt_sc_prev_partition = 0;        // single cell: 0 prev[] by random 4-byte stores (default); 1 / 2 through one radix pass on the position
+                                          // (measured SLOWER at 1 B records: 167.6 vs 156.0 ms per step, gpurun_out/r02w; 2 = also on small inputs, tests)
     int opt_sc_pack_umi = 1;              // single cell: 2-bit UMI sort keys when every UMI is fixed-length ACGT
     int opt_sc_algo = -1;                 // -1 auto, 0 exact search only, 1 cell table
     int opt_bam_lanes = 1;                // BGZF blocks decoded per warp by the inflate kernel (1..32): the streams of a warp

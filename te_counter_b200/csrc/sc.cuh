@@ -270,9 +270,8 @@ __global__ void sc_unpack_keyhead_kernel(int64_t n, const u64* __restrict__ skey
 // (position, value) pairs grouped by the high bits of the position: every CTA's stores fall into a few windows of
 // 2^shift positions that stay in L2 until their sectors are complete
 __global__ void sc_prev_place_kernel(int64_t n, const u32* __restrict__ at, const u32* __restrict__ val, u32* __restrict__ prev) {
-    const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;        // contiguous slice per CTA
-    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
-    for (int64_t t = lo + threadIdx.x; t < hi; t += blockDim.x) prev[at[t]] = val[t];
+    // grid-stride: at any moment the whole grid works inside one or two windows
+    SC_LOOP(t, n) prev[at[t]] = val[t];
 }
 __global__ void sc_gather_cs_kernel(int64_t n, const u32* __restrict__ perm, const uint4* __restrict__ frag, u32* __restrict__ scs) {
     SC_LOOP(j, n) scs[j] = __ldg(&frag[perm[j]].x);
@@ -1275,7 +1274,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
                     u32* at = reinterpret_cast<u32*>(free_k);
                     u32* val = at + N;
                     TEC_CUDA((rdx_pass<u32, true>(perm, free_v, at, val, N, pos_bits - part_bits, part_bits, plan, scratch, ctx->stream)));
-                    sc_prev_place_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(N, at, val, prev);
+                    sc_prev_place_kernel<<<SC_GRID(N)>>>(N, at, val, prev);
                     ctx->launches += 2 + RDX_LAUNCHES_PER_PASS;
                 } else {
                     sc_unpack_keyhead_kernel<true><<<SC_GRID(N)>>>(N, skey, perm, 2 * umi_len, cs_bits, scell, sumi, scs, prev, khead);

@@ -432,10 +432,10 @@ static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, 
     IndexView iv = ctx->idx.view();
     u64* counts = ctx->d_counts;
     u64* stats = ctx->d_counts + ctx->idx.n_ensg;
-    const bool use_stab2 = ctx->idx.has_stab2 && (ctx->opt_bulk_algo == -1 || ctx->opt_bulk_algo == 2) &&
+    const bool use_stab2 = !ctx->opt_bulk_strand && ctx->idx.has_stab2 && (ctx->opt_bulk_algo == -1 || ctx->opt_bulk_algo == 2) &&
                            bulk2_aligned(ctx->paired, start, end, chrom, mapq, flag);
     if (use_stab2) return bulk2_launch_one(ctx, n_units, start, end, chrom, mapq, flag);
-    const bool use_stab = ctx->idx.has_stab && ctx->opt_bulk_algo == 1;
+    const bool use_stab = !ctx->opt_bulk_strand && ctx->idx.has_stab && ctx->opt_bulk_algo == 1;   // the strand extension lives in the exact kernel only
     if (use_stab) {
         // fast kernel: one warp per 32 units, persistent grid; then the exact kernel on flagged units
         const int64_t n_tiles = (n_units + 31) / 32;
@@ -492,9 +492,9 @@ static int bulk_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start, 
     const int64_t want = (n_units + threads - 1) / threads;
     const int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->n_sm * 8);
     if (ctx->paired)
-        bulk_count_kernel<true><<<blocks, threads, 0, ctx->stream>>>(iv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats);
+        bulk_count_kernel<true><<<blocks, threads, 0, ctx->stream>>>(iv, n_units, ctx->qual, ctx->opt_bulk_strand, start, end, chrom, mapq, flag, counts, stats);
     else
-        bulk_count_kernel<false><<<blocks, threads, 0, ctx->stream>>>(iv, n_units, ctx->qual, start, end, chrom, mapq, flag, counts, stats);
+        bulk_count_kernel<false><<<blocks, threads, 0, ctx->stream>>>(iv, n_units, ctx->qual, ctx->opt_bulk_strand, start, end, chrom, mapq, flag, counts, stats);
     ctx->launches++;
     TEC_CUDA(cudaGetLastError());
     return TEC_OK;
@@ -598,6 +598,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_pack_umi") { ctx->opt_sc_pack_umi = value ? 1 : 0; }
     else if (k == "all_hot") { ctx->opt_all_hot = value ? 1 : 0; }
     else if (k == "sc_sort") { if (value < 0 || value > 1) TEC_FAIL(TEC_ERR_ARG, "sc_sort: 0 library sort in two stages, 1 packed keys + csrc/radix.cuh"); ctx->opt_sc_sort = (int)value; }
+    else if (k == "bulk_strand") { ctx->opt_bulk_strand = value ? 1 : 0; }     // opt-in extension, outside the parity claim (bulk.cuh)
     else if (k == "sc_prev_partition") { if (value < 0 || value > 2) TEC_FAIL(TEC_ERR_ARG, "sc_prev_partition: 0 random stores, 1 radix pass on large inputs, 2 always"); ctx->opt_sc_prev_partition = (int)value; }
     else if (k == "sc_sort_chunk") { if (value < 1 || value > 64) TEC_FAIL(TEC_ERR_ARG, "sc_sort_chunk: tiles per chunk of csrc/radix.cuh, 1..64"); g_rdx_chunk_tiles = (int)value; }
     else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }

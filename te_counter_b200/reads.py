@@ -200,9 +200,11 @@ def fill_bulk(batch, sam, chrom_map, paired, qual):
     return more
 
 
-def fill_sc(batch, sam, chrom_map, whitelist, qual, umis=True):
+def fill_sc(batch, sam, chrom_map, whitelist, qual, umis=True, umi_base=0):
     """Single-cell variant (te_count.py:393-438).  Tags are only looked at for records that pass the
-    flag and MAPQ tests, exactly where the reference would raise AssertionError for a missing tag."""
+    flag and MAPQ tests, exactly where the reference would raise AssertionError for a missing tag.
+    umis=False is the opt-in --noumi extension (measureTE(extensions=True)): UB / UR are not looked at and
+    the UMI code of a record is its ordinal in the file, umi_base + position in the batch."""
     start, end, chrom, mapq, flag = batch.start, batch.end, batch.chrom, batch.mapq, batch.flag
     cell, umi = batch.cell, batch.umi
     n = 0
@@ -245,17 +247,20 @@ def fill_sc(batch, sam, chrom_map, whitelist, qual, umis=True):
             umi[n] = 0
             n += 1
             continue
-        if 'UB' in tags:
-            u = tags['UB']
-        elif 'UR' in tags:
-            u = tags['UR']
+        if not umis:
+            code = umi_base + n
         else:
-            raise AssertionError('UB or UR tag not found!')
-        code = umi_cache.get(u)
-        if code is None:
-            code = encode_umi(u)
-            if len(umi_cache) < (1 << 20):
-                umi_cache[u] = code
+            if 'UB' in tags:
+                u = tags['UB']
+            elif 'UR' in tags:
+                u = tags['UR']
+            else:
+                raise AssertionError('UB or UR tag not found!')
+            code = umi_cache.get(u)
+            if code is None:
+                code = encode_umi(u)
+                if len(umi_cache) < (1 << 20):
+                    umi_cache[u] = code
         c = sc_id(r.reference_name)
         start[n] = r.reference_start
         e = r.reference_end

@@ -33,8 +33,10 @@ SC_BUNDLE_KEYS = 10000000        # te_count.py:377  `len(umis) >= 1e7`
 SC_CELL_PAD = 1000               # te_count.py:502  `maxcells+1000`
 
 
-def _open_alignment(filename):
-    """Host readers.  TEC_BAM_DECODER = auto (default) | gpu | native | pysam | python.  `auto` / `gpu`:
+def _open_alignment(filename, tags_optional=False):
+    """Host readers.  tags_optional (the --noumi extension): only the readers with pysam's interface, whose
+    records are packed by reads.fill_sc, can leave the UMI tags unread.
+      TEC_BAM_DECODER = auto (default) | gpu | native | pysam | python.  `auto` / `gpu`:
     the callers first try the device decoder (tec_bam_*) and come here only for files it refuses;
     then block-compressed BAM goes through libtecbam (threads inflate and parse into the pinned
     batch, fastbam.py) when it is built; anything else through pysam as in the reference
@@ -45,7 +47,7 @@ def _open_alignment(filename):
         raise ValueError('TEC_BAM_DECODER must be auto, gpu, native, pysam or python')
     if mode == 'gpu':
         mode = 'auto'
-    if mode == 'native' or (mode == 'auto' and _fastbam.available()):
+    if not tags_optional and (mode == 'native' or (mode == 'auto' and _fastbam.available())):
         try:
             return _fastbam.NativeBam(filename)
         except (_fastbam.NotBgzf, OSError):             # SAM text, plain gzip, not a regular file: next reader
@@ -102,7 +104,7 @@ class ScResult(Mapping):
 
 
 class measureTE:
-    def __init__(self, base_path, quality_threshold, device=None):
+    def __init__(self, base_path, quality_threshold, device=None, extensions=None):
         '''
         **Arguments**
             base_path (Required)
@@ -111,7 +113,16 @@ class measureTE:
                 MAPQ threshold
             device (extension)
                 CUDA ordinal; default LOCAL_RANK or 0
+            extensions (extension; default: the environment variable TEC_EXTENSIONS == '1')
+                Defined semantics for flag combinations on which the reference raises.
+                Off: every one of them raises exactly what the reference raises.  On:
+                  -q N       a one-element list (bin/te_count:30 hands one over) means its element
+                  --strand   in bulk mode: a feature on '+' / '-' is only a candidate for units whose first
+                             record is on that strand (exact-search kernel; te_count.py:58-59 raises)
+                  --noumi    every surviving record is its own molecule (te_count.py:429-442, :703 raise)
+                Nothing here is part of the parity claim; oracle/te_oracle_ext.py restates the rules.
         '''
+        self.extensions = (os.environ.get('TEC_EXTENSIONS') == '1') if extensions is None else bool(extensions)
         self.base_path = base_path
         self.total_reads = 0
         self.quality_threshold = quality_threshold
@@ -137,6 +148,8 @@ class measureTE:
 
     def _qual(self):
         q = self.quality_threshold
+        if self.extensions and isinstance(q, (list, tuple)) and len(q) == 1 and isinstance(q[0], (int, np.integer)):
+            return int(q[0])                                 # extension: -q N
         if not isinstance(q, (int, np.integer)):
             # bin/te_count:30 hands over a list when -q is given; te_count.py:88 then raises
             raise TypeError("'<' not supported between instances of 'int' and '%s'" % type(q).__name__)
@@ -157,10 +170,17 @@ class measureTE:
     # ---------------------------------------------------------------- bulk
     def _parse_bulk(self, filename, strand, log, paired):
         assert filename, 'You must specify a filename'
-        if strand:
+        if strand and not self.extensions:
             raise NotImplementedError()                       # te_count.py:58-59 / :183-184
         qual = self._qual()
         eng = self._engine()
+        eng.set_option('bulk_strand', 1 if strand else 0)     # extension: strand-aware candidates (exact-search kernel)
+        try:
+            return self._parse_bulk_run(eng, filename, log, paired, qual)
+        finally:
+            eng.set_option('bulk_strand', 0)
+
+    def _parse_bulk_run(self, eng, filename, log, paired, qual):
         cm = _reads.ChromMap(self.genome.chrom_keys)
         label = 'reads' if paired else 'SE reads'
         more, done, next_log = True, 0, 1000000
@@ -256,7 +276,7 @@ class measureTE:
         assert whitelistfilename, 'You must specify a whitelist of barcodes'
         assert label, 'You must specify a label'
         whitelist = _reads.Whitelist(whitelistfilename)
-        if not UMIS:
+        if not UMIS and not self.extensions:
             # te_count.py:429-442 records nothing without UMIs and the run ends at :703
             raise ZeroDivisionError('division by zero')
         qual = self._qual()
@@ -266,7 +286,7 @@ class measureTE:
         cm = _reads.ChromMap(self.genome.chrom_keys)
         log.info('Part 1: Collapsing UMI/CB combinations')
         more, done, next_log = True, 0, 10000000
-        if _device_decoder_wanted(eng):
+        if UMIS and _device_decoder_wanted(eng):
             try:
                 dev = eng.bam_open(filename)
                 try:
@@ -290,14 +310,14 @@ class measureTE:
         sam = batch = None
         if more:
             done, next_log = 0, 10000000
-            sam = _open_alignment(filename)
+            sam = _open_alignment(filename, tags_optional=not UMIS)
             native = isinstance(sam, _fastbam.NativeBam)
             if native:
                 sam.bind(cm, whitelist)
             batch = _reads.Batch(BATCH_RECORDS, sc=True, alloc=eng.pinned)
             eng.sc_begin(qual, strand, len(whitelist))
         while more:
-            more = sam.fill_sc(batch, qual) if native else _reads.fill_sc(batch, sam, cm, whitelist, qual)
+            more = sam.fill_sc(batch, qual) if native else _reads.fill_sc(batch, sam, cm, whitelist, qual, umis=UMIS, umi_base=done)
             eng.sc_push(batch.n, batch.start, batch.end, batch.chrom, batch.mapq, batch.flag,
                         batch.cell, batch.umi)
             done += batch.n

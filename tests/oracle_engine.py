@@ -3,7 +3,7 @@ answers come from the CPU oracle.  CPU-only tests plug it into measureTE to exer
 logic (packing, batching, logging, TSV writers) where no GPU exists.  Never used by the product."""
 import numpy as np
 
-from oracle import te_oracle
+from oracle import te_oracle, te_oracle_ext
 from te_counter_b200 import _lib
 
 
@@ -11,6 +11,10 @@ class OracleEngine:
     def __init__(self, device=0):
         self._pinned = []
         self.n_ensg = 0
+        self.options = {}
+
+    def set_option(self, key, value):
+        self.options[key] = int(value)
 
     def pinned(self, n, dtype):
         return np.empty(n, dtype=dtype)
@@ -32,7 +36,8 @@ class OracleEngine:
         cols = [np.concatenate(c) if c else np.zeros(0, np.int64) for c in self._cols]
         st = np.zeros(_lib.BULK_NSTATS, np.int64)
         try:
-            counts, s = te_oracle.bulk_count(self.idx, self._paired, self._qual, *cols)
+            fn = te_oracle_ext.bulk_count_stranded if self.options.get("bulk_strand") else te_oracle.bulk_count
+            counts, s = fn(self.idx, self._paired, self._qual, *cols)
         except te_oracle.ReferenceCrash as e:
             counts = [0] * self.n_ensg
             st[_lib.BS_CRASH_NAME if e.kind == "AttributeError" else _lib.BS_CRASH_ENHANCER] = 1

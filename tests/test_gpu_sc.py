@@ -184,7 +184,7 @@ def test_sc_sort_variants(engine):
             check_against_oracle(engine, idx, r, 20, True, 300, 2500, 40, 10)
             check_against_oracle(engine, idx, r, 20, False, 300, 10_000_000, 40, 10)
     finally:
-        engine.set_option("sc_prev_partition", 1)
+        engine.set_option("sc_prev_partition", 0)
         engine.set_option("sc_sort", 1)
         engine.set_option("sc_sort_chunk", 1)
 
