@@ -273,6 +273,16 @@ const char *tec_bam_reference_name(const tec_bam *b, int i);
 int tec_bam_set_chrom_map(tec_bam *b, const uint16_t *bulk_ids, const uint16_t *sc_ids, int32_t n, int32_t n_index);
 int tec_bam_set_whitelist(tec_bam *b, const char *barcodes, const int64_t *offsets, int32_t n);
 int tec_bam_count(tec_bam *b, int mode, int qual, int64_t *n_records);
+/* One BYTE RANGE of the file, for several ranks that split one BAM (single end and single cell; pairs are formed by
+ * the global record parity and stay with one decoder).  Counts the records that START in the BGZF blocks whose first
+ * byte lies in [byte_lo, byte_hi) into the running count.  out[TEC_BAM_RANGE_WORDS] = {records counted, start_block,
+ * start_off, exit_block, exit_off, file size}: where this range's first record starts and where the chain stands
+ * behind its last record, each as {file offset of the BGZF block, offset in its inflated data}.  start_block -1: the
+ * range began at the BAM header (byte_lo == 0, exact); -2: no record starts in the range.  The first record of any other
+ * range is the block-parallel guess, so the CALLER must check exit(rank) == start(next rank with records) for every
+ * rank and exit(last) == {file size, 0}; if that fails, decode the file in one piece (te_count.py does both). */
+#define TEC_BAM_RANGE_WORDS 6
+int tec_bam_count_range(tec_bam *b, int mode, int qual, int64_t byte_lo, int64_t byte_hi, int64_t *out);
 /* what = 0 blocks inflated by zlib on the host, 1..4 microseconds in load / inflate / chain / parse */
 int64_t tec_bam_info(const tec_bam *b, int what);
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "tec_bam_set_chrom_map": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32]),
     "tec_bam_set_whitelist": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.c_int32]),
     "tec_bam_count": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _c_i64p]),
+    "tec_bam_count_range": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _c_i64p]),
     "tec_bam_info": (ctypes.c_int64, [_vp, ctypes.c_int]),
     "tec_sc_matrix_text": (ctypes.c_int, [_vp, ctypes.c_int64, _c_u32p, ctypes.c_char_p, _c_i64p, _c_i64p]),
     "tec_sc_matrix_read": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp]),
@@ -159,6 +160,18 @@ class DeviceBam:
         rc = self._lib.tec_bam_count(self._h, int(mode), int(qual), ctypes.byref(n))
         if rc == 0:
             return n.value
+        self._raise(rc, mode)
+
+    def count_range(self, mode, qual, byte_lo, byte_hi):
+        """The records that start in the BGZF blocks of [byte_lo, byte_hi) (include/tecount.h: tec_bam_count_range).
+        Returns {n, start, exit, size}: start / exit are (block file offset, offset in the inflated block)."""
+        out = (ctypes.c_int64 * 6)()
+        rc = self._lib.tec_bam_count_range(self._h, int(mode), int(qual), int(byte_lo), int(byte_hi), out)
+        if rc == 0:
+            return {"n": out[0], "start": (out[1], out[2]), "exit": (out[3], out[4]), "size": out[5]}
+        self._raise(rc, mode)
+
+    def _raise(self, rc, mode):
         msg = (self._lib.tec_last_error(self._eng._h) or b"").decode()
         if rc == ERR_UNSUPPORTED:
             raise BamUnsupported("%s: %s" % (self.filename, msg))

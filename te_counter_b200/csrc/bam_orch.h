@@ -9,6 +9,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -377,6 +378,215 @@ int decode_all(Reader& r, Backend& be, int mode, int qual, int window_blocks, in
     }
     if (carry_n && !(paired && carry_is_lone_mate)) return r.fail(E_FORMAT, "truncated BAM file (partial record at the end)");
     if (n_records_out) *n_records_out = total_records;
+    return OK;
+}
+
+
+// ---- one BYTE RANGE of the file (several ranks split one BAM; SURVEY.md 8e "reads shard ... across the GPUs") ----
+// Rank r decodes the records that START in the BGZF blocks whose first byte lies in [lo, hi).  Its first block is the
+// first block start at or after lo (found by scanning for a header that is followed by two more); its first record
+// is the block-parallel GUESS of that block (find_start) -- unless the range begins at the BAM header, where the start
+// is known.  The last record may end beyond hi: RANGE_TAIL_BLOCKS / RANGE_TAIL_BYTES further blocks are inflated so that it is
+// complete, and the position where the chain then stands (`exit`) is where the next rank's first record must start.
+// The caller compares every rank's exit with the next rank's start (both as {file offset of the block, offset inside
+// its inflated data}): by induction from rank 0, whose start is exact, equality everywhere means every rank decoded
+// exactly its share of the true record chain; any difference means a wrong guess and the caller must decode the file
+// in one piece instead.  Single-end and single-cell modes only (pairs are formed by global record parity).
+constexpr int RANGE_TAIL_BLOCKS = 16;               // blocks behind the range that are inflated for its last record:
+constexpr size_t RANGE_TAIL_BYTES = size_t(1) << 20;   // at least 16 of them and at least 1 MiB of inflated data
+struct RangeResult {
+    int64_t n_records = 0;
+    int64_t start_block = -1, start_off = 0;      // -1: the range starts at the BAM header (exact); -2: no record starts in the range
+    int64_t exit_block = -2, exit_off = 0;        // where the next record starts; block == file size: end of file
+};
+
+inline bool bgzf_chain_ok(const MappedFile& f, size_t p, int n) {
+    for (int i = 0; i < n && p < f.size; i++) {
+        const uint8_t* cdata; uint32_t clen, isize, crc;
+        const int64_t bs = bgzf_block_at(f, p, &cdata, &clen, &isize, &crc);
+        if (bs < 0) return false;
+        p += (size_t)bs;
+    }
+    return true;
+}
+
+template <class Backend>
+int decode_range(Reader& r, Backend& be, int mode, int qual, int window_blocks, uint64_t lo, uint64_t hi, RangeResult* res) {
+    if (!r.have_map) return r.fail(E_ARG, "the chromosome map has not been set");
+    if (mode == bgzfdev::MODE_PE) return r.fail(E_ARG, "byte ranges are for single-end and single-cell decoding (pairs follow the global record parity)");
+    if (!res || lo > hi) return r.fail(E_ARG, "bad byte range");
+    if (window_blocks < 1) window_blocks = 1;
+    *res = RangeResult();
+    const size_t fsize = r.file.size;
+    const size_t hi_eff = (size_t)std::min<uint64_t>(hi, fsize);
+    const bool from_header = lo == 0;           // rank 0: the chain starts behind the BAM header, exactly
+    size_t pos = r.pos;
+    int64_t carry_n = 0;
+    bool adopted = from_header;                 // the chain has a first record
+    if (from_header) {
+        carry_n = (int64_t)r.after_header.size();
+        res->start_block = -1;
+    } else {
+        pos = std::max((size_t)lo, r.pos);      // the header's own blocks belong to rank 0
+        while (pos + 18 <= fsize && !(r.file.map[pos] == 0x1f && r.file.map[pos + 1] == 0x8b && r.file.map[pos + 2] == 8 &&
+                                      (r.file.map[pos + 3] & 4) && bgzf_chain_ok(r.file, pos, 3)))
+            pos++;
+        if (pos + 18 > fsize) pos = fsize;
+        res->start_block = -2;
+    }
+    if (pos >= hi_eff && !from_header) {                        // no block starts in the range
+        res->exit_block = -2;
+        return OK;
+    }
+    std::vector<BlockDesc> blocks;
+    std::vector<const uint8_t*> src;
+    std::vector<size_t> foff;                   // file offset of every block of the window
+    std::vector<int32_t> status;
+    std::vector<BlockChain> chain;
+    std::vector<int64_t> base;
+    std::vector<uint8_t> tmp;
+    int rc = be.reserve(1, (size_t)carry_n + 1, 1);
+    if (rc) return r.fail(E_BACKEND, "backend: cannot allocate the window");
+    if (carry_n && be.put(0, r.after_header.data(), (size_t)carry_n)) return r.fail(E_BACKEND, "backend: copy failed");
+    int64_t total_records = 0;
+    bool final_window = false;
+    while (!final_window) {
+        blocks.clear(); src.clear(); foff.clear();
+        size_t total = 0;
+        const size_t file_lo = pos;
+        auto take = [&]() -> int {
+            const uint8_t* cdata; uint32_t clen, isize, crc;
+            const int64_t bs = bgzf_block_at(r.file, pos, &cdata, &clen, &isize, &crc);
+            if (bs < 0) return (int)bs;
+            const size_t at = pos;
+            pos += (size_t)bs;
+            if (!isize) return OK;
+            BlockDesc d;
+            d.in_off = (uint64_t)(cdata - r.file.map) - file_lo; d.in_len = clen; d.out_off = (uint64_t)carry_n + total; d.out_len = isize;
+            d.crc = crc; d.pad = 0;
+            blocks.push_back(d); src.push_back(cdata); foff.push_back(at);
+            total += isize;
+            return OK;
+        };
+        while (pos < hi_eff && (int)blocks.size() < window_blocks) {
+            const int t = take();
+            if (t) return r.fail(t, t == E_NOT_BGZF ? "gzip member without a BC field: not BGZF" : "bad or truncated BGZF block");
+        }
+        final_window = pos >= hi_eff;
+        const int n_main = (int)blocks.size();
+        const int64_t boundary = carry_n + (int64_t)total;       // window position of the first block that is not ours
+        if (final_window) {
+            const int want = n_main + RANGE_TAIL_BLOCKS;
+            const size_t main_bytes = total;
+            while (pos < fsize && ((int)blocks.size() < want || total - main_bytes < RANGE_TAIL_BYTES)) {
+                const int t = take();
+                if (t) return r.fail(t, "bad or truncated BGZF block");
+            }
+        }
+        const size_t next_file_pos = pos;                        // block behind the window (end of file: fsize)
+        const int nb = (int)blocks.size();
+        const int64_t w_end = carry_n + (int64_t)total;
+        if (!nb && !carry_n && !from_header) {                   // nothing left (only empty blocks were skipped)
+            if (adopted) { res->exit_block = (int64_t)next_file_pos; res->exit_off = 0; }
+            break;
+        }
+        if (nb) {
+            const size_t comp = pos - file_lo;
+            rc = be.reserve(comp + 16, (size_t)w_end + 64, nb + 1);
+            if (rc) return r.fail(E_BACKEND, "backend: cannot allocate the window");
+            if (be.load(r.file, file_lo, comp)) return r.fail(E_BACKEND, "backend: reading the compressed blocks failed");
+            status.assign((size_t)nb, 0);
+            if (be.inflate(blocks.data(), nb, status.data())) return r.fail(E_BACKEND, "backend: inflate pass failed");
+            for (int i = 0; i < nb; i++) {
+                if (status[(size_t)i] == bgzfdev::ST_OK) continue;
+                const BlockDesc& d = blocks[(size_t)i];
+                tmp.resize(d.out_len);
+                if (!zlib_block(src[(size_t)i], d.in_len, tmp.data(), d.out_len, d.crc))
+                    return r.fail(E_FORMAT, "corrupt BGZF block (inflate or CRC32 failed)");
+                if (be.put((int64_t)d.out_off, tmp.data(), d.out_len)) return r.fail(E_BACKEND, "backend: copy failed");
+            }
+        }
+        // Block 0 of the chain pass "starts at 0" (the carry).  An empty pseudo block in front keeps that true while the
+        // chain has no first record yet and lets every real block make its own guess.
+        BlockDesc pseudo;
+        pseudo.in_off = 0; pseudo.in_len = 0; pseudo.out_off = 0; pseudo.out_len = 0; pseudo.crc = 0; pseudo.pad = 0;
+        int shift = 0;
+        if (!adopted || !n_main) {
+            if (!n_main) pseudo.out_len = (uint32_t)carry_n;      // no block of ours in this window: only the carried bytes
+            blocks.insert(blocks.begin(), pseudo);
+            foff.insert(foff.begin(), 0);
+            shift = 1;
+        }
+        const int nc = (int)blocks.size();
+        chain.assign((size_t)nc, BlockChain());
+        if (be.chain(blocks.data(), nc, w_end, (int32_t)r.refs.size(), chain.data())) return r.fail(E_BACKEND, "backend: chain pass failed");
+        int64_t expect = 0, n_rec = 0;
+        bool stopped = false;
+        for (int b = 0; b < nc; b++) {
+            const int64_t lo_b = (int64_t)blocks[(size_t)b].out_off, hi_b = lo_b + blocks[(size_t)b].out_len;
+            BlockChain& c = chain[(size_t)b];
+            const bool ours = b - shift < n_main || (shift && b == 0);
+            if (!adopted) {                                      // the first block that shows a record start gives the chain its start
+                if (b == 0 || !ours || c.start == bgzfdev::NO_START) { c.count = 0; c.start = bgzfdev::NO_START; continue; }
+                adopted = true;
+                expect = c.start;
+                res->start_block = (int64_t)foff[(size_t)b];
+                res->start_off = c.start - lo_b;
+            }
+            if (stopped || expect >= hi_b || !ours) { c.count = 0; c.start = bgzfdev::NO_START; continue; }
+            if (expect + 36 > w_end) { stopped = true; c.count = 0; c.start = bgzfdev::NO_START; continue; }
+            if (c.start != expect) {
+                char buf[160];
+                snprintf(buf, sizeof buf, "record boundaries could not be established block-parallel (block %d of the window: guess %lld, chain %lld)",
+                         b, (long long)c.start, (long long)expect);
+                return r.fail(E_UNSUPPORTED, buf);
+            }
+            if (c.bad) return r.fail(E_FORMAT, "alignment record with impossible block_size");
+            n_rec += c.count;
+            expect = c.exit;
+            if (c.exit < hi_b) stopped = true;
+        }
+        if (!adopted) { carry_n = 0; continue; }                 // nothing starts in this window: its bytes belong to the rank before
+        base.assign((size_t)nc, 0);
+        int64_t acc = 0;
+        for (int b = 0; b < nc; b++) { base[(size_t)b] = acc; acc += chain[(size_t)b].count; }
+        if (n_rec) {
+            int err = 0;
+            int64_t err_rec = -1;
+            if (be.parse(blocks.data(), nc, chain.data(), base.data(), n_rec, w_end, mode, qual, r, &err, &err_rec))
+                return r.fail(E_BACKEND, "backend: parse pass failed");
+            if (err) {
+                char buf[96];
+                snprintf(buf, sizeof buf, "record %lld of the range", (long long)(total_records + err_rec));
+                return r.fail(E_RECORD - err, buf);
+            }
+            if (be.deliver(n_rec, mode)) return r.fail(E_BACKEND, "backend: delivering the batch failed");
+            total_records += n_rec;
+        }
+        if (final_window) {
+            if (expect < boundary) {
+                if (next_file_pos >= fsize && nb - n_main == 0) return r.fail(E_FORMAT, "truncated BAM file (partial record at the end)");
+                char buf[200];
+                snprintf(buf, sizeof buf, "the last record of the range does not end within the tail window (chain at %lld, range ends at %lld, window %lld, %d + %d blocks)",
+                         (long long)expect, (long long)boundary, (long long)w_end, n_main, nb - n_main);
+                return r.fail(E_UNSUPPORTED, buf);
+            }
+            // the chain stands at `expect`: in one of the tail blocks, or right behind the window
+            res->exit_block = (int64_t)next_file_pos;
+            res->exit_off = 0;
+            if (expect > w_end) return r.fail(E_FORMAT, "record chain runs past the window");
+            for (int b = shift + n_main; b < nc; b++) {
+                const int64_t lo_b = (int64_t)blocks[(size_t)b].out_off, hi_b = lo_b + blocks[(size_t)b].out_len;
+                if (expect >= lo_b && expect < hi_b) { res->exit_block = (int64_t)foff[(size_t)b]; res->exit_off = expect - lo_b; break; }
+            }
+            break;
+        }
+        const int64_t left = w_end - expect;
+        if (left && expect && be.carry(expect, left)) return r.fail(E_BACKEND, "backend: carry failed");
+        carry_n = left;
+    }
+    if (!adopted) { res->start_block = -2; res->exit_block = -2; }
+    res->n_records = total_records;
     return OK;
 }
 

@@ -727,6 +727,26 @@ extern "C" int tec_bam_count(tec_bam* b, int mode, int qual, int64_t* n_records)
     return bam_status(ctx, b->reader, rc, &b->be);
 }
 
+extern "C" int tec_bam_count_range(tec_bam* b, int mode, int qual, int64_t byte_lo, int64_t byte_hi, int64_t* out) {
+    if (!b) return TEC_ERR_ARG;
+    tec_ctx* ctx = b->ctx;
+    if (!out) TEC_FAIL(TEC_ERR_ARG, "tec_bam_count_range: out must hold TEC_BAM_RANGE_WORDS values");
+    for (int i = 0; i < TEC_BAM_RANGE_WORDS; i++) out[i] = 0;
+    if (mode != bgzfdev::MODE_SE && mode != bgzfdev::MODE_SC) TEC_FAIL(TEC_ERR_ARG, "tec_bam_count_range: mode must be 0 (single end) or 2 (single cell)");
+    if (byte_lo < 0 || byte_hi < byte_lo) TEC_FAIL(TEC_ERR_ARG, "tec_bam_count_range: bad byte range");
+    if (mode == bgzfdev::MODE_SC) {
+        if (!ctx->sc || !ctx->sc->active) TEC_FAIL(TEC_ERR_STATE, "tec_bam_count_range: tec_sc_begin not called");
+    } else if (!ctx->bulk_active || ctx->paired) {
+        TEC_FAIL(TEC_ERR_STATE, "tec_bam_count_range: tec_bulk_begin not called for single-end counting");
+    }
+    TEC_CUDA(cudaSetDevice(ctx->device));
+    bamorch::RangeResult r;
+    const int rc = bamorch::decode_range(b->reader, b->be, mode, qual, ctx->opt_bam_window_blocks, (uint64_t)byte_lo, (uint64_t)byte_hi, &r);
+    out[0] = r.n_records; out[1] = r.start_block; out[2] = r.start_off; out[3] = r.exit_block; out[4] = r.exit_off;
+    out[5] = (int64_t)b->reader.file.size;
+    return bam_status(ctx, b->reader, rc, &b->be);
+}
+
 extern "C" int64_t tec_bam_info(const tec_bam* b, int what) {
     if (!b) return 0;
     switch (what) {

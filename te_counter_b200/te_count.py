@@ -27,6 +27,7 @@ from . import _lib
 from . import fastbam as _fastbam
 from . import index as _index
 from . import reads as _reads
+from . import shard as _shard
 
 BATCH_RECORDS = 1 << 20
 SC_BUNDLE_KEYS = 10000000        # te_count.py:377  `len(umis) >= 1e7`
@@ -184,7 +185,27 @@ class measureTE:
         cm = _reads.ChromMap(self.genome.chrom_keys)
         label = 'reads' if paired else 'SE reads'
         more, done, next_log = True, 0, 1000000
-        if _device_decoder_wanted(eng):
+        # One file, several ranks (torch.distributed job, one process per GPU; shard.py): every rank decodes a byte range
+        # on its GPU and the counters are summed.  Paired-end files, and files whose ranges the decoders cannot tile,
+        # are decoded by rank 0 alone; the sum is the same.
+        rank, world = _shard.world_info()
+        in_library = _shard.join_collectives(eng) if world > 1 else False
+        if world > 1:
+            sharded = None
+            if not paired and _device_decoder_wanted(eng):
+                def open_and_bind():
+                    dev = eng.bam_open(filename)
+                    dev.bind(cm)
+                    return dev
+                eng.bulk_begin(paired, qual)
+                sharded = _shard.count_ranges(open_and_bind, 0, qual)
+            if sharded is not None:
+                done, more = sharded[1], False
+                log.info('{:,} of them decoded by this rank ({} of {})'.format(sharded[0], rank, world))
+            elif rank != 0:
+                eng.bulk_begin(paired, qual)                  # nothing to decode here: rank 0 reads the whole file
+                more = False
+        if more and _device_decoder_wanted(eng):
             try:                                              # BGZF inflate, record split and packing on the device
                 dev = eng.bam_open(filename)
                 try:
@@ -224,7 +245,12 @@ class measureTE:
                 next_log += 1000000
         if sam is not None:
             sam.close()
+        if world > 1 and in_library:
+            eng.bulk_allreduce()                              # NCCL, issued by the library on its stream
         counts, st = eng.bulk_finish()
+        if world > 1 and not in_library:
+            from . import dist as _tdist
+            counts, st = _tdist.allreduce_counts_host(counts, st)
         if st[_lib.BS_CRASH_NAME]:
             log.error('Unmatched pair!')
             raise AttributeError("module 'sys' has no attribute 'quit'")      # te_count.py:94
@@ -286,7 +312,25 @@ class measureTE:
         cm = _reads.ChromMap(self.genome.chrom_keys)
         log.info('Part 1: Collapsing UMI/CB combinations')
         more, done, next_log = True, 0, 10000000
-        if UMIS and _device_decoder_wanted(eng):
+        # One file, several ranks (shard.py): byte ranges decoded per GPU, survivors exchanged by cell, the job-wide steps
+        # of Parts 1-3 all-reduced; rank r's records precede rank r + 1's, so the job-wide record order is the file's.
+        rank, world = _shard.world_info()
+        in_library = _shard.join_collectives(eng) if world > 1 else False
+        if world > 1:
+            sharded = None
+            if UMIS and _device_decoder_wanted(eng):
+                def open_and_bind():
+                    dev = eng.bam_open(filename)
+                    dev.bind(cm, whitelist)
+                    return dev
+                eng.sc_begin(qual, strand, len(whitelist))
+                sharded = _shard.count_ranges(open_and_bind, 2, qual)
+            if sharded is not None:
+                done, more = sharded[1], False
+            elif rank != 0:
+                eng.sc_begin(qual, strand, len(whitelist))    # rank 0 reads the whole file; this rank only receives its cells
+                more = False
+        if more and UMIS and _device_decoder_wanted(eng):
             try:
                 dev = eng.bam_open(filename)
                 try:
@@ -327,8 +371,18 @@ class measureTE:
         if sam is not None:
             sam.close()
         log.info(f'Part 2: Get the best {maxcells} barcodes and remove dupes')
+        self._sc_device_matrix = True
+        if world > 1:
+            import torch
+            from . import dist as _tdist
+            _tdist.sc_exchange_by_cell(eng, torch.device('cuda', self.device))
         n_triples, n_hit = eng.sc_finalize(_bundle_keys, maxcells, _pad)
+        if world > 1 and in_library:
+            n_triples = eng.sc_allgather_triples()            # every rank holds the job's triples (on the device too)
         ensg, cell, count, hcell, hcount, st = eng.sc_fetch(n_triples, n_hit)
+        if world > 1 and not in_library:
+            ensg, cell, count = _tdist.sc_gather_triples(ensg, cell, count)
+            self._sc_device_matrix = False                    # the device holds this rank's cells only: rows are written by the host
         idx = int(st[_lib.SS_UNITS]) + 1
         valid = int(st[_lib.SS_VALID])
         log.info(f'  Observed {int(st[_lib.SS_RAW_BARCODES]):,} raw barcodes')
@@ -381,7 +435,7 @@ class measureTE:
 
         with open(out_filename, 'w') as oh:
             oh.write('{}\t{}\n'.format('name', '\t'.join(result.keys())))
-            if sel is not None and hasattr(self._engine_obj, 'sc_matrix_text'):
+            if sel is not None and hasattr(self._engine_obj, 'sc_matrix_text') and getattr(self, '_sc_device_matrix', True):
                 # the rows are formatted on the device (libtecount tec_sc_matrix_text) and streamed out
                 oh.flush()
                 n_bytes = self._engine_obj.sc_matrix_text(sel, barcodes_to_do)

@@ -157,6 +157,16 @@ int bgzfdev_decode(void* h, int mode, int qual, int window_blocks, int64_t* n_re
     return bamorch::decode_all(s->reader, s->be, mode, qual, window_blocks, n_records);
 }
 
+// one byte range of the file (bam_orch.h decode_range); out[6] = {n_records, start_block, start_off, exit_block, exit_off, file size}
+int bgzfdev_decode_range(void* h, int mode, int qual, int window_blocks, int64_t lo, int64_t hi, int64_t* out) {
+    Session* s = (Session*)h;
+    bamorch::RangeResult r;
+    const int rc = bamorch::decode_range(s->reader, s->be, mode, qual, window_blocks, (uint64_t)lo, (uint64_t)hi, &r);
+    out[0] = r.n_records; out[1] = r.start_block; out[2] = r.start_off; out[3] = r.exit_block; out[4] = r.exit_off;
+    out[5] = (int64_t)s->reader.file.size;
+    return rc;
+}
+
 // copies the delivered columns out (cell / umi only for single cell)
 void bgzfdev_fetch(void* h, int32_t* start, int32_t* end, uint16_t* chrom, uint8_t* mapq, uint8_t* flag, uint32_t* cell, uint64_t* umi) {
     HostBackend& b = ((Session*)h)->be;
