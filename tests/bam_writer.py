@@ -6,11 +6,18 @@ import struct
 import zlib
 
 
-def _bgzf_block(data):
-    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+# the 28-byte end-of-file marker of SAMv1 section 4.1.2, as htslib / bgzip write it (an empty block, fixed Huffman code)
+BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def _bgzf_block(data, level=6, extra=b""):
+    """One BGZF block.  level 0 gives stored DEFLATE blocks (samtools -u / bgzip -l 0); `extra` = further gzip extra
+    subfields placed in front of BC (the format allows them; readers must skip what they do not know)."""
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
     comp = co.compress(data) + co.flush()
-    bsize = len(comp) + 25
-    head = struct.pack("<BBBBIBBHBBHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, ord("B"), ord("C"), 2, bsize)
+    xlen = 6 + len(extra)
+    bsize = len(comp) + 19 + xlen
+    head = struct.pack("<BBBBIBBH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, xlen) + extra + struct.pack("<BBHH", ord("B"), ord("C"), 2, bsize)
     return head + comp + struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data))
 
 
@@ -28,6 +35,8 @@ def _cigar_for(rec):
 
 
 def _aux(rec):
+    if rec.get("aux") is not None:                       # raw optional fields, as given
+        return rec["aux"]
     out = b""
     for t in ("CB", "CR", "UB", "UR"):
         if rec.get(t) is not None:
@@ -36,29 +45,35 @@ def _aux(rec):
     return out
 
 
-def write_bam(path, records, block=3000):
-    chroms = []
+def write_bam(path, records, block=3000, level=6, extra=b"", eof_every=0, chroms=None, header_text=None, eof=None):
+    """eof_every: an empty block after every n-th block (files glued together with `cat` carry them); chroms: the @SQ
+    order (default: first appearance); eof: the bytes of the final marker (default: an empty block from zlib)."""
+    chroms = list(chroms) if chroms is not None else []
     for r in records:
         if r["chrom"] is not None and r["chrom"] not in chroms:
             chroms.append(r["chrom"])
-    text = "@HD\tVN:1.6\tSO:unsorted\n" + "".join("@SQ\tSN:%s\tLN:300000000\n" % c for c in chroms)
+    text = header_text if header_text is not None else \
+        "@HD\tVN:1.6\tSO:unsorted\n" + "".join("@SQ\tSN:%s\tLN:300000000\n" % c for c in chroms)
     raw = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(chroms))
     for c in chroms:
         raw += struct.pack("<i", len(c) + 1) + c.encode() + b"\0" + struct.pack("<i", 300000000)
     for i, r in enumerate(records):
         name = r.get("name", "r%d" % i).encode() + b"\0"
         cig = _cigar_for(r)
-        l_seq = sum(n for n, op in cig if op in (0, 1, 4))
+        l_seq = r["l_seq"] if r.get("l_seq") is not None else sum(n for n, op in cig if op in (0, 1, 4, 7, 8))
         ref_id = chroms.index(r["chrom"]) if r["chrom"] is not None else -1
+        next_id = chroms.index(r["next_chrom"]) if r.get("next_chrom") is not None else -1
         body = struct.pack("<iiBBHHHiiii", ref_id, r["start"], len(name), r.get("mapq", 60), 4680, len(cig),
-                           r.get("flag", 0), l_seq, -1, -1, 0)
+                           r.get("flag", 0), l_seq, next_id, r.get("next_pos", -1), r.get("tlen", 0))
         body += name + b"".join(struct.pack("<I", n << 4 | op) for n, op in cig)
         body += b"\x11" * ((l_seq + 1) // 2) + b"\xff" * l_seq + _aux(r)
         raw += struct.pack("<i", len(body)) + body
     with open(path, "wb") as fh:
-        for o in range(0, len(raw), block):                  # many small blocks: records straddle them
-            fh.write(_bgzf_block(raw[o:o + block]))
-        fh.write(_bgzf_block(b""))                           # EOF marker
+        for k, o in enumerate(range(0, len(raw), block)):    # many small blocks: records straddle them
+            fh.write(_bgzf_block(raw[o:o + block], level, extra))
+            if eof_every and (k + 1) % eof_every == 0:
+                fh.write(BGZF_EOF)
+        fh.write(_bgzf_block(b"") if eof is None else eof)   # EOF marker
 
 
 def write_sam(path, records):

@@ -172,3 +172,26 @@ def test_device_decoder_errors(engine, tmp_path):
     sam.write_text("@HD\tVN:1.6\n")
     with pytest.raises(_lib.BamUnsupported):
         engine.bam_open(str(sam))
+
+
+@pytest.mark.parametrize("name", ["htslib_eof_marker", "empty_blocks_inside", "stored_blocks", "tiny_fixed_huffman_blocks", "extra_subfields",
+                                  "sq_order_and_comments"])
+def test_htslib_shaped_files_on_the_device(engine, tmp_path, name):
+    """The files of tests/test_bam_htslib_shapes.py (end-of-file marker, empty blocks inside, stored / fixed-Huffman blocks,
+    extra gzip subfields, every optional-field type, CG placeholder CIGARs ...) through the kernels: counts and statistics
+    equal those from the hand-computed columns pushed directly."""
+    from oracle import te_oracle
+    from test_bam_htslib_shapes import expected, write_variant
+    path = str(tmp_path / (name + ".bam"))
+    recs = write_variant(path, name)
+    idx = H.load_index("idx_rand_a.glb")
+    engine.upload_index(idx)
+    want = expected(recs, idx)
+    n, info, got = _device_run(engine, path, "se", idx, None, 20)
+    assert n == len(recs)
+    engine.bulk_begin(False, 20)
+    engine.bulk_push(len(recs), want["start"], want["end"], want["chrom"], want["mapq"], want["flag"])
+    counts, st = engine.bulk_finish()
+    assert np.array_equal(got[0], counts) and np.array_equal(got[1], st)
+    oc, _ = te_oracle.bulk_count(H.oracle_index(idx), False, 20, *[want[k].tolist() for k in ("start", "end", "chrom", "mapq", "flag")])
+    assert counts.tolist() == oc and sum(oc) > 0
