@@ -12,8 +12,10 @@
  *
  * Conventions as in tecount.h: plain C ABI, status return (0 / negative tbam_status), the caller
  * owns every buffer it passes, one reader per file, not thread-safe (the reader's own worker
- * threads are internal).  reference_end comes from the CIGAR field of the record: alignments of more than
- * 65535 operations, which BAM moves to a CG tag, are not expanded.  The host-side meaning of every field is the one of
+ * threads are internal).  reference_end comes from the CIGAR field of the record.  Alignments of more than
+ * 65535 operations, which BAM stores as the placeholder <l_seq>S<ref_len>N plus a CG:B,I tag (SAMv1 4.2.2), need no
+ * expansion for that: the placeholder's N operation carries the reference length (tests/test_bam_htslib_shapes.py).
+ * The host-side meaning of every field is the one of
  * te_counter_b200/reads.py (the Python packing this library replaces) and is cited per entry point.
  */
 #ifndef TECBAM_H

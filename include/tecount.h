@@ -263,8 +263,9 @@ int tec_sc_matrix_read(tec_ctx *ctx, int64_t offset, int64_t n, char *out);
  * mode: 0 single end, 1 paired end, 2 single cell.  On TEC_ERR_UNSUPPORTED start over with libtecbam.
  * Options (tec_set_option): "bam_window_blocks" (BGZF blocks per pass, default 65536: 4.3 GB of inflated bytes
  * in HBM), "bam_lanes" (blocks decoded per warp, default 1).  Limits shared with libtecbam: reference_end comes
- * from the CIGAR field of the record (alignments of more than 65535 operations, which BAM moves to a CG tag, are
- * not expanded); tag values are compared as bytes. */
+ * from the CIGAR field of the record (for alignments of more than 65535 operations that field is the placeholder
+ * <l_seq>S<ref_len>N of SAMv1 4.2.2, whose N operation carries the reference length: no expansion of the CG tag is
+ * needed); tag values are compared as bytes. */
 typedef struct tec_bam tec_bam;
 int tec_bam_open(tec_ctx *ctx, const char *path, tec_bam **out);
 void tec_bam_close(tec_bam *b);
