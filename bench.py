@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=600_000, help="records of the CPU-baseline sample")
     ap.add_argument("--ref-sample", type=int, default=300_000, help="reference arm: records per step")
     ap.add_argument("--sorted", action="store_true", help="coordinate-sorted arrival order (bulk_se)")
-    ap.add_argument("--sc-parity-records", type=int, default=20_000_000,
+    ap.add_argument("--sc-parity-records", type=int, default=30_000_000,
                     help="sc: records of the large parity check against the C++ oracle (0 = skip)")
     ap.add_argument("--sc-e2e-records", type=int, default=250_000_000, help="sc: records of the host-buffer leg")
     ap.add_argument("--file-records", type=int, default=8_000_000,
@@ -725,7 +725,11 @@ def sc_leg(C, headline):
     if not no_cpu and rank == 0 and args.sc_parity_records > 0:
         from oracle import te_oracle_c
         nb = min(n_rec, args.sc_parity_records)
-        big = [t[:nb].cpu().numpy() for t in cols]
+        # a whole-genome file of its own (a prefix of the timed, coordinate-sorted workload would cover one corner of the
+        # genome and too few distinct keys for a second bundle)
+        rp = synth.synth_sc_reads(synth.SEED + 1, idx, nb, n_whitelist=n_wl, device=dev, as_numpy=False)
+        big = [rp[k].cpu().numpy() for k in names]
+        del rp
         big[2] = big[2].view(np.uint16)
         big[5] = big[5].view(np.uint32)
         big[6] = big[6].view(np.uint64)

@@ -86,10 +86,28 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c
 _lib = None
 
 
+def _point_at_bundled_nccl():
+    """TEC_NCCL_LIB = the libnccl.so.2 PyTorch ships (nvidia/nccl/lib), unless the caller set one: the library binds
+    NCCL at run time, and a process that imports torch afterwards must find the copy torch was linked against."""
+    if os.environ.get("TEC_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else ()):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["TEC_NCCL_LIB"] = cand
+                return
+    except (ImportError, ValueError):
+        pass
+
+
 def load_library():
     """dlopen libtecount.so and attach the prototypes.  Raises ImportError when it is not built."""
     global _lib
     if _lib is None:
+        _point_at_bundled_nccl()
         if not os.path.exists(LIB_PATH):
             raise ImportError("libtecount.so is not built (%s); run `python -m te_counter_b200.build` "
                               "-- there is no CPU fallback" % LIB_PATH)

@@ -30,10 +30,16 @@ struct NcclApi {
 
     bool load() {
         if (handle) return true;
+        // TEC_NCCL_LIB (a path) first, then the copy this process already mapped (PyTorch's), then the search path.  The
+        // order matters in a process that imports torch later: the loader reuses a mapped libnccl.so.2 by name, and
+        // an older system copy would leave libtorch_cuda.so with unresolved symbols.
+        const char* env = getenv("TEC_NCCL_LIB");
+        if (env && *env) handle = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+        if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char* n : names) {
-            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
             if (handle) break;
+            handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
         }
         if (!handle) { why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : ""); return false; }
 #define TEC_NCCL_SYM(field, name) \
