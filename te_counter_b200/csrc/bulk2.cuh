@@ -472,8 +472,35 @@ __device__ __forceinline__ u32 b2_sector_hits(const Sector& s, const PointK a, c
 
 #define B2_QCAP2 512u             // per warp: at most B2_MAXD x 32 entries are added between two drains
 
+// The probes of a deferred entry: one sector chain holding both points, or one chain per point.  prim = primary sector,
+// pts = ra | rb << 16 (S2_R_NONE = no point).  A unit with a name mismatch has no probe (the reference dies there).
 template <bool PAIRED>
-__global__ void __launch_bounds__(256, 6)
+__device__ __forceinline__ int b2_probes(const uint4 rec, const Stab2View& sv, int shift, int cmask, u32 lim, u32 n_chrom, u32 (&prim)[2], u32 (&pts)[2]) {
+    if (!(rec.y & B2_DEF_GATHER)) { prim[0] = rec.y; pts[0] = rec.z; return 1; }
+    if (rec.y & B2_DEF_NAME) return 0;                       // (set for paired-end units only)
+    const u32 c = rec.y & 0xFFFFu;
+    const int loc1 = (int)rec.z, loc2 = (int)rec.w;
+    const uint2 cell = __ldg(sv.cells + min(c, n_chrom));
+    const int xa = loc1, xb = loc2 - 1;
+    const int mn = min(xa, xb), k = mn >> shift, base = mn & ~cmask;
+    const u32 rm = (u32)(max(xa, xb) - base);
+    if ((u32)k < cell.y && rm < lim) {
+        prim[0] = cell.x + (u32)k;
+        pts[0] = (u32)(xa - base) | ((u32)(xb - base) << 16);
+        return 1;
+    }
+    int np = 0;
+    if (xa >= 0 && (u32)(xa >> shift) < cell.y) { prim[np] = cell.x + (u32)(xa >> shift); pts[np] = (u32)(xa & cmask) | (S2_R_NONE << 16); ++np; }
+    if (xb >= 0 && (u32)(xb >> shift) < cell.y) { prim[np] = cell.x + (u32)(xb >> shift); pts[np] = S2_R_NONE | ((u32)(xb & cmask) << 16); ++np; }
+    return np;
+}
+
+// PF 0: every load of a chain waits for the one before it.  PF 1: the entry of the next turn is already in registers and its
+// primary sectors and overflow links are requested into L2 while this turn's chains are walked (the pass is bound by the
+// latency of dependent random loads, not by bandwidth).  PF 2: the overflow links of the next turn are read as well and
+// their sectors requested at the end of the turn.
+template <bool PAIRED, int PF>
+__global__ void __launch_bounds__(256, PF ? 5 : 6)
 bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ stats,
                     const uint4* __restrict__ defer_list, const u32* __restrict__ defer_count, u32 seg_cap, u32 n_seg, u32 parts,
                     u32* __restrict__ slow_list, u32 sv_n_chrom) {
@@ -505,44 +532,46 @@ bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ st
         }
         __syncwarp();
     };
+    const uint4 none = make_uint4(0u, B2_DEF_GATHER | B2_DEF_NAME, 0u, 0u);   // an entry without probes
     for (u32 w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_w; w += gridDim.x * (blockDim.x >> 5)) {
         const u32 seg = w % n_seg, part = w / n_seg;
         const u32 cnt = __ldg(defer_count + seg);
         const uint4* const list = defer_list + (size_t)seg * seg_cap;
-        for (u32 i0 = part * 32; i0 < cnt; i0 += parts * 32) {
+        const u32 step = parts * 32;
+        uint4 r1 = none, r2 = none;                               // PF: entries of this turn and of the next one
+        if (PF) {
+            if (part * 32 + lane < cnt) r1 = __ldg(list + part * 32 + lane);
+            if (part * 32 + step + lane < cnt) r2 = __ldg(list + part * 32 + step + lane);
+        }
+        for (u32 i0 = part * 32; i0 < cnt; i0 += step) {
             const bool live = i0 + lane < cnt;
             bool exact = false;
             u32 u = 0, nd = 0;
             u32 dist[B2_MAXD];
 #pragma unroll
             for (int i = 0; i < B2_MAXD; ++i) dist[i] = 0xFFFFFFFFu;
-            if (live) {
-                const uint4 rec = __ldg(list + i0 + lane);
-                u = rec.x;
-                // probes: one sector chain holding both points, or one chain per point
-                u32 prim[2], pts[2];                                       // pts = ra | rb << 16 (S2_R_NONE = none)
-                int np = 0;
-                if (!(rec.y & B2_DEF_GATHER)) {
-                    prim[0] = rec.y; pts[0] = rec.z; np = 1;
-                } else {
-                    const u32 c = rec.y & 0xFFFFu;
-                    const int loc1 = (int)rec.z, loc2 = (int)rec.w;
-                    const bool name_crash = PAIRED && (rec.y & B2_DEF_NAME);
-                    if (name_crash) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);            // :92-94
-                    // (a unit with a name mismatch may sit on a chromosome without cells: zero cells, no probe)
-                    const uint2 cell = name_crash ? make_uint2(0u, 0u) : __ldg(sv.cells + min(c, sv_n_chrom));
-                    const int xa = loc1, xb = loc2 - 1;
-                    const int mn = min(xa, xb), k = mn >> shift, base = mn & ~cmask;
-                    const u32 rm = (u32)(max(xa, xb) - base);
-                    if ((u32)k < cell.y && rm < lim) {
-                        prim[0] = cell.x + (u32)k;
-                        pts[0] = (u32)(xa - base) | ((u32)(xb - base) << 16);
-                        np = 1;
-                    } else {
-                        if (xa >= 0 && (u32)(xa >> shift) < cell.y) { prim[np] = cell.x + (u32)(xa >> shift); pts[np] = (u32)(xa & cmask) | (S2_R_NONE << 16); ++np; }
-                        if (xb >= 0 && (u32)(xb >> shift) < cell.y) { prim[np] = cell.x + (u32)(xb >> shift); pts[np] = S2_R_NONE | ((u32)(xb & cmask) << 16); ++np; }
-                    }
+            uint4 rec = none, r3 = none;
+            u32 o2[2] = {0u, 0u};
+            int np2 = 0;
+            if (PF) {
+                rec = r1;
+                // the turn after the next: its entry is requested now, used two turns from here
+                if (i0 + 2 * step + lane < cnt) r3 = __ldg(list + i0 + 2 * step + lane);
+                u32 prim2[2], pts2[2];
+                np2 = b2_probes<PAIRED>(r2, sv, shift, cmask, lim, sv_n_chrom, prim2, pts2);
+                for (int p = 0; p < np2; ++p) {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(sv.sectors + (size_t)prim2[p] * 8));
+                    if (PF == 2) o2[p] = __ldg(sv.ovf_first + prim2[p]);
+                    else asm volatile("prefetch.global.L2 [%0];" :: "l"(sv.ovf_first + prim2[p]));
                 }
+            } else if (live) {
+                rec = __ldg(list + i0 + lane);
+            }
+            if (live) {
+                u = rec.x;
+                u32 prim[2], pts[2];
+                if (PAIRED && (rec.y & B2_DEF_GATHER) && (rec.y & B2_DEF_NAME)) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);   // :92-94
+                const int np = b2_probes<PAIRED>(rec, sv, shift, cmask, lim, sv_n_chrom, prim, pts);
                 for (int p = 0; p < np; ++p) {
                     const u32 ra = pts[p] & 0xFFFFu, rb = pts[p] >> 16;
                     const PointK pa = make_point(ra), pb = make_point(rb);
@@ -589,6 +618,12 @@ bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ st
                         }
                     }
                 }
+            }
+            if (PF) {
+                if (PF == 2)
+                    for (int p = 0; p < np2; ++p) asm volatile("prefetch.global.L2 [%0];" :: "l"(sv.sectors + (size_t)o2[p] * 8));
+                r1 = r2;
+                r2 = r3;
             }
             // the warp is converged here: the ensg to count go through the queue
 #pragma unroll

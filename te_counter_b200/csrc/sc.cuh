@@ -323,19 +323,50 @@ __global__ void sc_keyhead_kernel(int64_t n, const u32* __restrict__ perm, const
     }
 }
 
-// bundle boundary search: flags of "first occurrence of its key at or after bundle start s"
-__global__ void sc_newkey_kernel(int64_t len, int64_t pos, int64_t s, const u32* __restrict__ prev, u32* __restrict__ f) {
-    SC_LOOP(k, len) {
-        const u32 p = prev[pos + k];
-        f[k] = (p == SC_NONE || (int64_t)p < s) ? 1u : 0u;
+// One-GPU bundle boundary search without the flag array: first occurrences per chunk of SC_BCHUNK survivors (one CTA
+// per chunk), prefix sum of the few thousand chunk counts on the host, then the exact survivor inside the one chunk
+// where the running count reaches bundle_keys.  Reads prev[] once (4 B per survivor) instead of flag + scan + search.
+#define SC_BCHUNK 4096
+__global__ void __launch_bounds__(256) sc_newkey_count_kernel(int64_t len, int64_t pos, int64_t s, const u32* __restrict__ prev, u32* __restrict__ cnt) {
+    __shared__ u32 s_w[8];
+    for (int64_t c = blockIdx.x; c * SC_BCHUNK < len; c += gridDim.x) {
+        const int64_t k0 = c * SC_BCHUNK, k1 = min(len, k0 + SC_BCHUNK);
+        u32 n = 0;
+        for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) {
+            const u32 p = prev[pos + k];
+            n += (p == SC_NONE || (int64_t)p < s) ? 1u : 0u;
+        }
+        n = (u32)warp_sum((u64)n);
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = n;
+        __syncthreads();
+        if (threadIdx.x == 0) cnt[c] = s_w[0] + s_w[1] + s_w[2] + s_w[3] + s_w[4] + s_w[5] + s_w[6] + s_w[7];
+        __syncthreads();
     }
 }
-// index k with inclusive-scan value == want at a flagged element (exactly one)
-__global__ void sc_find_kernel(int64_t len, int64_t pos, int64_t s, const u32* __restrict__ prev, const u32* __restrict__ incl,
-                               u32 want, u32* __restrict__ out) {
-    SC_LOOP(k, len) {
-        const u32 p = prev[pos + k];
-        if (incl[k] == want && (p == SC_NONE || (int64_t)p < s)) *out = (u32)k;
+// the k in [0, len) (len <= SC_BCHUNK) whose element is the want-th first occurrence (want >= 1); one CTA of 256 threads,
+// 16 consecutive elements per thread
+__global__ void __launch_bounds__(256) sc_newkey_pick_kernel(int64_t len, int64_t pos, int64_t s, const u32* __restrict__ prev, u32 want, u32* __restrict__ out) {
+    __shared__ u32 s_n[256];
+    const int64_t k0 = (int64_t)threadIdx.x * (SC_BCHUNK / 256);
+    u32 bits = 0, n = 0;
+    for (int j = 0; j < SC_BCHUNK / 256; ++j) {
+        if (k0 + j < len) {
+            const u32 p = prev[pos + k0 + j];
+            if (p == SC_NONE || (int64_t)p < s) { bits |= 1u << j; ++n; }
+        }
+    }
+    s_n[threadIdx.x] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 acc = 0;
+        for (int t = 0; t < 256; ++t) { const u32 x = s_n[t]; s_n[t] = acc; acc += x; }
+    }
+    __syncthreads();
+    const u32 before = s_n[threadIdx.x];
+    if (want > before && want <= before + n) {
+        u32 need = want - before;
+        for (int j = 0; j < SC_BCHUNK / 256; ++j)
+            if ((bits >> j) & 1u) { if (--need == 0) { *out = (u32)(k0 + j); break; } }
     }
 }
 
@@ -1348,35 +1379,44 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
             if (rc) return rc;
             if (g_end >= (int64_t)0xFFFFFFF0) TEC_FAIL(TEC_ERR_LIMIT, "single-cell path: more than 2^32 surviving records in the job");
         } else {
-            const int64_t WIN = std::max<int64_t>(int64_t(1) << 22, std::min<int64_t>(4 * bundle_keys, int64_t(1) << 28));
+            // windows of about the length of the bundle before (the first one: 4 x bundle_keys survivors)
+            const int64_t WIN0 = std::max<int64_t>(int64_t(1) << 22, std::min<int64_t>(4 * bundle_keys, int64_t(1) << 28));
+            const int64_t WMAX = int64_t(1) << 28;
             u32 *f = nullptr, *found = nullptr;
-            TEC_CUDA(A.get(&f, (size_t)std::min(WIN, N)));
+            TEC_CUDA(A.get(&f, (size_t)(WMAX / SC_BCHUNK + 1)));
             TEC_CUDA(A.get(&found, 1));
-            int64_t st = 0;
+            std::vector<u32> h_cnt;
+            int64_t st = 0, last_len = 0;
             while (st < N) {
                 bstart.push_back(st);
                 int64_t acc = 0, pos = st, next = N;
                 while (pos < N) {
-                    const int64_t len = std::min(WIN, N - pos);
-                    sc_newkey_kernel<<<SC_GRID(len)>>>(len, pos, st, prev, f);
+                    const int64_t want_len = last_len ? last_len + last_len / 4 + SC_BCHUNK : WIN0;
+                    const int64_t len = std::min(std::min(want_len, WMAX), N - pos);
+                    const int64_t n_chunks = (len + SC_BCHUNK - 1) / SC_BCHUNK;
+                    sc_newkey_count_kernel<<<(int)std::min<int64_t>(n_chunks, (int64_t)ctx->n_sm * 8), 256, 0, ctx->stream>>>(len, pos, st, prev, f);
                     ctx->launches++;
-                    rc = sc_incl_scan(ctx, f, len, SumU32());
-                    if (rc) return rc;
-                    u32 tot = 0;
-                    TEC_CUDA(cudaMemcpyAsync(&tot, f + len - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                    h_cnt.resize((size_t)n_chunks);
+                    TEC_CUDA(cudaMemcpyAsync(h_cnt.data(), f, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, ctx->stream));
                     TEC_CUDA(cudaStreamSynchronize(ctx->stream));
-                    if (acc + tot >= bundle_keys) {
-                        sc_find_kernel<<<SC_GRID(len)>>>(len, pos, st, prev, f, (u32)(bundle_keys - acc), found);
+                    int64_t c = 0;
+                    for (; c < n_chunks; ++c) {
+                        if (acc + h_cnt[(size_t)c] >= bundle_keys) break;
+                        acc += h_cnt[(size_t)c];
+                    }
+                    if (c < n_chunks) {
+                        const int64_t cpos = pos + c * SC_BCHUNK, clen = std::min<int64_t>(SC_BCHUNK, pos + len - cpos);
+                        sc_newkey_pick_kernel<<<1, 256, 0, ctx->stream>>>(clen, cpos, st, prev, (u32)(bundle_keys - acc), found);
                         ctx->launches++;
                         u32 k = 0;
                         TEC_CUDA(cudaMemcpyAsync(&k, found, 4, cudaMemcpyDeviceToHost, ctx->stream));
                         TEC_CUDA(cudaStreamSynchronize(ctx->stream));
-                        next = pos + k + 1;
+                        next = cpos + k + 1;
                         break;
                     }
-                    acc += tot;
                     pos += len;
                 }
+                last_len = next - st;
                 st = next;
             }
             A.release(f);
