@@ -124,8 +124,8 @@ int tec_trim(tec_ctx* ctx);
  * tec_index_upload --, 2 two-pass kernels), "stab_shift" (log2 of the cell size, 8..11, or 0 = default: 10 for
  * bulk, 11 for the single-cell pair table; used by the next tec_index_upload), "bulk_mode" (bit 0 table sectors
  * evict_last in L2, bit 1 sector prefetch, bit 2 tally through the per-warp hit queue, bit 3 deep pipeline),
- * "second_mode" (second bulk pass: 0 dependent loads, 1 the next turn's primary sectors requested ahead, 2 its
- * overflow sectors as well), "second_parts" (warps per segment of the deferred list, 0 = by mode), "ctas_per_sm",
+ * "second_mode" (second bulk pass: the register set of a unit's distinct ensg, 0 stored by position, 1 shifted
+ * in), "second_parts" (warps per segment of the deferred list), "ctas_per_sm",
  * "all_hot" (counters of every ensg in shared memory when they fit), "sc_algo" (-1 auto, 0 exact search in
  * Part 3, 1 cell table), "sc_pack_umi" (2-bit UMI sort keys when possible).
  * tec_get_info: "has_stab", "stab_bytes", "has_sc_stab", "sc_stab_bytes", "n_sm", "n_features",

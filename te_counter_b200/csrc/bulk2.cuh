@@ -144,13 +144,14 @@ struct B2Const {
     u64 pol_table;                // L2 policy of the table loads (evict_last when mode & B2_MODE_KEEP)
     u32 q_addr;                   // shared-memory address of the warp's hit queue (B2_QCAP 16-bit entries)
 };
-#define B2_QCAP 256u              // per warp; a unit adds at most 5 x 32 entries between two drains
+#define B2_QCAP 512u              // per warp; a tile adds at most 10 x 32 entries between two drains (31 may be pending)
 #define B2_DEF_GATHER 0x80000000u
 #define B2_DEF_NAME 0x40000000u
 #define B2_MODE_KEEP 1u           // table sectors: L2 evict_last (the records stream through with evict_first)
 #define B2_MODE_PREFETCH 2u       // request the next tile's sectors into L2 one turn ahead
 #define B2_MODE_QUEUE 4u          // tally through the per-warp hit queue instead of one reduction per entry
 #define B2_MODE_DEEP 8u           // 512-thread CTAs with 128 registers per thread: three tiles in flight per warp
+#define B2_MODE_SCAN 16u          // hit queue filled once per tile (both units of a lane): one warp prefix sum instead of ten ballots
 
 __device__ __forceinline__ Sector ld_sector_pol(const u32* sectors, u32 idx, u64 pol) {
     Sector r;
@@ -251,15 +252,74 @@ __device__ __forceinline__ void b2_q_drain(const B2Const& k, B2Thread& t, u64* _
     __syncwarp();
 }
 
+// Scan variant of the hit queue (B2_MODE_SCAN): the queue is linear (head = 0 after every drain, the < 32 pending entries
+// are moved to its front), a lane's hits of BOTH units of the tile are placed behind one warp prefix sum.
+// y: hit bits of unit 0 at 15, 31, 14, 30, 13 (entries 0..4), of unit 1 three bits lower.
+__device__ __forceinline__ void b2_q_put(u32& addr, bool hit, u32 slot) {
+    if (hit) {
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)slot) : "memory");
+        addr += 2u;
+    }
+}
+template <bool ALLHOT>
+__device__ __forceinline__ void b2_q_drain_linear(const B2Const& k, B2Thread& t, u64* __restrict__ counts, int lane, bool all) {
+    __syncwarp();
+    const u32 n = t.q_tail;
+    u32 g = 0;
+    while (n - g >= (all ? 1u : 32u)) {
+        unsigned short sl = 0;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sl) : "r"(k.q_addr + (g + (u32)lane) * 2u) : "memory");
+        const u32 slot = sl;
+        if ((u32)lane < n - g) {
+            if (ALLHOT || slot < k.n_hot) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(k.hot_addr + slot * 4u), "r"(k.one) : "memory");
+            else atomicAdd(counts + slot, 1ULL);
+        }
+        g += min(32u, n - g);
+    }
+    if (g) {                                                  // pending entries to the front
+        unsigned short sl = 0;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sl) : "r"(k.q_addr + (g + (u32)lane) * 2u) : "memory");
+        __syncwarp();
+        if ((u32)lane < n - g) asm volatile("st.shared.u16 [%0], %1;" :: "r"(k.q_addr + (u32)lane * 2u), "h"(sl) : "memory");
+        t.q_tail = n - g;
+    }
+    __syncwarp();
+}
+template <bool ALLHOT>
+__device__ __forceinline__ void b2_q_push_tile(const u32 y, const Sector (&s)[B2_UPT], const B2Const& k, B2Thread& t, u64* __restrict__ counts, int lane) {
+    const u32 cnt = __popc(y);
+    u32 incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    u32 addr = k.q_addr + (t.q_tail + incl - cnt) * 2u;
+    b2_q_put(addr, y & (1u << 15), s[0].w[6]);
+    b2_q_put(addr, y & (1u << 31), s[0].w[6] >> 16);
+    b2_q_put(addr, y & (1u << 14), s[0].w[7]);
+    b2_q_put(addr, y & (1u << 30), s[0].w[7] >> 16);
+    b2_q_put(addr, y & (1u << 13), s[0].w[5] >> 16);
+    b2_q_put(addr, y & (1u << 12), s[1].w[6]);
+    b2_q_put(addr, y & (1u << 28), s[1].w[6] >> 16);
+    b2_q_put(addr, y & (1u << 11), s[1].w[7]);
+    b2_q_put(addr, y & (1u << 27), s[1].w[7] >> 16);
+    b2_q_put(addr, y & (1u << 10), s[1].w[5] >> 16);
+    t.q_tail += total;
+    b2_q_drain_linear<ALLHOT>(k, t, counts, lane, false);
+}
+
 // Phase B: the sector test, the tally and the deferred list.
 __device__ __forceinline__ void b2_load_sectors(Sector (&s)[B2_UPT], const B2Stage& st, const Stab2View& sv, const B2Const& k) {
 #pragma unroll
     for (int j = 0; j < B2_UPT; ++j) s[j] = ld_sector_pol(sv.sectors, st.sec[j], k.pol_table);
 }
 
-template <bool ALLHOT, bool QUEUE>
+template <bool ALLHOT, int QUEUE>
 __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const Sector (&s)[B2_UPT], const u32 u0, const Stab2View& sv, const B2Const& k,
                                            B2Thread& t, u64* __restrict__ counts, u64* __restrict__ stats) {
+    u32 y = 0;                                                // QUEUE == 2: the hit bits of both units
 #pragma unroll
     for (int j = 0; j < B2_UPT; ++j) {
         const bool ok = (st.flags >> j) & 1u;
@@ -297,7 +357,10 @@ __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const Sector (&s)[
         } else {
             t.n_assigned += (a0 | a1 | a2) != 0;                                           // :128, :149
         }
-        if (QUEUE) {
+        if (QUEUE == 2) {
+            static_assert(B2_UPT == 2, "b2_q_push_tile places the hits of two units");
+            y |= (a0 | (a1 >> 1) | (a2 >> 2)) >> (3 * j);
+        } else if (QUEUE) {
             b2_q_push(a0 & 0x8000u, s[j].w[6], k, t);
             b2_q_push(a0 & 0x80000000u, s[j].w[6] >> 16, k, t);
             b2_q_push(a1 & 0x8000u, s[j].w[7], k, t);
@@ -317,9 +380,10 @@ __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const Sector (&s)[
         if (defer) t.wp[__popc(dm & k.lt_mask)] = make_uint4(u0 + j, st.sec[j], st.pts[j], 0u);
         t.wp += __popc(dm);
     }
+    if (QUEUE == 2) b2_q_push_tile<ALLHOT>(y, s, k, t, counts, (int)(threadIdx.x & 31));
 }
 
-template <bool PAIRED, int NT, bool ALLHOT, bool QUEUE, bool DEEP>
+template <bool PAIRED, int NT, bool ALLHOT, int QUEUE, bool DEEP>
 __global__ void __launch_bounds__(NT, DEEP ? 1 : 2048 / NT / 2)
 bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
@@ -441,7 +505,8 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
         b2_load_sectors(secl, sl, sv, k);
         b2_phase_b<ALLHOT, QUEUE>(sl, secl, u0, sv, k, t, counts, stats);
     }
-    if (QUEUE) b2_q_drain<ALLHOT>(k, t, counts, lane, true);
+    if (QUEUE == 2) b2_q_drain_linear<ALLHOT>(k, t, counts, lane, true);
+    else if (QUEUE) b2_q_drain<ALLHOT>(k, t, counts, lane, true);
     if (lane == 0) defer_count[gw] = (u32)(t.wp - my_list);
     u64 v[4] = {t.n_assigned, t.n_lowq, t.n_badchrom, t.n_qcfail};
 #pragma unroll
@@ -495,12 +560,13 @@ __device__ __forceinline__ int b2_probes(const uint4 rec, const Stab2View& sv, i
     return np;
 }
 
-// PF 0: every load of a chain waits for the one before it.  PF 1: the entry of the next turn is already in registers and its
-// primary sectors and overflow links are requested into L2 while this turn's chains are walked (the pass is bound by the
-// latency of dependent random loads, not by bandwidth).  PF 2: the overflow links of the next turn are read as well and
-// their sectors requested at the end of the turn.
-template <bool PAIRED, int PF>
-__global__ void __launch_bounds__(256, PF ? 5 : 6)
+// SET 0: the distinct ensg of a unit in registers, a new one stored at position nd (one compare + select per position).
+// SET 1: a new one enters at position 0 and the others move up (eight moves under one predicate), the slot of a hit entry
+// is picked by word and half instead of a chain of selects.
+// (Requesting the next turn's sectors into L2 one turn ahead was measured and dropped: the pass is bound by the divergent
+// instruction stream of the hit loop, not by the latency of its loads -- profiles/r02_bulk_se_ncu_summary.md.)
+template <bool PAIRED, int SET>
+__global__ void __launch_bounds__(256, 6)
 bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ stats,
                     const uint4* __restrict__ defer_list, const u32* __restrict__ defer_count, u32 seg_cap, u32 n_seg, u32 parts,
                     u32* __restrict__ slow_list, u32 sv_n_chrom) {
@@ -532,42 +598,19 @@ bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ st
         }
         __syncwarp();
     };
-    const uint4 none = make_uint4(0u, B2_DEF_GATHER | B2_DEF_NAME, 0u, 0u);   // an entry without probes
     for (u32 w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_w; w += gridDim.x * (blockDim.x >> 5)) {
         const u32 seg = w % n_seg, part = w / n_seg;
         const u32 cnt = __ldg(defer_count + seg);
         const uint4* const list = defer_list + (size_t)seg * seg_cap;
-        const u32 step = parts * 32;
-        uint4 r1 = none, r2 = none;                               // PF: entries of this turn and of the next one
-        if (PF) {
-            if (part * 32 + lane < cnt) r1 = __ldg(list + part * 32 + lane);
-            if (part * 32 + step + lane < cnt) r2 = __ldg(list + part * 32 + step + lane);
-        }
-        for (u32 i0 = part * 32; i0 < cnt; i0 += step) {
+        for (u32 i0 = part * 32; i0 < cnt; i0 += parts * 32) {
             const bool live = i0 + lane < cnt;
             bool exact = false;
             u32 u = 0, nd = 0;
             u32 dist[B2_MAXD];
 #pragma unroll
             for (int i = 0; i < B2_MAXD; ++i) dist[i] = 0xFFFFFFFFu;
-            uint4 rec = none, r3 = none;
-            u32 o2[2] = {0u, 0u};
-            int np2 = 0;
-            if (PF) {
-                rec = r1;
-                // the turn after the next: its entry is requested now, used two turns from here
-                if (i0 + 2 * step + lane < cnt) r3 = __ldg(list + i0 + 2 * step + lane);
-                u32 prim2[2], pts2[2];
-                np2 = b2_probes<PAIRED>(r2, sv, shift, cmask, lim, sv_n_chrom, prim2, pts2);
-                for (int p = 0; p < np2; ++p) {
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(sv.sectors + (size_t)prim2[p] * 8));
-                    if (PF == 2) o2[p] = __ldg(sv.ovf_first + prim2[p]);
-                    else asm volatile("prefetch.global.L2 [%0];" :: "l"(sv.ovf_first + prim2[p]));
-                }
-            } else if (live) {
-                rec = __ldg(list + i0 + lane);
-            }
             if (live) {
+                const uint4 rec = __ldg(list + i0 + lane);
                 u = rec.x;
                 u32 prim[2], pts[2];
                 if (PAIRED && (rec.y & B2_DEF_GATHER) && (rec.y & B2_DEF_NAME)) atomicAdd(stats + TEC_BS_CRASH_NAME, 1ULL);   // :92-94
@@ -587,14 +630,27 @@ bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ st
                         while (hit) {
                             const u32 low = hit & (0u - hit);
                             hit ^= low;
-                            const u32 w = (low == HB0) ? sector_slot_c<0>(s) : (low == HB1) ? sector_slot_c<1>(s) : (low == HB2) ? sector_slot_c<2>(s)
-                                          : (low == HB3) ? sector_slot_c<3>(s) : sector_slot_c<4>(s);
+                            u32 w;
+                            if (SET) {
+                                // HB0 / HB1 = bits 15 / 31 (slots in w6), HB2 / HB3 = bits 14 / 30 (w7), HB4 = bit 13 (high half of w5)
+                                const u32 word = (low & (HB0 | HB1)) ? s.w[6] : (low & (HB2 | HB3)) ? s.w[7] : s.w[5];
+                                w = (low & (HB1 | HB3 | HB4)) ? (word >> 16) : (word & 0xFFFFu);
+                            } else {
+                                w = (low == HB0) ? sector_slot_c<0>(s) : (low == HB1) ? sector_slot_c<1>(s) : (low == HB2) ? sector_slot_c<2>(s)
+                                    : (low == HB3) ? sector_slot_c<3>(s) : sector_slot_c<4>(s);
+                            }
                             bool found = false;
 #pragma unroll
                             for (int j = 0; j < B2_MAXD; ++j) found |= (dist[j] == w);
                             if (!found) {
+                                if (SET) {
 #pragma unroll
-                                for (int j = 0; j < B2_MAXD; ++j) if ((u32)j == nd) dist[j] = w;
+                                    for (int j = B2_MAXD - 1; j > 0; --j) dist[j] = dist[j - 1];
+                                    dist[0] = w;                                       // (the one that falls off the end: nd > B2_MAXD below)
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < B2_MAXD; ++j) if ((u32)j == nd) dist[j] = w;
+                                }
                                 ++nd;                                                  // nd > B2_MAXD: overflow
                             }
                         }
@@ -618,12 +674,6 @@ bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ st
                         }
                     }
                 }
-            }
-            if (PF) {
-                if (PF == 2)
-                    for (int p = 0; p < np2; ++p) asm volatile("prefetch.global.L2 [%0];" :: "l"(sv.sectors + (size_t)o2[p] * 8));
-                r1 = r2;
-                r2 = r3;
             }
             // the warp is converged here: the ensg to count go through the queue
 #pragma unroll

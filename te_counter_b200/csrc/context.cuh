@@ -166,8 +166,8 @@ struct tec_ctx {
     int opt_bulk_mode = 13;               // fast bulk kernel: bit 0 table sectors evict_last in L2, bit 1 prefetch the next tile's sectors,
                                           // bit 2 tally through the per-warp hit queue, bit 3 512-thread CTAs with three tiles in flight per warp
     int opt_bulk_strand = 0;              // extension (not in the reference): strand-aware bulk counting, exact kernel only
-    int opt_second_parts = 0;             // warps of the second bulk pass per segment of the deferred list (0: 2, or 5 with the prefetching variants)
-    int opt_second_mode = 1;              // second bulk pass: 0 dependent loads, 1 the next turn's primary sectors requested ahead, 2 + its overflow sectors
+    int opt_second_parts = 3;             // warps of the second bulk pass per segment of the deferred list (3: six CTAs per SM)
+    int opt_second_mode = 1;              // second bulk pass: register set of distinct ensg, 0 stored by position, 1 shifted in
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
     int opt_sc_sort = 1;                  // single cell: packed 64-bit keys + the 11-bit radix sort of csrc/radix.cuh (0: library sort, two stages)
     int opt_sc_prev_partition = 0;        // single cell: 0 prev[] by random 4-byte stores (default); 1 / 2 through one radix pass on the position

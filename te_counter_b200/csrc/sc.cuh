@@ -1540,12 +1540,32 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         if (h_npairs) {
             TEC_CUDA(A.get(&pairs_sorted, (size_t)h_npairs));
             size_t tb = 0;
-            const int kb = 32 + std::max(1, ceil_log2_i64(std::max<int64_t>(ctx->idx.n_ensg, 2)));
-            TEC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, pairs, pairs_sorted, (int)h_npairs, 0, std::min(kb, 64), ctx->stream));
-            rc = sc_cub_tmp(ctx, tb);
-            if (rc) return rc;
-            TEC_CUDA(cub::DeviceRadixSort::SortKeys(s->cub_tmp, tb, pairs, pairs_sorted, (int)h_npairs, 0, std::min(kb, 64), ctx->stream));
-            A.release(pairs);
+            if (ctx->opt_sc_sort != 0) {
+                // keys = ensg << 32 | cell: stable LSD over the cell bits, then over the ensg bits (csrc/radix.cuh, keys only;
+                // the zero bits between the two fields are never visited)
+                const RdxPlan plan = rdx_plan(h_npairs, ctx->n_sm);
+                u32* scratch = nullptr;
+                TEC_CUDA(A.get(&scratch, plan.counts_bytes / 4));
+                const int cell_bits = std::max(1, ceil_log2_i64(std::max<int64_t>(W, 2)));
+                const int ensg_bits = std::max(1, ceil_log2_i64(std::max<int64_t>(ctx->idx.n_ensg, 2)));
+                bool in_b = false, in_b2 = false;
+                int p1 = 0, p2 = 0;
+                TEC_CUDA((rdx_sort<u64, false>(pairs, nullptr, pairs_sorted, nullptr, h_npairs, 0, cell_bits, ctx->n_sm, scratch, ctx->stream, &in_b, &p1)));
+                u64 *k1 = in_b ? pairs_sorted : pairs, *k2 = in_b ? pairs : pairs_sorted;
+                TEC_CUDA((rdx_sort<u64, false>(k1, nullptr, k2, nullptr, h_npairs, 32, 32 + ensg_bits, ctx->n_sm, scratch, ctx->stream, &in_b2, &p2)));
+                u64* other = in_b2 ? k1 : k2;
+                pairs_sorted = in_b2 ? k2 : k1;
+                ctx->launches += RDX_LAUNCHES_PER_PASS * (p1 + p2);
+                A.release(scratch);
+                A.release(other);
+            } else {
+                const int kb = 32 + std::max(1, ceil_log2_i64(std::max<int64_t>(ctx->idx.n_ensg, 2)));
+                TEC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, pairs, pairs_sorted, (int)h_npairs, 0, std::min(kb, 64), ctx->stream));
+                rc = sc_cub_tmp(ctx, tb);
+                if (rc) return rc;
+                TEC_CUDA(cub::DeviceRadixSort::SortKeys(s->cub_tmp, tb, pairs, pairs_sorted, (int)h_npairs, 0, std::min(kb, 64), ctx->stream));
+                A.release(pairs);
+            }
             u64* ukeys = nullptr;
             u32 *ucnt = nullptr, *d_nruns = nullptr;
             TEC_CUDA(A.get(&ukeys, (size_t)h_npairs));

@@ -387,7 +387,8 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
     TEC_CUDA(cudaMemsetAsync(ctx->d_slow_list, 0, 4, ctx->stream));
 #define TEC_LAUNCH_FAST2(P, NT, AH, DP)                                                                                    \
     do {                                                                                                                   \
-        auto kfn = (ctx->opt_bulk_mode & B2_MODE_QUEUE) ? bulk2_fast_kernel<P, NT, AH, true, DP> : bulk2_fast_kernel<P, NT, AH, false, DP>; \
+        auto kfn = (ctx->opt_bulk_mode & B2_MODE_SCAN) ? bulk2_fast_kernel<P, NT, AH, 2, DP>                               \
+                   : (ctx->opt_bulk_mode & B2_MODE_QUEUE) ? bulk2_fast_kernel<P, NT, AH, 1, DP> : bulk2_fast_kernel<P, NT, AH, 0, DP>; \
         TEC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                        \
         kfn<<<blocks, NT, dyn, ctx->stream>>>(sv, ctx->idx.n_chrom, (u32)n_units, ctx->qual, start, end, chrom, mapq, flag, \
                                               counts, stats, (uint4*)ctx->d_defer_list, ctx->d_defer_count, (u32)seg_cap, n_hot, \
@@ -405,14 +406,13 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
 #undef TEC_LAUNCH_FAST2
     ctx->launches++;
     TEC_CUDA(cudaGetLastError());
-    const int pf = ctx->opt_second_mode;
-    const int parts = std::max(1, ctx->opt_second_parts > 0 ? ctx->opt_second_parts : (pf ? 5 : 2));
-    const int b2 = (int)std::min<int64_t>((n_warps * parts + 7) / 8, (int64_t)ctx->n_sm * (pf ? 5 : 6));
-#define TEC_LAUNCH_SECOND(P, PF)                                                                                               \
-    bulk2_second_kernel<P, PF><<<b2, 256, 0, ctx->stream>>>(sv, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count, \
-                                                            (u32)seg_cap, (u32)n_warps, (u32)parts, ctx->d_slow_list, (u32)ctx->idx.n_chrom)
-    if (ctx->paired) { if (pf == 2) TEC_LAUNCH_SECOND(true, 2); else if (pf == 1) TEC_LAUNCH_SECOND(true, 1); else TEC_LAUNCH_SECOND(true, 0); }
-    else { if (pf == 2) TEC_LAUNCH_SECOND(false, 2); else if (pf == 1) TEC_LAUNCH_SECOND(false, 1); else TEC_LAUNCH_SECOND(false, 0); }
+    const int parts = std::max(1, ctx->opt_second_parts);
+    const int b2 = (int)std::min<int64_t>((n_warps * parts + 7) / 8, (int64_t)ctx->n_sm * 6);
+#define TEC_LAUNCH_SECOND(P, SET)                                                                                              \
+    bulk2_second_kernel<P, SET><<<b2, 256, 0, ctx->stream>>>(sv, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count, \
+                                                             (u32)seg_cap, (u32)n_warps, (u32)parts, ctx->d_slow_list, (u32)ctx->idx.n_chrom)
+    if (ctx->paired) { if (ctx->opt_second_mode) TEC_LAUNCH_SECOND(true, 1); else TEC_LAUNCH_SECOND(true, 0); }
+    else { if (ctx->opt_second_mode) TEC_LAUNCH_SECOND(false, 1); else TEC_LAUNCH_SECOND(false, 0); }
 #undef TEC_LAUNCH_SECOND
     ctx->launches++;
     TEC_CUDA(cudaGetLastError());
@@ -602,9 +602,9 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "bulk_strand") { ctx->opt_bulk_strand = value ? 1 : 0; }     // opt-in extension, outside the parity claim (bulk.cuh)
     else if (k == "sc_prev_partition") { if (value < 0 || value > 2) TEC_FAIL(TEC_ERR_ARG, "sc_prev_partition: 0 random stores, 1 radix pass on large inputs, 2 always"); ctx->opt_sc_prev_partition = (int)value; }
     else if (k == "sc_sort_chunk") { if (value < 1 || value > 64) TEC_FAIL(TEC_ERR_ARG, "sc_sort_chunk: tiles per chunk of csrc/radix.cuh, 1..64"); g_rdx_chunk_tiles = (int)value; }
-    else if (k == "second_parts") { if (value < 0 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 0 (by mode) or 1..16"); ctx->opt_second_parts = (int)value; }
-    else if (k == "second_mode") { if (value < 0 || value > 2) TEC_FAIL(TEC_ERR_ARG, "second_mode: 0 dependent loads, 1 next turn's primary sectors requested ahead, 2 its overflow sectors as well"); ctx->opt_second_mode = (int)value; }
-    else if (k == "bulk_mode") { if (value < 0 || value > 15) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline"); ctx->opt_bulk_mode = (int)value; }
+    else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }
+    else if (k == "second_mode") { if (value < 0 || value > 1) TEC_FAIL(TEC_ERR_ARG, "second_mode: 0 distinct ensg stored by position, 1 shifted in"); ctx->opt_second_mode = (int)value; }
+    else if (k == "bulk_mode") { if (value < 0 || value > 31) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline, bit 4 hit queue filled once per tile"); ctx->opt_bulk_mode = (int)value; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else if (k == "bam_lanes") { if (value < 1 || value > 32) TEC_FAIL(TEC_ERR_ARG, "bam_lanes: 1..32"); ctx->opt_bam_lanes = (int)value; }
     else if (k == "bam_window_blocks") { if (value < 1 || value > (1 << 20)) TEC_FAIL(TEC_ERR_ARG, "bam_window_blocks: 1..1048576"); ctx->opt_bam_window_blocks = (int)value; }

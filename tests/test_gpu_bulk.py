@@ -86,6 +86,30 @@ def test_bulk_counter_placement(engine, paired, all_hot):
         (os_["assigned"], os_["lowq"], os_["badchrom"], os_["qcfail"])
 
 
+@pytest.mark.parametrize("paired", [False, True])
+@pytest.mark.parametrize("bulk_mode,second_mode", [(0, 0), (5, 1), (13, 0), (13, 1), (29, 1), (21, 1), (31, 0)])
+def test_bulk_kernel_variants(engine, paired, bulk_mode, second_mode):
+    """Every variant of the two-pass kernels (tally by reduction / ballot queue / scan queue, shallow / deep pipeline,
+    both register sets of the second pass) against the oracle: dense pile-ups, gapped reads, EDGE cells."""
+    idx = synth.synth_index(5, n_te=30000, n_exon=12000, n_gene=900, n_te_names=500, chrom_len=1_500_000, n_chrom=3)
+    r = synth.synth_bulk_reads(6, idx, 150_001 if not paired else 150_002, paired=paired, edge_frac=0.05)
+    engine.set_option("bulk_mode", bulk_mode)
+    engine.set_option("second_mode", second_mode)
+    try:
+        engine.upload_index(idx)
+        engine.bulk_begin(paired, 20)
+        engine.bulk_push(len(r["start"]), r["start"], r["end"], r["chrom"], r["mapq"], r["flag"])
+        counts, st = engine.bulk_finish()
+    finally:
+        engine.set_option("bulk_mode", 13)
+        engine.set_option("second_mode", 1)
+    oc, os_ = te_oracle.bulk_count(H.oracle_index(idx), paired, 20, r["start"].tolist(), r["end"].tolist(),
+                                   r["chrom"].tolist(), r["mapq"].tolist(), r["flag"].tolist())
+    assert counts.tolist() == oc
+    assert (st[_lib.BS_ASSIGNED], st[_lib.BS_LOWQ], st[_lib.BS_BADCHROM], st[_lib.BS_QCFAIL]) == \
+        (os_["assigned"], os_["lowq"], os_["badchrom"], os_["qcfail"])
+
+
 def test_bulk_deep_pileup_overflow_path(engine):
     """> BULK_MAX_DISTINCT distinct ensg under one read: the O(h^2) re-walk path."""
     n = 40
