@@ -125,7 +125,8 @@ int tec_trim(tec_ctx* ctx);
  * bulk, 11 for the single-cell pair table; used by the next tec_index_upload), "bulk_mode" (bit 0 table sectors
  * evict_last in L2, bit 1 sector prefetch, bit 2 tally through the per-warp hit queue, bit 3 deep pipeline),
  * "second_mode" (second bulk pass: the register set of a unit's distinct ensg, 0 stored by position, 1 shifted
- * in), "second_parts" (warps per segment of the deferred list), "ctas_per_sm",
+ * in, 2 = 1 + the units that two sectors answer go through a straight-line kernel first), "second_parts" (warps
+ * per segment of the deferred list), "ctas_per_sm",
  * "all_hot" (counters of every ensg in shared memory when they fit), "sc_algo" (-1 auto, 0 exact search in
  * Part 3, 1 cell table), "sc_pack_umi" (2-bit UMI sort keys when possible).
  * tec_get_info: "has_stab", "stab_bytes", "has_sc_stab", "sc_stab_bytes", "n_sm", "n_features",

@@ -560,6 +560,147 @@ __device__ __forceinline__ int b2_probes(const uint4 rec, const Stab2View& sv, i
     return np;
 }
 
+// Deferred units that TWO sectors answer, straight-line and converged (no hit loop, no chain loop): an overflow unit
+// whose chain ends in the first overflow sector (primary + ovf_first[primary], both points), or a unit whose points lie
+// in two cells whose primary sectors answer one point each (spliced single-end reads).  Duplicates: twins inside a
+// primary sector by its flag bits; an ensg hit in both sectors, or twice inside an overflow sector, by comparing the at
+// most 5 + 5 slots.  Everything else (EDGE cells, longer chains, name mismatches, single-probe gathers) is left IN PLACE
+// for bulk2_second_kernel: the m-th entry a warp leaves goes where the m-th entry of its walk was; part_count[w] = how
+// many.  Only used when every ensg is of a counted type (sv.all_counted).
+template <bool PAIRED>
+__global__ void __launch_bounds__(256, 5)
+bulk2_pair_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ stats,
+                  uint4* __restrict__ defer_list, const u32* __restrict__ defer_count, u32 seg_cap, u32 n_seg, u32 parts,
+                  u32* __restrict__ part_count, u32 sv_n_chrom) {
+    __shared__ u32 s_hot[TEC_HOT_SLOTS];
+    __shared__ unsigned short s_q[8][B2_QCAP2];
+    for (int i = threadIdx.x; i < TEC_HOT_SLOTS; i += blockDim.x) s_hot[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    unsigned short* const q = s_q[threadIdx.x >> 5];
+    u32 q_head = 0, q_tail = 0;                                    // warp-uniform
+    const u32 lt_mask = (1u << lane) - 1u;
+    const int shift = sv.shift;
+    const int cmask = (1 << shift) - 1;
+    const u32 lim = (u32)(cmask + 1 + sv.ext);
+    u32 n_assigned = 0;
+    const u32 n_w = n_seg * parts;
+    auto drain = [&](bool all) {
+        __syncwarp();
+        while (q_tail - q_head >= (all ? 1u : 32u)) {
+            const u32 slot = q[(q_head + (u32)lane) & (B2_QCAP2 - 1u)];
+            if ((u32)lane < q_tail - q_head) {
+                if (slot < TEC_HOT_SLOTS) atomicAdd(&s_hot[slot], 1u);
+                else atomicAdd(counts + slot, 1ULL);
+            }
+            q_head += min(32u, q_tail - q_head);
+        }
+        __syncwarp();
+    };
+    for (u32 w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_w; w += gridDim.x * (blockDim.x >> 5)) {
+        const u32 seg = w % n_seg, part = w / n_seg;
+        const u32 cnt = __ldg(defer_count + seg);
+        uint4* const list = defer_list + (size_t)seg * seg_cap;
+        u32 m_out = 0;                                             // entries left for the second pass (warp-uniform)
+        for (u32 i0 = part * 32; i0 < cnt; i0 += parts * 32) {
+            const bool live = i0 + lane < cnt;
+            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+            if (live) rec = list[i0 + lane];                       // plain load: the list is rewritten in place below
+            bool left = false, use = false, two_chains = false;
+            u32 secA = 0, secB = 0, ptsA = 0, ptsB = 0;
+            if (live) {
+                if (!(rec.y & B2_DEF_GATHER)) {                    // one chain, both points: primary + first overflow sector
+                    secA = rec.y; ptsA = ptsB = rec.z;
+                    secB = __ldg(sv.ovf_first + secA);
+                    use = true;
+                } else if (rec.y & B2_DEF_NAME) {
+                    left = true;                                   // the second pass counts the crash (:92-94)
+                } else {
+                    u32 prim[2], pts[2];
+                    const int np = b2_probes<PAIRED>(rec, sv, shift, cmask, lim, sv_n_chrom, prim, pts);
+                    if (np == 2) { secA = prim[0]; ptsA = pts[0]; secB = prim[1]; ptsB = pts[1]; use = two_chains = true; }
+                    else if (np == 1) left = true;                 // (no probe at all: nothing to count)
+                }
+            }
+            const Sector sA = ld_sector(sv.sectors, secA);
+            const Sector sB = ld_sector(sv.sectors, secB);
+            const u32 hA = sA.w[2] >> 16, hB = sB.w[2] >> 16;
+            const u32 raA = ptsA & 0xFFFFu, rbA = ptsA >> 16, raB = ptsB & 0xFFFFu, rbB = ptsB >> 16;
+            const int rmA = max(raA == S2_R_NONE ? -1 : (int)raA, rbA == S2_R_NONE ? -1 : (int)rbA);
+            const int rmB = max(raB == S2_R_NONE ? -1 : (int)raB, rbB == S2_R_NONE ? -1 : (int)rbB);
+            // does the chain go on behind this sector for this point?
+            const bool onA = ((hA & S2_H_MORE) != 0) & (rmA >= (int)(hA & S2_THR_MASK));
+            const bool onB = ((hB & S2_H_MORE) != 0) & (rmB >= (int)(hB & S2_THR_MASK));
+            bool useB = use;
+            if (use) {
+                if (hA & S2_H_EDGE) left = true;
+                if (two_chains) { if (onA || onB || (hB & S2_H_EDGE)) left = true; }
+                else { useB = onA; if (onA && onB) left = true; }
+            }
+            const bool go = use && !left;
+            u32 hitA = go ? b2_sector_hits(sA, make_point(raA), make_point(rbA)) : 0u;
+            u32 hitB = (go && useB) ? b2_sector_hits(sB, make_point(raB), make_point(rbB)) : 0u;
+            // twins of a primary sector count once (the flag bits are zero in overflow sectors)
+            hitA &= ~(((hitA & HB0) << 16) & sA.w[2] & 0x80000000u);
+            hitA &= ~(((hitA & HB2) << 16) & sA.w[2] & 0x40000000u);
+            hitB &= ~(((hitB & HB0) << 16) & sB.w[2] & 0x80000000u);
+            hitB &= ~(((hitB & HB2) << 16) & sB.w[2] & 0x40000000u);
+            // slots; an entry that was not hit gets a value no slot has
+            const u32 a0 = (hitA & HB0) ? (sA.w[6] & 0xFFFFu) : 0x10000u, a1 = (hitA & HB1) ? (sA.w[6] >> 16) : 0x10001u;
+            const u32 a2 = (hitA & HB2) ? (sA.w[7] & 0xFFFFu) : 0x10002u, a3 = (hitA & HB3) ? (sA.w[7] >> 16) : 0x10003u;
+            const u32 a4 = (hitA & HB4) ? (sA.w[5] >> 16) : 0x10004u;
+            const u32 b0 = (hitB & HB0) ? (sB.w[6] & 0xFFFFu) : 0x20000u, b1 = (hitB & HB1) ? (sB.w[6] >> 16) : 0x20001u;
+            const u32 b2 = (hitB & HB2) ? (sB.w[7] & 0xFFFFu) : 0x20002u, b3 = (hitB & HB3) ? (sB.w[7] >> 16) : 0x20003u;
+            const u32 b4 = (hitB & HB4) ? (sB.w[5] >> 16) : 0x20004u;
+            // (| and &, not || and &&: no short-circuit branches, the warp stays converged)
+            const bool k0 = ((hitB & HB0) != 0) & !((b0 == a0) | (b0 == a1) | (b0 == a2) | (b0 == a3) | (b0 == a4));
+            const bool k1 = ((hitB & HB1) != 0) & !((b1 == a0) | (b1 == a1) | (b1 == a2) | (b1 == a3) | (b1 == a4) | (b1 == b0));
+            const bool k2 = ((hitB & HB2) != 0) & !((b2 == a0) | (b2 == a1) | (b2 == a2) | (b2 == a3) | (b2 == a4) | (b2 == b0) | (b2 == b1));
+            const bool k3 = ((hitB & HB3) != 0) & !((b3 == a0) | (b3 == a1) | (b3 == a2) | (b3 == a3) | (b3 == a4) | (b3 == b0) | (b3 == b1) | (b3 == b2));
+            const bool k4 = ((hitB & HB4) != 0) & !((b4 == a0) | (b4 == a1) | (b4 == a2) | (b4 == a3) | (b4 == a4) | (b4 == b0) | (b4 == b1) | (b4 == b2) | (b4 == b3));
+            const u32 nd = (u32)__popc(hitA) + (u32)k0 + (u32)k1 + (u32)k2 + (u32)k3 + (u32)k4;
+            n_assigned += nd != 0;                                                     // :128, :149
+            // the warp is converged: one prefix sum places every lane's ensg in the queue
+            u32 incl = nd;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            u32 at = q_tail + incl - nd;
+            if (hitA & HB0) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)a0;
+            if (hitA & HB1) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)a1;
+            if (hitA & HB2) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)a2;
+            if (hitA & HB3) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)a3;
+            if (hitA & HB4) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)a4;
+            if (k0) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)b0;
+            if (k1) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)b1;
+            if (k2) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)b2;
+            if (k3) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)b3;
+            if (k4) q[at++ & (B2_QCAP2 - 1u)] = (unsigned short)b4;
+            q_tail += total;
+            drain(false);
+            // what is left goes back into the list, densely in this warp's walk order
+            const u32 lm = __ballot_sync(0xFFFFFFFFu, left);
+            if (left) {
+                const u32 m = m_out + (u32)__popc(lm & lt_mask);
+                list[part * 32u + (m >> 5) * parts * 32u + (m & 31u)] = rec;
+            }
+            m_out += (u32)__popc(lm);
+        }
+        if (lane == 0) part_count[w] = m_out;
+    }
+    drain(true);
+    const u64 a_sum = warp_sum((u64)n_assigned);
+    if (lane == 0 && a_sum) atomicAdd(stats + TEC_BS_ASSIGNED, a_sum);
+    __syncthreads();
+    for (int i = threadIdx.x; i < TEC_HOT_SLOTS; i += blockDim.x) {
+        const u32 x = s_hot[i];
+        if (x) atomicAdd(counts + i, (u64)x);
+    }
+}
+
 // SET 0: the distinct ensg of a unit in registers, a new one stored at position nd (one compare + select per position).
 // SET 1: a new one enters at position 0 and the others move up (eight moves under one predicate), the slot of a hit entry
 // is picked by word and half instead of a chain of selects.
@@ -569,7 +710,7 @@ template <bool PAIRED, int SET>
 __global__ void __launch_bounds__(256, 6)
 bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ stats,
                     const uint4* __restrict__ defer_list, const u32* __restrict__ defer_count, u32 seg_cap, u32 n_seg, u32 parts,
-                    u32* __restrict__ slow_list, u32 sv_n_chrom) {
+                    u32* __restrict__ slow_list, u32 sv_n_chrom, const u32* __restrict__ part_count) {
     // hot ensg counters privatised per CTA (a Zipf-hot TE name would otherwise serialise in one L2 slice)
     __shared__ u32 s_hot[TEC_HOT_SLOTS];
     __shared__ unsigned short s_q[8][B2_QCAP2];                    // per warp: ensg slots waiting to be counted
@@ -600,10 +741,15 @@ bulk2_second_kernel(Stab2View sv, u64* __restrict__ counts, u64* __restrict__ st
     };
     for (u32 w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_w; w += gridDim.x * (blockDim.x >> 5)) {
         const u32 seg = w % n_seg, part = w / n_seg;
-        const u32 cnt = __ldg(defer_count + seg);
+        // part_count: bulk2_pair_kernel went first and left, in place, the entries it could not answer -- the m-th one of
+        // (segment, part) at the position the m-th entry of that part's walk had
+        const u32 seg_cnt = __ldg(defer_count + seg);
+        const u32 cnt = part_count ? part * 32u + ((__ldg(part_count + w) + 31u) / 32u) * parts * 32u : seg_cnt;
+        const u32 left_n = part_count ? __ldg(part_count + w) : 0u;
         const uint4* const list = defer_list + (size_t)seg * seg_cap;
-        for (u32 i0 = part * 32; i0 < cnt; i0 += parts * 32) {
-            const bool live = i0 + lane < cnt;
+        u32 turn = 0;
+        for (u32 i0 = part * 32; i0 < cnt; i0 += parts * 32, ++turn) {
+            const bool live = part_count ? (turn * 32u + (u32)lane < left_n) : (i0 + lane < seg_cnt);
             bool exact = false;
             u32 u = 0, nd = 0;
             u32 dist[B2_MAXD];

@@ -159,6 +159,8 @@ struct tec_ctx {
     u32* d_defer_list = nullptr;          // bulk2: per-warp segments of deferred unit indices
     u32* d_defer_count = nullptr;         // bulk2: entries per segment
     int64_t defer_cap = 0, defer_warps = 0;
+    u32* d_part_count = nullptr;          // bulk2: entries bulk2_pair_kernel left per (segment, part)
+    int64_t part_cap = 0;
     std::vector<int32_t> ensg_of_slot;    // slot = rank of an ensg by number of feature rows
     // options (tec_set_option)
     int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 cell-table kernel with in-kernel rings (round 1), 2 two-pass kernels (bulk2.cuh)
@@ -166,8 +168,9 @@ struct tec_ctx {
     int opt_bulk_mode = 13;               // fast bulk kernel: bit 0 table sectors evict_last in L2, bit 1 prefetch the next tile's sectors,
                                           // bit 2 tally through the per-warp hit queue, bit 3 512-thread CTAs with three tiles in flight per warp
     int opt_bulk_strand = 0;              // extension (not in the reference): strand-aware bulk counting, exact kernel only
-    int opt_second_parts = 3;             // warps of the second bulk pass per segment of the deferred list (3: six CTAs per SM)
-    int opt_second_mode = 1;              // second bulk pass: register set of distinct ensg, 0 stored by position, 1 shifted in
+    int opt_second_parts = 4;             // warps of the second bulk pass (and of bulk2_pair_kernel) per segment of the deferred list
+    int opt_second_mode = 2;              // second bulk pass: register set of distinct ensg, 0 stored by position, 1 shifted in; 2: units that
+                                          // two sectors answer go through the straight-line bulk2_pair_kernel first
     int opt_all_hot = 1;                  // counters of every ensg in shared memory when they fit
     int opt_sc_sort = 1;                  // single cell: packed 64-bit keys + the 11-bit radix sort of csrc/radix.cuh (0: library sort, two stages)
     int opt_sc_prev_partition = 0;        // single cell: 0 prev[] by random 4-byte stores (default); 1 / 2 through one radix pass on the position
@@ -234,8 +237,9 @@ inline void tec_ctx::free_index() {
     d_slow_list = nullptr;
     cudaFree(d_ring); cudaFree(d_ring_u);
     d_ring = nullptr; d_ring_u = nullptr; ring_cap = 0;
-    cudaFree(d_defer_list); cudaFree(d_defer_count);
+    cudaFree(d_defer_list); cudaFree(d_defer_count); cudaFree(d_part_count);
     d_defer_list = nullptr; d_defer_count = nullptr; defer_cap = 0; defer_warps = 0;
+    d_part_count = nullptr; part_cap = 0;
     slow_cap = 0;
     has_index = false;
     bulk_active = false;

@@ -408,9 +408,31 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
     TEC_CUDA(cudaGetLastError());
     const int parts = std::max(1, ctx->opt_second_parts);
     const int b2 = (int)std::min<int64_t>((n_warps * parts + 7) / 8, (int64_t)ctx->n_sm * 6);
+    // units that two sectors answer go through the straight-line kernel first; it leaves the rest in place
+    const bool pair_pass = ctx->opt_second_mode >= 2 && sv.all_counted;
+    const u32* part_count = nullptr;
+    if (pair_pass) {
+        if (n_warps * parts > ctx->part_cap) {
+            TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_part_count);
+            ctx->d_part_count = nullptr; ctx->part_cap = 0;
+            const int64_t cap = std::max<int64_t>(n_warps * parts, 148 * 32 * 4);
+            TEC_CUDA(cudaMalloc(&ctx->d_part_count, (size_t)cap * 4));
+            ctx->part_cap = cap;
+        }
+        if (ctx->paired)
+            bulk2_pair_kernel<true><<<b2, 256, 0, ctx->stream>>>(sv, counts, stats, (uint4*)ctx->d_defer_list, ctx->d_defer_count, (u32)seg_cap,
+                                                                 (u32)n_warps, (u32)parts, ctx->d_part_count, (u32)ctx->idx.n_chrom);
+        else
+            bulk2_pair_kernel<false><<<b2, 256, 0, ctx->stream>>>(sv, counts, stats, (uint4*)ctx->d_defer_list, ctx->d_defer_count, (u32)seg_cap,
+                                                                  (u32)n_warps, (u32)parts, ctx->d_part_count, (u32)ctx->idx.n_chrom);
+        ctx->launches++;
+        TEC_CUDA(cudaGetLastError());
+        part_count = ctx->d_part_count;
+    }
 #define TEC_LAUNCH_SECOND(P, SET)                                                                                              \
     bulk2_second_kernel<P, SET><<<b2, 256, 0, ctx->stream>>>(sv, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count, \
-                                                             (u32)seg_cap, (u32)n_warps, (u32)parts, ctx->d_slow_list, (u32)ctx->idx.n_chrom)
+                                                             (u32)seg_cap, (u32)n_warps, (u32)parts, ctx->d_slow_list, (u32)ctx->idx.n_chrom, part_count)
     if (ctx->paired) { if (ctx->opt_second_mode) TEC_LAUNCH_SECOND(true, 1); else TEC_LAUNCH_SECOND(true, 0); }
     else { if (ctx->opt_second_mode) TEC_LAUNCH_SECOND(false, 1); else TEC_LAUNCH_SECOND(false, 0); }
 #undef TEC_LAUNCH_SECOND
@@ -603,7 +625,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_prev_partition") { if (value < 0 || value > 2) TEC_FAIL(TEC_ERR_ARG, "sc_prev_partition: 0 random stores, 1 radix pass on large inputs, 2 always"); ctx->opt_sc_prev_partition = (int)value; }
     else if (k == "sc_sort_chunk") { if (value < 1 || value > 64) TEC_FAIL(TEC_ERR_ARG, "sc_sort_chunk: tiles per chunk of csrc/radix.cuh, 1..64"); g_rdx_chunk_tiles = (int)value; }
     else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }
-    else if (k == "second_mode") { if (value < 0 || value > 1) TEC_FAIL(TEC_ERR_ARG, "second_mode: 0 distinct ensg stored by position, 1 shifted in"); ctx->opt_second_mode = (int)value; }
+    else if (k == "second_mode") { if (value < 0 || value > 2) TEC_FAIL(TEC_ERR_ARG, "second_mode: 0 distinct ensg stored by position, 1 shifted in, 2 two-sector kernel first"); ctx->opt_second_mode = (int)value; }
     else if (k == "bulk_mode") { if (value < 0 || value > 31) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline, bit 4 hit queue filled once per tile"); ctx->opt_bulk_mode = (int)value; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else if (k == "bam_lanes") { if (value < 1 || value > 32) TEC_FAIL(TEC_ERR_ARG, "bam_lanes: 1..32"); ctx->opt_bam_lanes = (int)value; }
