@@ -419,6 +419,7 @@ def bulk_leg(C, wl, headline):
     clocks = sampler.stop(t0, t1)
     launches = eng.launch_count() - l0
     deferred, slow = eng.get_info("last_deferred_units"), eng.get_info("last_slow_units")
+    left = eng.get_info("last_left_units")
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
     ms_step = C.max_over_ranks(e0.elapsed_time(e1)) / K
     value = n_rec * world / (ms_step / 1e3)
@@ -537,9 +538,10 @@ def bulk_leg(C, wl, headline):
            "config": workload_config(args, wl, n_rec, world), "gpu_launches": int(launches), "dtype": "int32",
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": C.peak, "unit": "GB/s",
                         "frac": achieved / C.peak, "traffic": traffic, "peak_source": C.peak_src, "traffic_source": traffic_src,
-                        "kernel": "bulk2_fast_kernel<%s> + bulk2_second_kernel (deferred units) + bulk_slow_kernel (exact search)"
+                        "kernel": "bulk2_fast_kernel<%s> + bulk2_pair_kernel / bulk2_second_kernel (deferred units) + bulk_slow_kernel (exact search)"
                                   % ("paired" if paired else "single"),
                         "cell_table_bytes": eng.get_info("stab_bytes"), "deferred_units_per_launch": deferred,
+                        "left_units_per_launch": left,
                         "slow_units_per_launch": slow, "kernel_ms": kern_ms, "algorithmic_bytes_per_record": bpr},
            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity, "parity_full": parity_full,
            "stats": {"units": int(st[0]), "assigned": int(st[1]), "lowq": int(st[2]), "badchrom": int(st[3]),

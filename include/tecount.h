@@ -130,7 +130,8 @@ int tec_trim(tec_ctx* ctx);
  * "all_hot" (counters of every ensg in shared memory when they fit), "sc_algo" (-1 auto, 0 exact search in
  * Part 3, 1 cell table), "sc_pack_umi" (2-bit UMI sort keys when possible).
  * tec_get_info: "has_stab", "stab_bytes", "has_sc_stab", "sc_stab_bytes", "n_sm", "n_features",
- * "stab_primary", "stab_overflow", "stab_entries", "last_slow_units", "last_deferred_units", "stab_refused";
+ * "stab_primary", "stab_overflow", "stab_entries", "last_slow_units", "last_deferred_units", "last_left_units"
+ * (deferred units the two-sector kernel left for the second pass), "stab_refused";
  * -1 for unknown keys. */
 int tec_set_option(tec_ctx* ctx, const char* key, int64_t value);
 int64_t tec_get_info(tec_ctx* ctx, const char* key);

@@ -151,6 +151,7 @@ struct B2Const {
 #define B2_MODE_PREFETCH 2u       // request the next tile's sectors into L2 one turn ahead
 #define B2_MODE_QUEUE 4u          // tally through the per-warp hit queue instead of one reduction per entry
 #define B2_MODE_DEEP 8u           // 512-thread CTAs with 128 registers per thread: three tiles in flight per warp
+#define B2_MODE_768 32u           // with B2_MODE_DEEP: 768-thread CTAs (85 registers), two tiles in flight per warp
 #define B2_MODE_SCAN 16u          // hit queue filled once per tile (both units of a lane): one warp prefix sum instead of ten ballots
 
 __device__ __forceinline__ Sector ld_sector_pol(const u32* sectors, u32 idx, u64 pol) {
@@ -383,8 +384,8 @@ __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const Sector (&s)[
     if (QUEUE == 2) b2_q_push_tile<ALLHOT>(y, s, k, t, counts, (int)(threadIdx.x & 31));
 }
 
-template <bool PAIRED, int NT, bool ALLHOT, int QUEUE, bool DEEP>
-__global__ void __launch_bounds__(NT, DEEP ? 1 : 2048 / NT / 2)
+template <bool PAIRED, int NT, bool ALLHOT, int QUEUE, int DEPTH>
+__global__ void __launch_bounds__(NT, DEPTH ? 1 : 2048 / NT / 2)
 bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                   const uint16_t* __restrict__ chrom, const uint8_t* __restrict__ mapq,
@@ -432,12 +433,13 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
     const bool pf = (mode & B2_MODE_PREFETCH) != 0;
     u32 tile = gw;
     B2Raw<PAIRED> raw;
-    if constexpr (DEEP) {
-        // Full tiles of 64 units, warp-strided, three tiles in flight per warp (128 registers per thread, one CTA of
-        // NT threads per SM): while tile i is tested and tallied, the sectors of tiles i+1 and i+2 and the records of
-        // tile i+3 are on their way -- the warp's own arithmetic hides its own L2 / HBM latency.
-        B2Stage st[3];
-        Sector sec[3][B2_UPT];
+    if constexpr (DEPTH != 0) {
+        // Full tiles of 64 units, warp-strided, DEPTH tiles in flight per warp (one CTA per SM: 512 threads with 128 registers
+        // and three tiles, or 768 threads with 85 registers and two): while tile i is tested and tallied, the sectors of the
+        // tiles behind it and the records of tile i + DEPTH are on their way -- the warp's own arithmetic hides its own
+        // L2 / HBM latency.
+        B2Stage st[DEPTH];
+        Sector sec[DEPTH][B2_UPT];
         auto fill = [&](B2Stage& stg, Sector (&sc)[B2_UPT], u32 tl) {       // records of `tl` are in raw
             b2_phase_a<PAIRED, true>(raw, tl * 64 + 2 * lane, sv, k, t, stg);
             if (tl + stride < n_full && tl + stride >= tl)
@@ -446,15 +448,16 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
         };
         if (tile < n_full) {
             b2_load<PAIRED, true>(raw, tile * 64 + 2 * lane, n_units, start, end, chrom, mapq, flag, pol);
-            fill(st[0], sec[0], tile);
-            if (tile + stride < n_full) fill(st[1], sec[1], tile + stride);
+#pragma unroll
+            for (int d = 0; d < DEPTH - 1; ++d)
+                if (tile + (u32)d * stride < n_full) fill(st[d], sec[d], tile + (u32)d * stride);
         }
         while (tile < n_full) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < DEPTH; ++r) {
                 if (tile < n_full) {
-                    const u32 t2 = tile + 2 * stride;
-                    if (t2 < n_full) fill(st[(r + 2) % 3], sec[(r + 2) % 3], t2);
+                    const u32 t2 = tile + (u32)(DEPTH - 1) * stride;
+                    if (t2 < n_full) fill(st[(r + DEPTH - 1) % DEPTH], sec[(r + DEPTH - 1) % DEPTH], t2);
                     b2_phase_b<ALLHOT, QUEUE>(st[r], sec[r], tile * 64 + 2 * lane, sv, k, t, counts, stats);
                     tile += stride;
                 }

@@ -160,7 +160,7 @@ struct tec_ctx {
     u32* d_defer_count = nullptr;         // bulk2: entries per segment
     int64_t defer_cap = 0, defer_warps = 0;
     u32* d_part_count = nullptr;          // bulk2: entries bulk2_pair_kernel left per (segment, part)
-    int64_t part_cap = 0;
+    int64_t part_cap = 0, last_part_n = 0;
     std::vector<int32_t> ensg_of_slot;    // slot = rank of an ensg by number of feature rows
     // options (tec_set_option)
     int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 cell-table kernel with in-kernel rings (round 1), 2 two-pass kernels (bulk2.cuh)

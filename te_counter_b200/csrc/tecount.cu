@@ -358,7 +358,8 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
     // every counter in shared memory: one CTA per SM, of 1024 threads (64 registers) or, B2_MODE_DEEP, of 512 threads
     // with 128 registers and three tiles in flight per warp
     const bool deep = allhot && (ctx->opt_bulk_mode & B2_MODE_DEEP);
-    const int nt = allhot && !deep ? 1024 : 512;
+    const bool deep768 = deep && (ctx->opt_bulk_mode & B2_MODE_768);
+    const int nt = allhot && !deep ? 1024 : deep768 ? 768 : 512;
     const u32 n_hot = allhot ? (u32)ctx->idx.n_ensg : (u32)std::min<int64_t>(TEC_HOT_SLOTS, ctx->idx.n_ensg);
     const int wpb = nt / 32;
     const size_t dyn = (size_t)n_hot * 4 + 128 + (size_t)wpb * B2_QCAP * 2;   // + one scratch word per lane, + the warps' hit queues
@@ -395,13 +396,15 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
                                               (u32)ctx->opt_bulk_mode);                                                    \
     } while (0)
     if (ctx->paired) {
-        if (deep) TEC_LAUNCH_FAST2(true, 512, true, true);
-        else if (allhot) TEC_LAUNCH_FAST2(true, 1024, true, false);
-        else TEC_LAUNCH_FAST2(true, 512, false, false);
+        if (deep768) TEC_LAUNCH_FAST2(true, 768, true, 2);
+        else if (deep) TEC_LAUNCH_FAST2(true, 512, true, 3);
+        else if (allhot) TEC_LAUNCH_FAST2(true, 1024, true, 0);
+        else TEC_LAUNCH_FAST2(true, 512, false, 0);
     } else {
-        if (deep) TEC_LAUNCH_FAST2(false, 512, true, true);
-        else if (allhot) TEC_LAUNCH_FAST2(false, 1024, true, false);
-        else TEC_LAUNCH_FAST2(false, 512, false, false);
+        if (deep768) TEC_LAUNCH_FAST2(false, 768, true, 2);
+        else if (deep) TEC_LAUNCH_FAST2(false, 512, true, 3);
+        else if (allhot) TEC_LAUNCH_FAST2(false, 1024, true, 0);
+        else TEC_LAUNCH_FAST2(false, 512, false, 0);
     }
 #undef TEC_LAUNCH_FAST2
     ctx->launches++;
@@ -429,6 +432,9 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
         ctx->launches++;
         TEC_CUDA(cudaGetLastError());
         part_count = ctx->d_part_count;
+        ctx->last_part_n = n_warps * parts;
+    } else {
+        ctx->last_part_n = 0;
     }
 #define TEC_LAUNCH_SECOND(P, SET)                                                                                              \
     bulk2_second_kernel<P, SET><<<b2, 256, 0, ctx->stream>>>(sv, counts, stats, (const uint4*)ctx->d_defer_list, ctx->d_defer_count, \
@@ -626,7 +632,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_sort_chunk") { if (value < 1 || value > 64) TEC_FAIL(TEC_ERR_ARG, "sc_sort_chunk: tiles per chunk of csrc/radix.cuh, 1..64"); g_rdx_chunk_tiles = (int)value; }
     else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }
     else if (k == "second_mode") { if (value < 0 || value > 2) TEC_FAIL(TEC_ERR_ARG, "second_mode: 0 distinct ensg stored by position, 1 shifted in, 2 two-sector kernel first"); ctx->opt_second_mode = (int)value; }
-    else if (k == "bulk_mode") { if (value < 0 || value > 31) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline, bit 4 hit queue filled once per tile"); ctx->opt_bulk_mode = (int)value; }
+    else if (k == "bulk_mode") { if (value < 0 || value > 63) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline, bit 4 hit queue filled once per tile, bit 5 768-thread CTAs with two tiles in flight"); ctx->opt_bulk_mode = (int)value; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else if (k == "bam_lanes") { if (value < 1 || value > 32) TEC_FAIL(TEC_ERR_ARG, "bam_lanes: 1..32"); ctx->opt_bam_lanes = (int)value; }
     else if (k == "bam_window_blocks") { if (value < 1 || value > (1 << 20)) TEC_FAIL(TEC_ERR_ARG, "bam_window_blocks: 1..1048576"); ctx->opt_bam_window_blocks = (int)value; }
@@ -651,6 +657,15 @@ extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
         std::vector<u32> h((size_t)ctx->defer_warps);
         if (cudaMemcpy(h.data(), ctx->d_defer_count, h.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        int64_t n = 0;
+        for (u32 x : h) n += x;
+        return n;
+    }
+    if (k == "last_left_units") {          // deferred units bulk2_pair_kernel left for the second pass in the last launch (-1: it did not run)
+        if (!ctx->d_part_count || !ctx->last_part_n) return -1;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+        std::vector<u32> h((size_t)ctx->last_part_n);
+        if (cudaMemcpy(h.data(), ctx->d_part_count, h.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         int64_t n = 0;
         for (u32 x : h) n += x;
         return n;

@@ -1,0 +1,10 @@
+#!/bin/bash
+O=gpurun_out/r02aj
+mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_bulk.py -x -q -m gpu -k "variants" > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
+tail -3 $O/pytest.log
+CFG="bulk_mode=13;bulk_mode=45;bulk_mode=61"
+timeout 600 python tools/bulk_sweep.py --workload bulk_pe --steps 8 --configs "$CFG" > $O/sweep_pe.jsonl 2> $O/sweep_pe.err
+cut -c 1-160 $O/sweep_pe.jsonl; tail -2 $O/sweep_pe.err
+timeout 600 python tools/bulk_sweep.py --workload bulk_se --steps 8 --configs "$CFG" > $O/sweep_se.jsonl 2> $O/sweep_se.err
+cut -c 1-160 $O/sweep_se.jsonl; tail -2 $O/sweep_se.err
