@@ -1,0 +1,8 @@
+#!/bin/bash
+O=gpurun_out/r02al
+mkdir -p $O
+CFG="bulk_mode=13;bulk_mode=77;bulk_mode=93"
+timeout 600 python tools/bulk_sweep.py --workload bulk_pe --steps 8 --configs "$CFG" > $O/sweep_pe.jsonl 2> $O/sweep_pe.err
+cut -c 1-160 $O/sweep_pe.jsonl; tail -2 $O/sweep_pe.err
+timeout 600 python tools/bulk_sweep.py --workload bulk_se --steps 8 --configs "$CFG" > $O/sweep_se.jsonl 2> $O/sweep_se.err
+cut -c 1-160 $O/sweep_se.jsonl; tail -2 $O/sweep_se.err
