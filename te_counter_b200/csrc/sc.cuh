@@ -121,6 +121,11 @@ static int sc_cub_tmp(tec_ctx* ctx, size_t bytes) {
 struct MaxU32 { __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a > b ? a : b; } };
 struct MaxI32 { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
 struct SumU32 { __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a + b; } };
+// line j of the sorted order is the winner of its key group (te_count.py:552-555): head of a segment, first kept line of the key
+struct ScIsWinner {
+    const u32 *shead_pos, *khead_pos, *winner_at;
+    __device__ __forceinline__ bool operator()(u32 j) const { return shead_pos[j] == j && winner_at[khead_pos[j]] == j; }
+};
 
 #define SC_GRID(n) (int)std::max<int64_t>(1, std::min<int64_t>(((n) + 255) / 256, (int64_t)ctx->n_sm * 16)), 256, 0, ctx->stream
 #define SC_LOOP(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
@@ -737,17 +742,6 @@ __device__ void sc_count_fragment(const IndexView& iv, const ScTableView& tv, in
 }
 
 // winners compacted into a dense list, so that every lane of sc_part3_kernel has a fragment to count
-__global__ void sc_winflag_kernel(int64_t n, const u32* __restrict__ shead_pos, const u32* __restrict__ khead_pos,
-                                  const u32* __restrict__ winner_at, u32* __restrict__ f) {
-    SC_LOOP(j, n) f[j] = (shead_pos[j] == (u32)j && winner_at[khead_pos[j]] == (u32)j) ? 1u : 0u;
-}
-__global__ void sc_winlist_kernel(int64_t n, const u32* __restrict__ excl, const u32* __restrict__ total, u32* __restrict__ wlist) {
-    SC_LOOP(j, n) {
-        const u32 p = excl[j], nx = (j + 1 < n) ? excl[j + 1] : *total;
-        if (nx != p) wlist[p] = (u32)j;
-    }
-}
-
 // one thread per winning segment; all columns are in sorted (cell, umi, i) order.  The increments of
 // a warp's fragments are appended with one atomic per warp.
 __global__ void sc_part3_kernel(int64_t n, int64_t n_win, const u32* __restrict__ wlist, IndexView iv, ScTableView tv, int strand_mode,
@@ -1489,19 +1483,23 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
         TEC_CUDA(A.get(&d_np, 1));
         TEC_CUDA(A.get(&d_over, 1));
         // dense list of the winning lines
-        u32 *wflag = nullptr, *wlist = nullptr, *d_nwin = nullptr;
-        TEC_CUDA(A.get(&wflag, (size_t)N + 1));
+        u32 *wlist = nullptr, *d_nwin = nullptr;
+        TEC_CUDA(A.get(&wlist, (size_t)std::max<int64_t>(N, 1)));
         TEC_CUDA(A.get(&d_nwin, 1));
-        sc_winflag_kernel<<<SC_GRID(N)>>>(N, shead, khead, winner_at, wflag);
-        TEC_CUDA(cudaMemsetAsync(wflag + N, 0, 4, ctx->stream));
-        rc = sc_excl_sum(ctx, wflag, wflag, N + 1);
-        if (rc) return rc;
         u32 h_nwin = 0;
-        TEC_CUDA(cudaMemcpyAsync(&h_nwin, wflag + N, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        TEC_CUDA(cudaMemcpyAsync(d_nwin, wflag + N, 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        TEC_CUDA(cudaStreamSynchronize(ctx->stream));
-        TEC_CUDA(A.get(&wlist, (size_t)h_nwin));
-        sc_winlist_kernel<<<SC_GRID(N)>>>(N, wflag, d_nwin, wlist);
+        {
+            // one selection pass over the positions 0..N-1 (no flag array, prefix sum and list kernel)
+            ScIsWinner is_winner;
+            is_winner.shead_pos = shead; is_winner.khead_pos = khead; is_winner.winner_at = winner_at;
+            cub::CountingInputIterator<u32> positions(0u);
+            size_t tb = 0;
+            TEC_CUDA(cub::DeviceSelect::If(nullptr, tb, positions, wlist, d_nwin, (int)N, is_winner, ctx->stream));
+            rc = sc_cub_tmp(ctx, tb);
+            if (rc) return rc;
+            TEC_CUDA(cub::DeviceSelect::If(s->cub_tmp, tb, positions, wlist, d_nwin, (int)N, is_winner, ctx->stream));
+            TEC_CUDA(cudaMemcpyAsync(&h_nwin, d_nwin, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            TEC_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
         ctx->launches += 2;
         A.release(winner_at);
         u64 h_stats_before[TEC_SC_NSTATS];
@@ -1534,7 +1532,7 @@ extern "C" int tec_sc_finalize(tec_ctx* ctx, int64_t bundle_keys, int64_t maxcel
             cap_pairs = std::min<int64_t>(std::max<int64_t>((int64_t)h_npairs + 1024, cap_pairs * 2), (int64_t)0xFFFFFFF0);
         }
         // release what Part 3 no longer needs before sorting the pair list
-        A.release(wflag); A.release(wlist); A.release(minumi); A.release(present); A.release(bundle); A.release(shead); A.release(khead);
+        A.release(wlist); A.release(minumi); A.release(present); A.release(bundle); A.release(shead); A.release(khead);
         A.release(sumi); A.release(scell); A.release(perm); A.release(scs);
         // ---- triples: sort (ensg, cell) keys, run-length encode
         if (h_npairs) {
