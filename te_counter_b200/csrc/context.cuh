@@ -158,7 +158,7 @@ struct tec_ctx {
     int64_t ring_cap = 0;                 // entries
     u32* d_defer_list = nullptr;          // bulk2: per-warp segments of deferred unit indices
     u32* d_defer_count = nullptr;         // bulk2: entries per segment
-    int64_t defer_cap = 0, defer_warps = 0;
+    int64_t defer_cap = 0, defer_warps = 0, last_defer_n = 0;
     u32* d_part_count = nullptr;          // bulk2: entries bulk2_pair_kernel left per (segment, part)
     int64_t part_cap = 0, last_part_n = 0;
     std::vector<int32_t> ensg_of_slot;    // slot = rank of an ensg by number of feature rows
@@ -238,8 +238,8 @@ inline void tec_ctx::free_index() {
     cudaFree(d_ring); cudaFree(d_ring_u);
     d_ring = nullptr; d_ring_u = nullptr; ring_cap = 0;
     cudaFree(d_defer_list); cudaFree(d_defer_count); cudaFree(d_part_count);
-    d_defer_list = nullptr; d_defer_count = nullptr; defer_cap = 0; defer_warps = 0;
-    d_part_count = nullptr; part_cap = 0;
+    d_defer_list = nullptr; d_defer_count = nullptr; defer_cap = 0; defer_warps = 0; last_defer_n = 0;
+    d_part_count = nullptr; part_cap = 0; last_part_n = 0;
     slow_cap = 0;
     has_index = false;
     bulk_active = false;

@@ -386,6 +386,7 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
         ctx->slow_cap = cap;
     }
     TEC_CUDA(cudaMemsetAsync(ctx->d_slow_list, 0, 4, ctx->stream));
+    ctx->last_defer_n = n_warps;
 #define TEC_LAUNCH_FAST2(P, NT, AH, DP)                                                                                    \
     do {                                                                                                                   \
         auto kfn = (ctx->opt_bulk_mode & B2_MODE_SCAN) ? bulk2_fast_kernel<P, NT, AH, 2, DP>                               \
@@ -655,7 +656,7 @@ extern "C" int64_t tec_get_info(tec_ctx* ctx, const char* key) {
     if (k == "last_deferred_units") {      // units the last fast-kernel launch handed to the second pass
         if (!ctx->d_defer_count || !ctx->defer_warps) return 0;
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
-        std::vector<u32> h((size_t)ctx->defer_warps);
+        std::vector<u32> h((size_t)(ctx->last_defer_n > 0 ? ctx->last_defer_n : ctx->defer_warps));   // the segments the last launch used
         if (cudaMemcpy(h.data(), ctx->d_defer_count, h.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         int64_t n = 0;
         for (u32 x : h) n += x;
