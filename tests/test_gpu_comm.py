@@ -80,7 +80,7 @@ def test_sc_exchange_and_allgather_single_rank(engine, bundle_keys, maxcells, pa
 def test_two_ranks_over_nccl_match_the_oracle():
     import torch
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (the driver's scaling run and tools/gpu_round2_*.sh cover it)")
+        pytest.skip("needs two GPUs (the driver's scaling run and tools/gpu_passes/gpu_round2_n2.sh cover it)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29577", os.path.join(ROOT, "tools", "sc_dist_parity.py"), "--records-per-rank", "3000000",
            "--bundle-keys", "400000"]
