@@ -123,7 +123,8 @@ int tec_trim(tec_ctx* ctx);
 /* tuning knobs: "bulk_algo" (-1 auto, 0 exact search kernel, 1 round-1 cell-table kernel -- set before
  * tec_index_upload --, 2 two-pass kernels), "stab_shift" (log2 of the cell size, 8..11, or 0 = default: 10 for
  * bulk, 11 for the single-cell pair table; used by the next tec_index_upload), "bulk_mode" (bit 0 table sectors
- * evict_last in L2, bit 1 sector prefetch, bit 2 tally through the per-warp hit queue, bit 3 deep pipeline),
+ * evict_last in L2, bit 1 sector prefetch, bit 2 tally through the per-warp hit queue, bit 3 deep pipeline, bit 4
+ * queue filled behind a warp prefix sum, bit 5 768-thread CTAs, bit 6 queue drained once per tile; default 77),
  * "second_mode" (second bulk pass: the register set of a unit's distinct ensg, 0 stored by position, 1 shifted
  * in, 2 = 1 + the units that two sectors answer go through a straight-line kernel first), "second_parts" (warps
  * per segment of the deferred list), "ctas_per_sm",

@@ -151,6 +151,7 @@ struct B2Const {
 #define B2_MODE_PREFETCH 2u       // request the next tile's sectors into L2 one turn ahead
 #define B2_MODE_QUEUE 4u          // tally through the per-warp hit queue instead of one reduction per entry
 #define B2_MODE_DEEP 8u           // 512-thread CTAs with 128 registers per thread: three tiles in flight per warp
+#define B2_MODE_TILE_DRAIN 64u    // ballot queue drained once per tile instead of once per unit
 #define B2_MODE_768 32u           // with B2_MODE_DEEP: 768-thread CTAs (85 registers), two tiles in flight per warp
 #define B2_MODE_SCAN 16u          // hit queue filled once per tile (both units of a lane): one warp prefix sum instead of ten ballots
 
@@ -367,7 +368,7 @@ __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const Sector (&s)[
             b2_q_push(a1 & 0x8000u, s[j].w[7], k, t);
             b2_q_push(a1 & 0x80000000u, s[j].w[7] >> 16, k, t);
             b2_q_push(a2 != 0, s[j].w[5] >> 16, k, t);
-            b2_q_drain<ALLHOT>(k, t, counts, (int)(threadIdx.x & 31), false);
+            if (QUEUE == 1) b2_q_drain<ALLHOT>(k, t, counts, (int)(threadIdx.x & 31), false);    // QUEUE 3: once per tile, below
         } else {
             b2_bump<ALLHOT, false>(a0 & 0x8000u, b2_lo16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
             b2_bump<ALLHOT, false>(a0 & 0x80000000u, b2_hi16(s[j].w[6]), k.hot_addr, k.scratch_addr, k.n_hot, counts, k.one);
@@ -382,6 +383,7 @@ __device__ __forceinline__ void b2_phase_b(const B2Stage& st, const Sector (&s)[
         t.wp += __popc(dm);
     }
     if (QUEUE == 2) b2_q_push_tile<ALLHOT>(y, s, k, t, counts, (int)(threadIdx.x & 31));
+    if (QUEUE == 3) b2_q_drain<ALLHOT>(k, t, counts, (int)(threadIdx.x & 31), false);           // at most 31 + 10 x 32 entries < B2_QCAP
 }
 
 template <bool PAIRED, int NT, bool ALLHOT, int QUEUE, int DEPTH>
@@ -510,6 +512,7 @@ bulk2_fast_kernel(Stab2View sv, int n_chrom, u32 n_units, int qual,
     }
     if (QUEUE == 2) b2_q_drain_linear<ALLHOT>(k, t, counts, lane, true);
     else if (QUEUE) b2_q_drain<ALLHOT>(k, t, counts, lane, true);
+    static_assert(B2_QCAP >= 31u + 10u * 32u, "a tile's hits must fit the ring between two drains");
     if (lane == 0) defer_count[gw] = (u32)(t.wp - my_list);
     u64 v[4] = {t.n_assigned, t.n_lowq, t.n_badchrom, t.n_qcfail};
 #pragma unroll

@@ -165,8 +165,9 @@ struct tec_ctx {
     // options (tec_set_option)
     int opt_bulk_algo = -1;               // -1 auto, 0 exact search kernel, 1 cell-table kernel with in-kernel rings (round 1), 2 two-pass kernels (bulk2.cuh)
     int opt_stab_shift = 0;               // log2 of the cell size; 0 = TEC_BULK_STAB_SHIFT / TEC_SC_STAB_SHIFT
-    int opt_bulk_mode = 13;               // fast bulk kernel: bit 0 table sectors evict_last in L2, bit 1 prefetch the next tile's sectors,
-                                          // bit 2 tally through the per-warp hit queue, bit 3 512-thread CTAs with three tiles in flight per warp
+    int opt_bulk_mode = 77;               // fast bulk kernel: bit 0 table sectors evict_last in L2, bit 1 prefetch the next tile's sectors,
+                                          // bit 2 tally through the per-warp hit queue, bit 3 512-thread CTAs with three tiles in flight per warp,
+                                          // bit 4 queue filled behind a warp prefix sum, bit 5 768-thread CTAs, bit 6 queue drained once per tile
     int opt_bulk_strand = 0;              // extension (not in the reference): strand-aware bulk counting, exact kernel only
     int opt_second_parts = 4;             // warps of the second bulk pass (and of bulk2_pair_kernel) per segment of the deferred list
     int opt_second_mode = 2;              // second bulk pass: register set of distinct ensg, 0 stored by position, 1 shifted in; 2: units that

@@ -390,7 +390,8 @@ static int bulk2_launch_one(tec_ctx* ctx, int64_t n_units, const int32_t* start,
 #define TEC_LAUNCH_FAST2(P, NT, AH, DP)                                                                                    \
     do {                                                                                                                   \
         auto kfn = (ctx->opt_bulk_mode & B2_MODE_SCAN) ? bulk2_fast_kernel<P, NT, AH, 2, DP>                               \
-                   : (ctx->opt_bulk_mode & B2_MODE_QUEUE) ? bulk2_fast_kernel<P, NT, AH, 1, DP> : bulk2_fast_kernel<P, NT, AH, 0, DP>; \
+                   : (ctx->opt_bulk_mode & B2_MODE_QUEUE) ? ((ctx->opt_bulk_mode & B2_MODE_TILE_DRAIN) ? bulk2_fast_kernel<P, NT, AH, 3, DP> : bulk2_fast_kernel<P, NT, AH, 1, DP>) \
+                   : bulk2_fast_kernel<P, NT, AH, 0, DP>; \
         TEC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                        \
         kfn<<<blocks, NT, dyn, ctx->stream>>>(sv, ctx->idx.n_chrom, (u32)n_units, ctx->qual, start, end, chrom, mapq, flag, \
                                               counts, stats, (uint4*)ctx->d_defer_list, ctx->d_defer_count, (u32)seg_cap, n_hot, \
@@ -633,7 +634,7 @@ extern "C" int tec_set_option(tec_ctx* ctx, const char* key, int64_t value) {
     else if (k == "sc_sort_chunk") { if (value < 1 || value > 64) TEC_FAIL(TEC_ERR_ARG, "sc_sort_chunk: tiles per chunk of csrc/radix.cuh, 1..64"); g_rdx_chunk_tiles = (int)value; }
     else if (k == "second_parts") { if (value < 1 || value > 16) TEC_FAIL(TEC_ERR_ARG, "second_parts: 1..16"); ctx->opt_second_parts = (int)value; }
     else if (k == "second_mode") { if (value < 0 || value > 2) TEC_FAIL(TEC_ERR_ARG, "second_mode: 0 distinct ensg stored by position, 1 shifted in, 2 two-sector kernel first"); ctx->opt_second_mode = (int)value; }
-    else if (k == "bulk_mode") { if (value < 0 || value > 63) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline, bit 4 hit queue filled once per tile, bit 5 768-thread CTAs with two tiles in flight"); ctx->opt_bulk_mode = (int)value; }
+    else if (k == "bulk_mode") { if (value < 0 || value > 127) TEC_FAIL(TEC_ERR_ARG, "bulk_mode: bit 0 table evict_last, bit 1 sector prefetch, bit 2 tally through the hit queue, bit 3 deep pipeline, bit 4 hit queue filled once per tile, bit 5 768-thread CTAs with two tiles in flight, bit 6 ballot queue drained once per tile"); ctx->opt_bulk_mode = (int)value; }
     else if (k == "ctas_per_sm") { if (value < 1 || value > 8) TEC_FAIL(TEC_ERR_ARG, "ctas_per_sm: 1..8"); ctx->opt_ctas_per_sm = (int)value; }
     else if (k == "bam_lanes") { if (value < 1 || value > 32) TEC_FAIL(TEC_ERR_ARG, "bam_lanes: 1..32"); ctx->opt_bam_lanes = (int)value; }
     else if (k == "bam_window_blocks") { if (value < 1 || value > (1 << 20)) TEC_FAIL(TEC_ERR_ARG, "bam_window_blocks: 1..1048576"); ctx->opt_bam_window_blocks = (int)value; }

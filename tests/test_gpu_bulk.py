@@ -87,7 +87,7 @@ def test_bulk_counter_placement(engine, paired, all_hot):
 
 
 @pytest.mark.parametrize("paired", [False, True])
-@pytest.mark.parametrize("bulk_mode,second_mode", [(0, 0), (5, 1), (13, 0), (13, 1), (13, 2), (29, 2), (21, 1), (31, 0), (4, 2), (45, 2), (61, 2)])
+@pytest.mark.parametrize("bulk_mode,second_mode", [(0, 0), (5, 1), (13, 0), (13, 1), (13, 2), (29, 2), (21, 1), (31, 0), (4, 2), (45, 2), (61, 2), (77, 2), (69, 2)])
 def test_bulk_kernel_variants(engine, paired, bulk_mode, second_mode):
     """Every variant of the two-pass kernels (tally by reduction / ballot queue / scan queue, shallow / deep pipeline,
     both register sets of the second pass) against the oracle: dense pile-ups, gapped reads, EDGE cells."""
@@ -101,7 +101,7 @@ def test_bulk_kernel_variants(engine, paired, bulk_mode, second_mode):
         engine.bulk_push(len(r["start"]), r["start"], r["end"], r["chrom"], r["mapq"], r["flag"])
         counts, st = engine.bulk_finish()
     finally:
-        engine.set_option("bulk_mode", 13)
+        engine.set_option("bulk_mode", 77)
         engine.set_option("second_mode", 2)
     oc, os_ = te_oracle.bulk_count(H.oracle_index(idx), paired, 20, r["start"].tolist(), r["end"].tolist(),
                                    r["chrom"].tolist(), r["mapq"].tolist(), r["flag"].tolist())
