@@ -22,9 +22,9 @@ for r in rows[1:]:
     v = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
     if r[mi].startswith("gpu__time"):
         d["ms"] += v
-    elif "read" in r[mi]:
+    elif r[mi].startswith("dram__bytes_read"):
         d["rd"] += v
-    else:
+    elif r[mi].startswith("dram__bytes_write"):
         d["wr"] += v
 tot = sum(d["ms"] for d in per.values())
 print("%d launches, %.1f ms under ncu\n" % (sum(len(d["n"]) for d in per.values()), tot))
