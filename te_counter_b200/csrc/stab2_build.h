@@ -257,3 +257,68 @@ inline int stab2_unit(const StabTable2& t, int c, int64_t xa, int64_t xb, std::v
     if (exact || (int)out.size() > max_distinct) return 2;
     return 1;
 }
+
+// Scalar statement of bulk2_pair_kernel (bulk2.cuh) for a unit the fast kernel deferred: the two sectors it reads, its
+// completeness rules, the twin rule by flag bits and the 5 + 5 slot comparison.  Returns false when the kernel leaves the
+// unit to bulk2_second_kernel; else out = the slots it counts (sorted), each once.
+inline bool stab2_pair_unit(const StabTable2& t, int c, int64_t xa, int64_t xb, std::vector<uint32_t>& out) {
+    out.clear();
+    const int64_t ncc = t.cell_base[(size_t)c + 1] - t.cell_base[(size_t)c];
+    const int64_t S = (int64_t)1 << t.shift;
+    const int64_t mn = std::min(xa, xb), k = mn >> t.shift, base = k << t.shift;
+    const int64_t rmax = std::max(xa, xb) - base;
+    int64_t secA, secB;
+    uint32_t raA, rbA, raB, rbB;
+    bool two_chains;
+    if (k >= 0 && k < ncc && rmax < S + t.ext) {               // one chain, both points: primary + first overflow sector
+        secA = t.cell_base[(size_t)c] + k;
+        secB = (int64_t)t.ovf_first[(size_t)secA];
+        raA = raB = (uint32_t)(xa - base); rbA = rbB = (uint32_t)(xb - base);
+        two_chains = false;
+    } else {
+        Stab2Probe pr[2];
+        int np = 0;
+        if (xa >= 0 && (xa >> t.shift) < ncc) pr[np++] = {t.cell_base[(size_t)c] + (xa >> t.shift), (uint32_t)(xa & (S - 1)), S2_R_NONE};
+        if (xb >= 0 && (xb >> t.shift) < ncc) pr[np++] = {t.cell_base[(size_t)c] + (xb >> t.shift), S2_R_NONE, (uint32_t)(xb & (S - 1))};
+        if (np == 0) return true;                               // no probe: nothing to count
+        if (np == 1) return false;                              // left to the second pass
+        secA = pr[0].prim; raA = pr[0].ra; rbA = pr[0].rb;
+        secB = pr[1].prim; raB = pr[1].ra; rbB = pr[1].rb;
+        two_chains = true;
+    }
+    const uint32_t* wA = &t.sectors[(size_t)secA * 8];
+    const uint32_t* wB = &t.sectors[(size_t)secB * 8];
+    const uint32_t hA = wA[2] >> 16, hB = wB[2] >> 16;
+    const int rmA = std::max(raA == S2_R_NONE ? -1 : (int)raA, rbA == S2_R_NONE ? -1 : (int)rbA);
+    const int rmB = std::max(raB == S2_R_NONE ? -1 : (int)raB, rbB == S2_R_NONE ? -1 : (int)rbB);
+    const bool onA = (hA & S2_H_MORE) && rmA >= (int)(hA & S2_THR_MASK);
+    const bool onB = (hB & S2_H_MORE) && rmB >= (int)(hB & S2_THR_MASK);
+    bool useB = true;
+    if (hA & S2_H_EDGE) return false;
+    if (two_chains) { if (onA || onB || (hB & S2_H_EDGE)) return false; }
+    else { useB = onA; if (onA && onB) return false; }
+    bool hitA[5], hitB[5];
+    for (int i = 0; i < 5; ++i) {
+        hitA[i] = stab2_entry_hit(wA, i, raA) || stab2_entry_hit(wA, i, rbA);
+        hitB[i] = useB && (stab2_entry_hit(wB, i, raB) || stab2_entry_hit(wB, i, rbB));
+    }
+    if ((hA & S2_H_TW01) && hitA[0]) hitA[1] = false;
+    if ((hA & S2_H_TW23) && hitA[2]) hitA[3] = false;
+    if ((hB & S2_H_TW01) && hitB[0]) hitB[1] = false;
+    if ((hB & S2_H_TW23) && hitB[2]) hitB[3] = false;
+    uint32_t a[5], b[5];
+    for (int i = 0; i < 5; ++i) {
+        a[i] = hitA[i] ? stab2_entry_slot(wA, i) : 0x10000u + (uint32_t)i;
+        b[i] = hitB[i] ? stab2_entry_slot(wB, i) : 0x20000u + (uint32_t)i;
+    }
+    for (int i = 0; i < 5; ++i) if (hitA[i]) out.push_back(a[i]);
+    for (int j = 0; j < 5; ++j) {
+        if (!hitB[j]) continue;
+        bool dup = false;
+        for (int i = 0; i < 5; ++i) dup |= b[j] == a[i];
+        for (int i = 0; i < j; ++i) dup |= b[j] == b[i];
+        if (!dup) out.push_back(b[j]);
+    }
+    std::sort(out.begin(), out.end());
+    return true;
+}

@@ -18,7 +18,8 @@ def test_cell_table_against_brute_force(tmp_path):
 
 def test_cell_table_layout2_against_brute_force(tmp_path):
     """Layout 2 (stab2_build.h) behind the default two-pass bulk kernels: thresholds, twin pairs, EDGE cells,
-    overflow chains -- every unit of random indices against brute force through the scalar reader."""
+    overflow chains -- every unit of random indices against brute force through the scalar reader; every deferred unit
+    also through the scalar statement of the two-sector kernel (bulk2_pair_kernel)."""
     exe = str(tmp_path / "stab2_selftest")
     subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tools", "stab2_selftest.cpp")], check=True)
     r = subprocess.run([exe, "9"], capture_output=True, text=True)

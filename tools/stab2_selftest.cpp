@@ -2,7 +2,9 @@
 // exhaustive point pairs checked against brute force -- the set of distinct ensg stabbed by x1 or x2 -- through
 // stab2_unit(), the scalar statement of what the two kernels of bulk2.cuh do (fast sector test with in-place
 // twin rule, second pass over sector chains).  Units routed to the exact search must be exactly those that
-// touch an EDGE cell or hit too many ensg.  Exit code 0 = all good.  Run by tests/test_cell_table_cpu.py.
+// touch an EDGE cell or hit too many ensg.  Every deferred unit also goes through stab2_pair_unit(), the scalar
+// statement of bulk2_pair_kernel (two sectors, completeness rules, 5 + 5 slot comparison): what it answers must be the
+// brute-force set, and it must leave EDGE units alone.  Exit code 0 = all good.  Run by tests/test_cell_table_cpu.py.
 #include "../te_counter_b200/csrc/stab2_build.h"
 #include <cstdio>
 #include <cstdlib>
@@ -20,7 +22,7 @@ static std::vector<uint32_t> brute2(const std::vector<int64_t>& off, const std::
 int main(int argc, char** argv) {
     const int rounds = argc > 1 ? atoi(argv[1]) : 6;
     std::mt19937_64 rng(777);
-    long checked = 0, fast = 0, second = 0, exact = 0, twin_sectors = 0, forced = 0;
+    long checked = 0, fast = 0, second = 0, exact = 0, twin_sectors = 0, forced = 0, pair_done = 0, pair_left = 0;
     for (int round = 0; round < rounds; ++round) {
         const int shift = 8 + round % 4;                       // 8..11
         const int n_chrom = 1 + round % 3;
@@ -62,6 +64,21 @@ int main(int argc, char** argv) {
                 const int how = stab2_unit(t, c, xa, xb, got, 8);
                 const auto want = brute2(off, L, R, slot, c, xa, xb);
                 ++checked;
+                if (how != 0) {
+                    // the two-sector kernel goes first on every deferred unit: what it answers must be the brute-force set
+                    // (each ensg once), and it must leave every unit of an EDGE cell to the passes behind it
+                    std::vector<uint32_t> pg;
+                    if (stab2_pair_unit(t, c, xa, xb, pg)) {
+                        ++pair_done;
+                        if (pg != want) {
+                            printf("round %d: two-sector kernel mismatch chrom %d xa %ld xb %ld shift %d: want %zu got %zu\n", round, c, (long)xa, (long)xb, shift, want.size(), pg.size());
+                            return false;
+                        }
+                        if (how == 2 && want.size() <= 8) { printf("round %d: two-sector kernel answered an EDGE unit c %d xa %ld xb %ld\n", round, c, (long)xa, (long)xb); return false; }
+                    } else {
+                        ++pair_left;
+                    }
+                }
                 fast += how == 0; second += how == 1; exact += how == 2;
                 if (how == 2) {
                     // legitimate only for EDGE cells or large sets
@@ -107,7 +124,7 @@ int main(int argc, char** argv) {
             }
         }
     }
-    printf("cell table 2 self-test ok: %ld units (%ld fast, %ld second pass, %ld exact), %ld twin sectors, %ld forced\n",
-           checked, fast, second, exact, twin_sectors, forced);
+    printf("cell table 2 self-test ok: %ld units (%ld fast, %ld second pass, %ld exact), %ld twin sectors, %ld forced; two-sector kernel: %ld answered, %ld left\n",
+           checked, fast, second, exact, twin_sectors, forced, pair_done, pair_left);
     return 0;
 }
