@@ -530,10 +530,14 @@ def bulk_leg(C, wl, headline):
     achieved = n_rec * bpr / (kern_ms / 1e3) / 1e9
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "r02_bulk_ncu_traffic.json")
-    if paired and os.path.exists(tp):
+    if os.path.exists(tp):
         t = json.load(open(tp))
-        traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["records_per_launch"] * n_rec
-        traffic_src = t.get("source")
+        if paired:
+            traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["records_per_launch"] * n_rec
+            traffic_src = t.get("source")
+        elif "bulk_se" in t:
+            traffic = (t["bulk_se"]["dram_bytes_read"] + t["bulk_se"]["dram_bytes_write"]) / t["bulk_se"]["records_per_step"] * n_rec
+            traffic_src = t["bulk_se"].get("source")
     leg = {"value": value, "unit": "records/s", "ms_per_step": ms_step, "steps": K, "warmup": W,
            "config": workload_config(args, wl, n_rec, world), "gpu_launches": int(launches), "dtype": "int32",
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": C.peak, "unit": "GB/s",
