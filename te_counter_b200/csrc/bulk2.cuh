@@ -15,7 +15,9 @@
 //                        Every other unit
 //                        that passed the filter is appended to the warp's own segment of the deferred list
 //                        (no atomics: the list is partitioned by warp).
-//   bulk2_second_kernel  the deferred units (about 6 % of a paired-end workload): one or two sector chains,
+//   bulk2_pair_kernel    the deferred units (5 % of the pairs of a paired-end workload, 13 % of spliced single-end
+//                        reads) that two sectors answer, straight-line; leaves the rest in place for
+//   bulk2_second_kernel  one or two sector chains,
 //                        a register set of distinct ensg, hot counters in shared memory.  Units in EDGE cells
 //                        (the reference's two-bucket candidate rule can bite there) or with more distinct ensg
 //                        than the register set go on to bulk_slow_kernel's exact search.
