@@ -153,9 +153,9 @@ struct B2Const {
 #define B2_MODE_PREFETCH 2u       // request the next tile's sectors into L2 one turn ahead
 #define B2_MODE_QUEUE 4u          // tally through the per-warp hit queue instead of one reduction per entry
 #define B2_MODE_DEEP 8u           // 512-thread CTAs with 128 registers per thread: three tiles in flight per warp
-#define B2_MODE_TILE_DRAIN 64u    // ballot queue drained once per tile instead of once per unit
-#define B2_MODE_768 32u           // with B2_MODE_DEEP: 768-thread CTAs (85 registers), two tiles in flight per warp
 #define B2_MODE_SCAN 16u          // hit queue filled once per tile (both units of a lane): one warp prefix sum instead of ten ballots
+#define B2_MODE_768 32u           // with B2_MODE_DEEP: 768-thread CTAs (85 registers), two tiles in flight per warp
+#define B2_MODE_TILE_DRAIN 64u    // ballot queue drained once per tile instead of once per unit (default: 1 + 4 + 8 + 64 = 77)
 
 __device__ __forceinline__ Sector ld_sector_pol(const u32* sectors, u32 idx, u64 pol) {
     Sector r;
